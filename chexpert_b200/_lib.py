@@ -1,0 +1,76 @@
+"""ctypes binding of libaaconv_b200.so (C ABI declared in include/aaconv_b200.h).
+
+There is no fallback: if the shared object is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libaaconv_b200.so')
+
+FP32, BF16 = 0, 1
+PRECISIONS = {'fp32': FP32, 'bf16': BF16}
+
+
+class Dims(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ('B', 'Cin', 'Hin', 'Win', 'Cout', 'H', 'W', 'ksize', 'stride', 'pad', 'dil', 'dk', 'dv', 'nh',
+                 'relative')]
+
+
+class Params(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ('conv_w', 'qkv_w', 'out_w', 'key_rel_h', 'key_rel_w')]
+
+
+class ParamGrads(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ('conv_w', 'qkv_w', 'out_w', 'key_rel_h', 'key_rel_w')]
+
+
+# every symbol the header declares: name -> (restype, argtypes)
+_P = ctypes.c_void_p
+_DP = ctypes.POINTER(Dims)
+SYMBOLS = {
+    'aaconv_abi_version': (ctypes.c_int, []),
+    'aaconv_last_error': (ctypes.c_char_p, []),
+    'aaconv_validate': (ctypes.c_int, [_DP, ctypes.c_int]),
+    'aaconv_saved_bytes': (ctypes.c_size_t, [_DP, ctypes.c_int]),
+    'aaconv_scratch_bytes': (ctypes.c_size_t, [_DP, ctypes.c_int]),
+    'aaconv_saved_offset': (ctypes.c_int64, [_DP, ctypes.c_int, ctypes.c_char_p]),
+    'aaconv_forward': (ctypes.c_int, [_DP, ctypes.c_int, _P, ctypes.POINTER(Params), _P, _P, _P, _P, _P]),
+    'aaconv_backward': (ctypes.c_int, [_DP, ctypes.c_int, _P, ctypes.POINTER(Params), _P, _P, _P, _P,
+                                       ctypes.POINTER(ParamGrads), _P]),
+    'aaconv_bce_forward_backward': (ctypes.c_int, [_P, _P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int,
+                                                   _P, _P, _P, _P, _P]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load():
+    """Load (once) and return the CDLL; raises RuntimeError if the extension was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f'{LIB_PATH} is missing: build it with `python chexpert_b200/csrc/build.py` '
+                    '(or __graft_entry__.build()). chexpert_b200 has no CPU / eager fallback.')
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SYMBOLS.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            if lib.aaconv_abi_version() != 1:
+                raise RuntimeError('libaaconv_b200.so ABI version mismatch')
+            _lib = lib
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = load().aaconv_last_error().decode(errors='replace')
+        raise RuntimeError(f'{what} failed (code {code}): {msg}')

@@ -1,0 +1,79 @@
+// extern "C" surface of libaaconv_b200.so (see include/aaconv_b200.h).
+#include "fp32_path.cuh"
+#include "bf16_path.cuh"
+
+namespace aaconv {
+int bce_launch(const float* z, const float* targets, int ld, const int32_t* cols, int B, int C, float* el,
+               float* loss, float* dz, const float* grad_scale, cudaStream_t st);
+
+static int validate(const aaconv_dims* dd, int precision) {
+  if (!dd) return fail(AACONV_E_ARG, "dims is NULL");
+  const aaconv_dims& d = *dd;
+  if (precision != AACONV_FP32 && precision != AACONV_BF16) return fail(AACONV_E_ARG, "unknown precision %d", precision);
+  if (d.B <= 0 || d.Cin <= 0 || d.Hin <= 0 || d.Win <= 0 || d.Cout <= 0 || d.nh <= 0 || d.dk <= 0 || d.dv <= 0)
+    return fail(AACONV_E_ARG, "non-positive dimension");
+  if (d.dk % d.nh) return fail(AACONV_E_ARG, "nh must divide dk");       // attn_aug_conv.py:27
+  if (d.dv % d.nh) return fail(AACONV_E_ARG, "nh must divide dv");       // attn_aug_conv.py:28
+  if (d.stride <= 0 || d.ksize <= 0 || d.dil <= 0 || d.pad < 0) return fail(AACONV_E_ARG, "bad conv geometry");
+  if (d.ksize > 8) return fail(AACONV_E_UNSUPPORTED, "kernel_size > 8");
+  const int H = (d.Hin - 1) / d.stride + 1, W = (d.Win - 1) / d.stride + 1;   // 1x1 strided projection
+  if (H != d.H || W != d.W)
+    return fail(AACONV_E_ARG, "input_dims (%d,%d) do not match the strided map (%d,%d)", d.H, d.W, H, W);
+  if (d.Cout > d.dv) {
+    const int Hc = (d.Hin + 2 * d.pad - d.dil * (d.ksize - 1) - 1) / d.stride + 1;
+    const int Wc = (d.Win + 2 * d.pad - d.dil * (d.ksize - 1) - 1) / d.stride + 1;
+    if (Hc != H || Wc != W)
+      return fail(AACONV_E_ARG, "conv branch map (%d,%d) != attention map (%d,%d): cannot concatenate", Hc, Wc, H, W);
+  }
+  return 0;
+}
+}  // namespace aaconv
+
+using namespace aaconv;
+
+extern "C" {
+
+int aaconv_abi_version(void) { return AACONV_ABI_VERSION; }
+const char* aaconv_last_error(void) { return last_error_ref().c_str(); }
+int aaconv_validate(const aaconv_dims* d, int precision) { return validate(d, precision); }
+
+size_t aaconv_saved_bytes(const aaconv_dims* d, int precision) {
+  if (validate(d, precision)) return 0;
+  return precision == AACONV_FP32 ? f32_saved_bytes(Dims(*d)) : bf16_saved_bytes(Dims(*d));
+}
+size_t aaconv_scratch_bytes(const aaconv_dims* d, int precision) {
+  if (validate(d, precision)) return 0;
+  return precision == AACONV_FP32 ? f32_scratch_bytes(Dims(*d)) : bf16_scratch_bytes(Dims(*d));
+}
+int64_t aaconv_saved_offset(const aaconv_dims* d, int precision, const char* name) {
+  if (validate(d, precision) || !name) return -1;
+  return precision == AACONV_FP32 ? f32_saved_offset(Dims(*d), name) : bf16_saved_offset(Dims(*d), name);
+}
+
+int aaconv_forward(const aaconv_dims* d, int precision, const float* x, const aaconv_params* p, float* y,
+                   float* weights, void* saved, void* scratch, void* stream) {
+  AACONV_TRY(validate(d, precision));
+  if (!x || !p || !y || !saved || !scratch) return fail(AACONV_E_ARG, "NULL buffer");
+  if (!p->qkv_w || !p->out_w || (d->Cout > d->dv && !p->conv_w) || (d->relative && (!p->key_rel_h || !p->key_rel_w)))
+    return fail(AACONV_E_ARG, "NULL parameter");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return precision == AACONV_FP32 ? f32_forward(Dims(*d), x, p, y, weights, saved, scratch, st)
+                                  : bf16_forward(Dims(*d), x, p, y, weights, saved, scratch, st);
+}
+
+int aaconv_backward(const aaconv_dims* d, int precision, const float* x, const aaconv_params* p, const float* dy,
+                    const void* saved, void* scratch, float* dx, const aaconv_param_grads* g, void* stream) {
+  AACONV_TRY(validate(d, precision));
+  if (!x || !p || !dy || !saved || !scratch || !g) return fail(AACONV_E_ARG, "NULL buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return precision == AACONV_FP32 ? f32_backward(Dims(*d), x, p, dy, saved, scratch, dx, g, st)
+                                  : bf16_backward(Dims(*d), x, p, dy, saved, scratch, dx, g, st);
+}
+
+int aaconv_bce_forward_backward(const float* z, const float* targets, int ld, const int32_t* cols, int B, int C,
+                                float* element_loss, float* loss, float* dz, const float* grad_scale, void* stream) {
+  if (!z || !targets || B <= 0 || C <= 0 || ld < (cols ? 1 : C)) return fail(AACONV_E_ARG, "bad BCE arguments");
+  return bce_launch(z, targets, ld, cols, B, C, element_loss, loss, dz, grad_scale, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

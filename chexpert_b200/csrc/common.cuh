@@ -1,0 +1,77 @@
+// Shared host/device helpers for libaaconv_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <string>
+
+#include "../../include/aaconv_b200.h"
+
+namespace aaconv {
+
+// ---- error plumbing (thread-local text, int codes across the ABI) ------------------------------
+std::string& last_error_ref();
+int fail(int code, const char* fmt, ...);
+
+#define AACONV_CUDA_OK(expr)                                                                       \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return ::aaconv::fail(AACONV_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,          \
+                            cudaGetErrorString(e__));                                              \
+  } while (0)
+
+#define AACONV_LAUNCH_OK(name)                                                                     \
+  do {                                                                                             \
+    cudaError_t e__ = cudaGetLastError();                                                          \
+    if (e__ != cudaSuccess)                                                                        \
+      return ::aaconv::fail(AACONV_E_CUDA, "%s:%d launch %s -> %s", __FILE__, __LINE__, name,     \
+                            cudaGetErrorString(e__));                                              \
+  } while (0)
+
+#define AACONV_TRY(expr)                                                                           \
+  do {                                                                                             \
+    int r__ = (expr);                                                                              \
+    if (r__ != 0) return r__;                                                                      \
+  } while (0)
+
+// ---- derived dimensions ------------------------------------------------------------------------
+struct Dims {
+  int B, Cin, Hin, Win, Cout, H, W, ks, stride, pad, dil, dk, dv, nh, relative;
+  int dkh, dvh, L, Cc /*conv-branch channels*/, Nqkv, BN /*B*nh*/, RW, RH;
+  float qscale;
+  __host__ explicit Dims(const aaconv_dims& d)
+      : B(d.B), Cin(d.Cin), Hin(d.Hin), Win(d.Win), Cout(d.Cout), H(d.H), W(d.W), ks(d.ksize),
+        stride(d.stride), pad(d.pad), dil(d.dil), dk(d.dk), dv(d.dv), nh(d.nh), relative(d.relative) {
+    dkh = nh > 0 ? dk / nh : 0;
+    dvh = nh > 0 ? dv / nh : 0;
+    L = H * W;
+    Cc = Cout > dv ? Cout - dv : 0;
+    Nqkv = 2 * dk + dv;
+    BN = B * nh;
+    RW = 2 * W - 1;
+    RH = 2 * H - 1;
+    qscale = dkh > 0 ? 1.0f / sqrtf((float)dkh) : 0.f;
+  }
+};
+
+inline size_t align256(size_t n) { return (n + 255) & ~size_t(255); }
+
+// Bump allocator over a caller-owned buffer.
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base(static_cast<char*>(b)) {}
+  template <class T>
+  T* take(size_t count) {
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += align256(count * sizeof(T));
+    return p;
+  }
+};
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace aaconv

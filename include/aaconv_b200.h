@@ -1,0 +1,109 @@
+/*
+ * aaconv_b200.h -- C ABI of the B200-native AAConv2d hot path (libaaconv_b200.so).
+ *
+ * The reference (kamenbliznashki/chexpert) has no FFI layer: the boundary it exposes for this path is
+ * the nn.Module contract of AAConv2d (models/attn_aug_conv.py:19-100) and the loss callable
+ * (chexpert.py:530,160).  This header is what a Python/ctypes (or any FFI) host binds instead of the
+ * ATen ops those lines call.  Every entry point
+ *   - takes plain device pointers, ints and a CUDA stream handle (void* == cudaStream_t); no torch types;
+ *   - returns 0 on success, a negative AACONV_E_* code otherwise (aaconv_last_error() has the text);
+ *   - never allocates persistent device memory: outputs, the saved-for-backward block and scratch are
+ *     caller-owned buffers sized by the *_bytes() queries;
+ *   - is asynchronous on `stream` and holds no global mutable state (safe from the autograd worker thread).
+ *
+ * Tensor layouts at the boundary are the reference's: x (B,Cin,Hin,Win) and y (B,Cout,H,W) contiguous
+ * NCHW, parameters in their state_dict shapes (attn_aug_conv.py:34-41).  fp32 everywhere at the boundary;
+ * `precision` selects the arithmetic inside (AACONV_FP32: fp32 FFMA path, rtol 1e-4 parity;
+ * AACONV_BF16: bf16 tcgen05 tensor-core path with fp32 accumulation and fp32 softmax statistics).
+ */
+#ifndef AACONV_B200_H_
+#define AACONV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AACONV_ABI_VERSION 1
+
+enum { AACONV_FP32 = 0, AACONV_BF16 = 1 };
+
+enum {
+  AACONV_OK = 0,
+  AACONV_E_ARG = -1,       /* bad dimension / null pointer / unsupported configuration */
+  AACONV_E_CUDA = -2,      /* a CUDA runtime call or launch failed */
+  AACONV_E_UNSUPPORTED = -3
+};
+
+/* Static description of one AAConv2d call.  Mirrors the constructor arguments of
+ * attn_aug_conv.py:20 plus the input extent; H,W are the post-stride map == input_dims when relative. */
+typedef struct aaconv_dims {
+  int32_t B, Cin, Hin, Win;
+  int32_t Cout;            /* out_channels of the module (conv branch gets Cout-dv, attention dv) */
+  int32_t H, W;            /* output map: floor((Hin-1)/stride)+1, ... (attn_aug_conv.py:35,70)      */
+  int32_t ksize, stride, pad, dil;
+  int32_t dk, dv, nh;
+  int32_t relative;        /* attn_aug_conv.py:76 */
+} aaconv_dims;
+
+/* Parameter block, state_dict order of attn_aug_conv.py:34-41.  conv_w may be NULL iff Cout <= dv
+ * (attn_aug_conv.py:34 -> self.conv is None); key_rel_* are ignored when !relative. */
+typedef struct aaconv_params {
+  const float* conv_w;     /* (Cout-dv, Cin, k, k) */
+  const float* qkv_w;      /* (2dk+dv, Cin, 1, 1)  */
+  const float* out_w;      /* (dv, dv, 1, 1)       */
+  const float* key_rel_h;  /* (dk/nh, 2H-1)        */
+  const float* key_rel_w;  /* (dk/nh, 2W-1)        */
+} aaconv_params;
+
+typedef struct aaconv_param_grads {   /* any member may be NULL: that gradient is skipped */
+  float* conv_w;
+  float* qkv_w;
+  float* out_w;
+  float* key_rel_h;
+  float* key_rel_w;
+} aaconv_param_grads;
+
+int aaconv_abi_version(void);
+const char* aaconv_last_error(void);          /* thread-local text of the last failing call */
+int aaconv_validate(const aaconv_dims* d, int precision);
+
+/* Sizes of the caller-owned work buffers (bytes; multiples of 256). */
+size_t aaconv_saved_bytes(const aaconv_dims* d, int precision);     /* forward -> backward state       */
+size_t aaconv_scratch_bytes(const aaconv_dims* d, int precision);   /* transient, either direction     */
+
+/* Byte offsets of the named blocks inside the saved buffer (for tests and the visualise path).
+ * names: "q","k","v","o","lse" (fp32 path: q,k (B,nh,L,dkh) with q pre-scaled; v,o (B,nh,L,dvh);
+ * lse (B,nh,L)).  Returns -1 for an unknown name. */
+int64_t aaconv_saved_offset(const aaconv_dims* d, int precision, const char* name);
+
+/* Forward: replaces AAConv2d.forward (attn_aug_conv.py:65-97).
+ *   y        (B,Cout,H,W)   conv channels first, attention channels last (attn_aug_conv.py:95)
+ *   weights  optional (B,nh,HW,HW) softmax probabilities -- the tensor the reference stashes as
+ *            self.weights (attn_aug_conv.py:87); NULL = do not materialise it.                       */
+int aaconv_forward(const aaconv_dims* d, int precision, const float* x, const aaconv_params* p,
+                   float* y, float* weights, void* saved, void* scratch, void* stream);
+
+/* Backward: the adjoint autograd derives from attn_aug_conv.py:65-97.
+ *   dy (B,Cout,H,W); dx (B,Cin,Hin,Win) or NULL; parameter grads are WRITTEN (not accumulated).      */
+int aaconv_backward(const aaconv_dims* d, int precision, const float* x, const aaconv_params* p,
+                    const float* dy, const void* saved, void* scratch,
+                    float* dx, const aaconv_param_grads* g, void* stream);
+
+/* Loss: replaces nn.BCEWithLogitsLoss(reduction='none')(z,t) [.sum(1).mean(0)]  (chexpert.py:530,160,205).
+ *   z (B,C) logits.  Targets are either
+ *     targets (B,C) floats in {0,1} (already U-Ones'd, dataset.py:139,142), with cols == NULL, or
+ *     raw labels (B,ld) in {nan,-1,0,1} with cols[C] the selected columns (dataset.py:25): the kernel
+ *     applies blank->0 and -1->1 itself.
+ *   element_loss (B,C) or NULL; loss scalar (sum over classes, mean over batch) or NULL;
+ *   dz (B,C) or NULL = d loss / d z * grad_scale[0] (grad_scale NULL = 1).                           */
+int aaconv_bce_forward_backward(const float* z, const float* targets, int ld, const int32_t* cols,
+                                int B, int C, float* element_loss, float* loss, float* dz,
+                                const float* grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* AACONV_B200_H_ */

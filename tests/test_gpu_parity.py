@@ -1,0 +1,123 @@
+"""GPU parity: the CUDA path, called through the module / C ABI, against the oracle and the reference fixtures."""
+import numpy as np
+import os
+import pytest
+import torch
+
+from oracle import aaconv_oracle as O
+from tests.helpers import GOLDEN, golden_cases, load_case, rel_err
+
+pytestmark = pytest.mark.gpu
+
+# fp32 mode: north_star asks for rtol 1e-4 against the reference; measured as max-abs error relative to the
+# tensor's max-abs value (gradient tensors span many orders of magnitude, so a per-element rtol is ill-posed).
+FP32_TOL = 1e-4
+
+
+def _module(s, p, precision):
+    import chexpert_b200 as cb
+    m = cb.AAConv2d(s.in_channels, s.out_channels, s.kernel_size, s.stride, s.dk, s.dv, s.nh, s.relative,
+                    s.input_dims, precision=precision)
+    m.load_state_dict({k: v.float() for k, v in p.items()}, strict=True)
+    return m.cuda()
+
+
+@pytest.mark.parametrize('name', golden_cases('f64'))
+def test_fp32_matches_reference_fixture(name):
+    s, p, g, t = load_case(name, 'f64')
+    m = _module(s, p, 'fp32')
+    x = t['x'].float().cuda().requires_grad_(True)
+    y, w = m(x, return_attn=True)
+    y.backward(t['dy'].float().cuda())
+    assert rel_err(y.cpu(), t['y']) < FP32_TOL
+    assert rel_err(w.cpu(), t['weights']) < FP32_TOL
+    assert rel_err(x.grad.cpu(), g['x']) < FP32_TOL
+    for n, prm in m.named_parameters():
+        assert rel_err(prm.grad.cpu(), g[n]) < FP32_TOL, n
+
+
+@pytest.mark.parametrize('tag,shape,B,hin', [
+    ('T3', O.AAConvShape(1024, 512, 3, 2, 160, 48, 8, True, (10, 10)), 2, 20),
+    ('T2', O.AAConvShape(512, 256, 3, 2, 160, 24, 8, True, (20, 20)), 1, 40),
+])
+def test_fp32_transition_shapes_vs_oracle(tag, shape, B, hin):
+    p = O.init_params(shape, seed=0)
+    g0 = torch.Generator().manual_seed(1)
+    x = torch.relu(torch.randn(B, shape.in_channels, hin, hin, generator=g0))
+    dy = torch.randn(B, shape.out_channels, *shape.input_dims, generator=g0)
+    y_ref, g_ref = O.aaconv_backward_closed(x.double(), {k: v.double() for k, v in p.items()}, shape, dy.double())
+    m = _module(shape, p, 'fp32')
+    xc = x.cuda().requires_grad_(True)
+    y = m(xc)
+    y.backward(dy.cuda())
+    assert rel_err(y.cpu(), y_ref) < FP32_TOL
+    assert rel_err(xc.grad.cpu(), g_ref['x']) < FP32_TOL
+    for n, prm in m.named_parameters():
+        assert rel_err(prm.grad.cpu(), g_ref[n]) < FP32_TOL, n
+
+
+def test_weights_are_opt_in_and_rows_sum_to_one():
+    s, p, g, t = load_case('nonsquare_s2', 'f64')
+    m = _module(s, p, 'fp32')
+    x = t['x'].float().cuda()
+    with torch.no_grad():
+        m(x)
+        assert m.weights is None                      # never materialised by default
+        m.store_weights = True
+        m(x)
+    B, nh = x.shape[0], s.nh
+    H, W = s.input_dims
+    assert m.weights.shape == (B, nh, H * W, H * W)
+    # read contract of the visualise path (chexpert.py:383-387)
+    v = m.weights.data[0].reshape(m.nh, H, W, H, W)
+    assert torch.allclose(v.sum((-1, -2)), torch.ones(nh, H, W, device='cuda'), atol=1e-5)
+
+
+def test_needs_input_grad_is_honoured():
+    s, p, g, t = load_case('heads8_dkh20', 'f64')
+    m = _module(s, p, 'fp32')
+    for prm in m.parameters():
+        prm.requires_grad_(False)
+    m.key_rel_w.requires_grad_(True)
+    x = t['x'].float().cuda()
+    y = m(x)
+    y.backward(t['dy'].float().cuda())
+    assert m.in_proj_qkv.weight.grad is None and m.conv.weight.grad is None
+    assert rel_err(m.key_rel_w.grad.cpu(), g['key_rel_w']) < FP32_TOL
+
+
+def test_shape_mismatch_raises():
+    import chexpert_b200 as cb
+    m = cb.AAConv2d(8, 16, 3, 2, 8, 4, 2, True, (4, 4)).cuda()
+    with pytest.raises(RuntimeError):
+        m(torch.randn(1, 8, 10, 10, device='cuda'))    # 5x5 map vs input_dims 4x4
+    with pytest.raises(RuntimeError):
+        m(torch.randn(1, 7, 8, 8, device='cuda'))
+
+
+def test_bce_kernel_matches_reference_fixture():
+    import chexpert_b200 as cb
+    z = np.load(os.path.join(GOLDEN, 'bce.npz'))
+    zz = torch.from_numpy(z['z']).cuda().requires_grad_(True)
+    t = torch.from_numpy(z['t']).cuda()
+    el = cb.BCEWithLogitsLoss('none')(zz, t)
+    assert torch.allclose(el.cpu(), torch.from_numpy(z['el']), rtol=1e-5, atol=2e-6)
+    loss = cb.BCEWithLogitsLoss('train')(zz, t)
+    loss.backward()
+    assert torch.allclose(loss.cpu(), torch.from_numpy(z['loss']), rtol=1e-5)
+    assert torch.allclose(zz.grad.cpu(), torch.from_numpy(z['gz']), rtol=1e-4, atol=1e-7)
+    # reference usage: element losses then .sum(1).mean(0) through autograd  (chexpert.py:160)
+    zz.grad = None
+    cb.BCEWithLogitsLoss('none')(zz, t).sum(1).mean(0).backward()
+    assert torch.allclose(zz.grad.cpu(), torch.from_numpy(z['gz']), rtol=1e-4, atol=1e-7)
+
+
+def test_bce_raw_uones_labels():
+    import chexpert_b200 as cb
+    g = torch.Generator().manual_seed(3)
+    raw = torch.tensor([float('nan'), -1.0, 0.0, 1.0])[torch.randint(0, 4, (16, 14), generator=g)]
+    z = torch.randn(16, 5, generator=g)
+    t = O.uones_targets(raw)
+    want, _ = O.bce_train_loss(z, t)
+    got = cb.BCEWithLogitsLoss('train', raw_labels=True)(z.cuda(), raw.cuda())
+    assert torch.allclose(got.cpu(), want, rtol=1e-5)
