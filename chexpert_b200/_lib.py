@@ -42,6 +42,9 @@ SYMBOLS = {
                                        ctypes.POINTER(ParamGrads), _P]),
     'aaconv_bce_forward_backward': (ctypes.c_int, [_P, _P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int,
                                                    _P, _P, _P, _P, _P]),
+    'aaconv_launch_count': (ctypes.c_longlong, []),
+    'aaconv_profile_begin': (ctypes.c_int, [_P]),
+    'aaconv_profile_end': (ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_float), ctypes.c_int]),
 }
 
 _lock = threading.Lock()
@@ -74,3 +77,22 @@ def check(code, what):
     if code != 0:
         msg = load().aaconv_last_error().decode(errors='replace')
         raise RuntimeError(f'{what} failed (code {code}): {msg}')
+
+
+def launch_count():
+    return int(load().aaconv_launch_count())
+
+
+def profile_begin(stream_ptr):
+    check(load().aaconv_profile_begin(ctypes.c_void_p(stream_ptr)), 'aaconv_profile_begin')
+
+
+def profile_end(max_entries=4096):
+    """-> list of (kernel name, milliseconds) in launch order since profile_begin()."""
+    names = ctypes.create_string_buffer(max_entries * 40)
+    ms = (ctypes.c_float * max_entries)()
+    n = load().aaconv_profile_end(names, len(names), ms, max_entries)
+    if n < 0:
+        check(n, 'aaconv_profile_end')
+    ns = names.value.decode().split('\n')
+    return [(ns[i] if i < len(ns) else '?', float(ms[i])) for i in range(n)]

@@ -5,20 +5,6 @@
 
 namespace aaconv {
 
-std::string& last_error_ref() {
-  static thread_local std::string s;
-  return s;
-}
-int fail(int code, const char* fmt, ...) {
-  char buf[512];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof buf, fmt, ap);
-  va_end(ap);
-  last_error_ref() = buf;
-  return code;
-}
-
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                      int count, int splits, int accumulate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

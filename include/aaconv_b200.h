@@ -103,6 +103,15 @@ int aaconv_bce_forward_backward(const float* z, const float* targets, int ld, co
                                 int B, int C, float* element_loss, float* loss, float* dz,
                                 const float* grad_scale, void* stream);
 
+/* Accounting / measurement helpers used by bench.py (no reference counterpart).
+ *   aaconv_launch_count   kernels launched by this library since it was loaded (all threads).
+ *   aaconv_profile_begin  start recording a CUDA event after every launch made on `stream`.
+ *   aaconv_profile_end    stop; fills ms[i] = device time of launch i (gap to the previous mark) and the
+ *                         '\n'-joined kernel names; returns the number of entries written (<= max_entries). */
+long long aaconv_launch_count(void);
+int aaconv_profile_begin(void* stream);
+int aaconv_profile_end(char* names_buf, size_t names_len, float* ms, int max_entries);
+
 #ifdef __cplusplus
 }
 #endif
