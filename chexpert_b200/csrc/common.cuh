@@ -23,13 +23,18 @@ int fail(int code, const char* fmt, ...);
                             cudaGetErrorString(e__));                                              \
   } while (0)
 
-#define AACONV_LAUNCH_OK(name)                                                                     \
+// Called right after every kernel launch of this library: error check + launch accounting (+ optional
+// per-launch CUDA-event profile, see aaconv_profile_begin/end).
+void note_launch(const char* name, cudaStream_t st);
+#define AACONV_LAUNCH_OK_ON(name, stream__)                                                        \
   do {                                                                                             \
     cudaError_t e__ = cudaGetLastError();                                                          \
     if (e__ != cudaSuccess)                                                                        \
       return ::aaconv::fail(AACONV_E_CUDA, "%s:%d launch %s -> %s", __FILE__, __LINE__, name,     \
                             cudaGetErrorString(e__));                                              \
+    ::aaconv::note_launch(name, stream__);                                                         \
   } while (0)
+#define AACONV_LAUNCH_OK(name) AACONV_LAUNCH_OK_ON(name, st)
 
 #define AACONV_TRY(expr)                                                                           \
   do {                                                                                             \
