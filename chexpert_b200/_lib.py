@@ -35,7 +35,7 @@ SYMBOLS = {
     'aaconv_last_error': (ctypes.c_char_p, []),
     'aaconv_validate': (ctypes.c_int, [_DP, ctypes.c_int]),
     'aaconv_saved_bytes': (ctypes.c_size_t, [_DP, ctypes.c_int]),
-    'aaconv_scratch_bytes': (ctypes.c_size_t, [_DP, ctypes.c_int]),
+    'aaconv_scratch_bytes': (ctypes.c_size_t, [_DP, ctypes.c_int, ctypes.c_int]),
     'aaconv_saved_offset': (ctypes.c_int64, [_DP, ctypes.c_int, ctypes.c_char_p]),
     'aaconv_forward': (ctypes.c_int, [_DP, ctypes.c_int, _P, ctypes.POINTER(Params), _P, _P, _P, _P, _P]),
     'aaconv_backward': (ctypes.c_int, [_DP, ctypes.c_int, _P, ctypes.POINTER(Params), _P, _P, _P, _P,

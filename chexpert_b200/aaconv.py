@@ -64,7 +64,8 @@ class AAConvFunction(torch.autograd.Function):
                 raise RuntimeError(f'AAConv2d: feature map {d.H}x{d.W} does not match input_dims of the relative tables')
             y = torch.empty(d.B, d.Cout, d.H, d.W, device=xf.device, dtype=torch.float32)
             saved = torch.empty(lib.aaconv_saved_bytes(ctypes.byref(d), prec), device=xf.device, dtype=torch.uint8)
-            scratch = torch.empty(lib.aaconv_scratch_bytes(ctypes.byref(d), prec), device=xf.device, dtype=torch.uint8)
+            scratch = torch.empty(lib.aaconv_scratch_bytes(ctypes.byref(d), prec, int(bool(want_weights))), device=xf.device,
+                                  dtype=torch.uint8)
             weights = (torch.empty(d.B, d.nh, d.H * d.W, d.H * d.W, device=xf.device, dtype=torch.float32)
                        if want_weights else None)
             pp = _lib.Params(*[_ptr(p) for p in params])
@@ -91,7 +92,7 @@ class AAConvFunction(torch.autograd.Function):
         with torch.cuda.device(xf.device):
             dx = torch.empty_like(xf) if need[0] else None
             grads = [torch.empty_like(p) if (p is not None and need[i + 1]) else None for i, p in enumerate(params)]
-            scratch = torch.empty(lib.aaconv_scratch_bytes(ctypes.byref(d), prec), device=xf.device, dtype=torch.uint8)
+            scratch = torch.empty(lib.aaconv_scratch_bytes(ctypes.byref(d), prec, 0), device=xf.device, dtype=torch.uint8)
             pp = _lib.Params(*[_ptr(p) for p in params])
             gg = _lib.ParamGrads(*[_ptr(g) for g in grads])
             _lib.check(lib.aaconv_backward(ctypes.byref(d), prec, _ptr(xf), ctypes.byref(pp), _ptr(dyf), _ptr(saved),

@@ -41,9 +41,9 @@ size_t aaconv_saved_bytes(const aaconv_dims* d, int precision) {
   if (validate(d, precision)) return 0;
   return precision == AACONV_FP32 ? f32_saved_bytes(Dims(*d)) : bf16_saved_bytes(Dims(*d));
 }
-size_t aaconv_scratch_bytes(const aaconv_dims* d, int precision) {
+size_t aaconv_scratch_bytes(const aaconv_dims* d, int precision, int want_weights) {
   if (validate(d, precision)) return 0;
-  return precision == AACONV_FP32 ? f32_scratch_bytes(Dims(*d)) : bf16_scratch_bytes(Dims(*d));
+  return precision == AACONV_FP32 ? f32_scratch_bytes(Dims(*d)) : bf16_scratch_bytes(Dims(*d), want_weights);
 }
 int64_t aaconv_saved_offset(const aaconv_dims* d, int precision, const char* name) {
   if (validate(d, precision) || !name) return -1;

@@ -1,0 +1,515 @@
+// bf16 tcgen05 attention core of AAConv2d -- backward (recompute), and the shared operand builder.
+//
+// Augmented operands (one row per query / key position, bf16, KP columns, K-major):
+//   Qa[row] = [ c*q | c*Aq | c*Bq | -lse2_hi | -lse2_lo | 0.. | dO | -delta_hi | -delta_lo | 0.. ]
+//   Ka[row] = [  k  | 1hot(x') | 1hot(y') |   1   |    1    | 0.. |  v |     1    |     1    | 0.. ]
+//              `------------- S block: columns [0, C1) ------------'  `-- V block: [C1, C1+16) --'
+//   c = log2(e);  Aq[x'] = q.key_rel_w[:, x'-x+W-1];  Bq[y'] = q.key_rel_h[:, y'-y+H-1]   (rel_to_abs as an
+//   index computation, attn_aug_conv.py:43-63);  lse2 = c*lse split into two bf16 so the sum is exact to ~1e-4.
+// so that two MMAs give, with no per-element subtraction on the CUDA cores,
+//   S'[q,k]  = Qa[q,0:C1].Ka[k,0:C1]      = log2e * (logit[q,k] - lse[q])      ->  P = 2^S'
+//   dP'[q,k] = Qa[q,C1:C1+16].Ka[k,C1:..] = dO[q].v[k] - delta[q]              ->  dS = P * dP'
+// and the same shared-memory tiles, viewed MN-major, are the B operands of
+//   dV += P^T dO,  dK += dS^T Qa[:, 0:dkh]  (key-stationary kernel),  dQa += dS Ka[:, 0:KD]  (query-stationary kernel).
+// dQa[:, dkh:KD] are the gradients of Aq/Bq, i.e. the relative-logit gradients summed over key rows / columns.
+//
+// Out-of-range rows are zero-filled by TMA: S' = 0, dP' = 0 -> dS = 0 and P multiplies zero dO rows, so the
+// backward needs no masking at all.
+#include "tc_common.cuh"
+#include "bf16_path.cuh"
+
+namespace aaconv {
+
+using tc::smem_u32;
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------------
+// layout of the augmented operands
+// ------------------------------------------------------------------------------------------------
+AugLayout aug_layout(const Dims& d) {
+  AugLayout a;
+  a.KD = d.dkh + (d.relative ? d.W + d.H : 0);
+  a.C1 = cdiv(a.KD + 2, 16) * 16;
+  a.KP = cdiv(a.C1 + 16, 64) * 64;
+  a.NQ = cdiv(a.KD, 16) * 16;
+  return a;
+}
+
+int aug_supported(const Dims& d) {
+  const AugLayout a = aug_layout(d);
+  if (d.dvh + 2 > 16) return fail(AACONV_E_UNSUPPORTED, "bf16 attention kernels support dv/nh <= 14 (got %d)", d.dvh);
+  if (a.KP > 192 || d.dkh > 32)
+    return fail(AACONV_E_UNSUPPORTED, "bf16 attention kernels support dk/nh <= 32 and dk/nh + H + W <= 158 (got %d, %d)",
+                d.dkh, a.KD);
+  return 0;
+}
+
+__device__ __forceinline__ void split_bf16(float x, bf16& hi, bf16& lo) {
+  hi = __float2bfloat16(x);
+  lo = __float2bfloat16(x - __bfloat162float(hi));
+}
+
+// mode 0 (forward): the lse columns of Qa carry +BIG / 0 (shifts every in-range logit, so zero-filled
+// out-of-range keys fall 2^-BIG below: masking without a compare); dO/delta columns are zero.
+// mode 1 (backward): full layout.
+__global__ void aug_build_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                                 const float* __restrict__ krw, const float* __restrict__ krh,
+                                 const float* __restrict__ lse, const float* __restrict__ d_o,
+                                 const float* __restrict__ delta, bf16* __restrict__ qa, bf16* __restrict__ ka,
+                                 size_t rows, int L, int H, int W, int dkh, int dvh, int KD, int C1, int KP, int relative,
+                                 int mode, float big) {
+  extern __shared__ float sm[];
+  const float LOG2E = 1.4426950408889634f;
+  const int RW = 2 * W - 1, RH = 2 * H - 1;
+  float* kw = sm;                                   // dkh x RW
+  float* kh = kw + (relative ? dkh * RW : 0);       // dkh x RH
+  float* qs = kh + (relative ? dkh * RH : 0);       // 16 x dkh
+  float* ks = qs + 16 * dkh;
+  if (relative) {
+    for (int i = threadIdx.x; i < dkh * RW; i += blockDim.x) kw[i] = krw[i];
+    for (int i = threadIdx.x; i < dkh * RH; i += blockDim.x) kh[i] = krh[i];
+  }
+  const int c = threadIdx.x;                        // blockDim.x == KP
+  for (size_t r0 = (size_t)blockIdx.x * 16; r0 < rows; r0 += (size_t)gridDim.x * 16) {
+    __syncthreads();
+    const int nr = (int)min((size_t)16, rows - r0);
+    for (int i = threadIdx.x; i < nr * dkh; i += blockDim.x) { qs[i] = q[r0 * dkh + i]; ks[i] = k[r0 * dkh + i]; }
+    __syncthreads();
+    for (int rr = 0; rr < nr; ++rr) {
+      const size_t row = r0 + rr;
+      const int l = (int)(row % L), y = l / W, x = l - y * W;
+      float qv = 0.f, kv = 0.f;
+      if (c < dkh) {
+        qv = qs[rr * dkh + c] * LOG2E;
+        kv = ks[rr * dkh + c];
+      } else if (c < KD) {
+        const bool isw = c < dkh + W;
+        const int pos = isw ? c - dkh : c - dkh - W;
+        const float* tab = isw ? kw + (pos - x + W - 1) : kh + (pos - y + H - 1);
+        const int R = isw ? RW : RH;
+        float a = 0.f;
+        for (int e = 0; e < dkh; ++e) a = fmaf(qs[rr * dkh + e], tab[e * R], a);
+        qv = a * LOG2E;
+        kv = (pos == (isw ? x : y)) ? 1.f : 0.f;
+      } else if (c < KD + 2) {
+        kv = 1.f;
+        if (mode == 0) {
+          qv = (c == KD) ? big : 0.f;
+        } else {
+          bf16 hi, lo;
+          split_bf16(-lse[row] * LOG2E, hi, lo);
+          qv = __bfloat162float(c == KD ? hi : lo);
+        }
+      } else if (c >= C1 && c < C1 + dvh) {
+        kv = v[row * dvh + (c - C1)];
+        qv = mode ? d_o[row * dvh + (c - C1)] : 0.f;
+      } else if (c >= C1 + dvh && c < C1 + dvh + 2) {
+        kv = 1.f;
+        if (mode) {
+          bf16 hi, lo;
+          split_bf16(-delta[row], hi, lo);
+          qv = __bfloat162float(c == C1 + dvh ? hi : lo);
+        }
+      }
+      qa[row * KP + c] = __float2bfloat16(qv);
+      ka[row * KP + c] = __float2bfloat16(kv);
+    }
+  }
+}
+
+int aug_build(const Dims& d, int mode, const float* q, const float* k, const float* v, const float* krw,
+              const float* krh, const float* lse, const float* d_o, const float* delta, void* qa, void* ka,
+              cudaStream_t st) {
+  const AugLayout a = aug_layout(d);
+  const size_t rows = (size_t)d.BN * d.L;
+  const size_t smem = sizeof(float) * ((d.relative ? (size_t)d.dkh * (d.RW + d.RH) : 0) + 32 * (size_t)d.dkh);
+  AACONV_CUDA_OK(cudaFuncSetAttribute(aug_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)std::min<size_t>((rows + 15) / 16, 148 * 16);
+  aug_build_kernel<<<grid, a.KP, smem, st>>>(q, k, v, krw, krh, lse, d_o, delta, static_cast<bf16*>(qa),
+                                            static_cast<bf16*>(ka), rows, d.L, d.H, d.W, d.dkh, d.dvh, a.KD, a.C1, a.KP,
+                                            d.relative, mode, AUG_BIG);
+  AACONV_LAUNCH_OK(mode ? "aug_build_bwd" : "aug_build_fwd");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ping-pong kernel skeleton: 8 math warps (two warpgroups, one TMEM slot each), 1 TMA warp, 1 MMA warp
+// ------------------------------------------------------------------------------------------------
+constexpr int PP_THREADS = 320;
+constexpr int PP_BM = 128;        // stationary rows (TMEM lanes)
+constexpr int PP_BN = 64;         // streamed rows per tile (TMEM columns per slot)
+constexpr int PP_STAGES = 4;
+
+template <int KATOMS>
+struct __align__(1024) PPSmem {
+  bf16 stat[KATOMS][PP_BM * 64];                   // stationary operand, 16 KB per 64-column atom
+  bf16 strm[PP_STAGES][KATOMS][PP_BN * 64];        // streamed operand, 8 KB per atom
+  uint64_t bar_stat, bar_full[PP_STAGES], bar_empty[PP_STAGES];
+  uint64_t bar_s_full[2], bar_p_ready[2], bar_mma_done[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint64_t desc_k(const void* atom_base, int ks) {          // K-major, k-step ks inside the atom
+  return tc::desc_advance(tc::smem_desc_sw128_kmajor(smem_u32(atom_base)), (ks & 3) * 32);
+}
+// MN-major view of a streamed tile: B[n, kk] = tile[row kk][col n0 + n]; rows are 128 B apart, 8-row groups
+// 1024 B apart (SBO), 64-column chunks one atom (PP_BN*128 B) apart (LBO).
+__device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t idesc_bmn(int M, int N) { return tc::idesc_bf16_f32(M, N) | (1u << 16); }
+
+// ---- key-stationary: dK, dV ------------------------------------------------------------------------
+// TMEM columns: slot s at 192*s: S'^T [0,64) dP'^T [64,128) P^T [128,160) dS^T [160,192);  dV at 384, dK at 400.
+template <int KATOMS>
+__global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dkv_tc_kernel(
+    const __grid_constant__ CUtensorMap tm_k_stat, const __grid_constant__ CUtensorMap tm_q_strm,
+    float* __restrict__ dk, float* __restrict__ dv, int L, int dkh, int dvh, int C1) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  PPSmem<KATOMS>& sm = *reinterpret_cast<PPSmem<KATOMS>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bn = blockIdx.y, k0 = blockIdx.x * PP_BM;
+  const int ntiles = (L + PP_BN - 1) / PP_BN;
+  const int nks = C1 >> 4;
+  constexpr uint32_t COL_DV = 384, COL_DK = 400;
+
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&sm.bar_stat, 1);
+    for (int s = 0; s < PP_STAGES; ++s) { tc::mbar_init(&sm.bar_full[s], 1); tc::mbar_init(&sm.bar_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&sm.bar_s_full[s], 1);
+      tc::mbar_init(&sm.bar_p_ready[s], 128);
+      tc::mbar_init(&sm.bar_mma_done[s], 1);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 8 && lane == 0) { tc::tma_prefetch_desc(&tm_k_stat); tc::tma_prefetch_desc(&tm_q_strm); }
+  if (warp == 9) tc::tmem_alloc<512>(&sm.tmem_base);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      tc::mbar_arrive_expect_tx(&sm.bar_stat, KATOMS * PP_BM * 64 * 2);
+      for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.stat[a], &tm_k_stat, &sm.bar_stat, a * 64, k0, bn);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j % PP_STAGES, ph = (j / PP_STAGES) & 1;
+        tc::mbar_wait(&sm.bar_empty[s], ph ^ 1);
+        tc::mbar_arrive_expect_tx(&sm.bar_full[s], KATOMS * PP_BN * 64 * 2);
+        for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.strm[s][a], &tm_q_strm, &sm.bar_full[s], a * 64, j * PP_BN, bn);
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = tc::idesc_bf16_f32(PP_BM, PP_BN);
+      constexpr uint32_t idesc_dv = idesc_bmn(PP_BM, 16);
+      constexpr uint32_t idesc_dk = idesc_bmn(PP_BM, 32);
+      tc::mbar_wait(&sm.bar_stat, 0);
+      // software pipeline: scores of tile j are issued before the gradient MMAs of tile j-1
+      for (int j = 0; j <= ntiles; ++j) {
+        if (j < ntiles) {
+          const int st = j % PP_STAGES, slot = j & 1;
+          const uint32_t tslot = tmem + 192 * slot;
+          tc::mbar_wait(&sm.bar_full[st], (j / PP_STAGES) & 1);
+          tc::tc_fence_after();
+          for (int ks = 0; ks < nks; ++ks)
+            tc::mma_ss(tslot, desc_k(sm.stat[ks >> 2], ks), desc_k(sm.strm[st][ks >> 2], ks), idesc_s, ks > 0);
+          tc::mma_ss(tslot + 64, desc_k(sm.stat[nks >> 2], nks), desc_k(sm.strm[st][nks >> 2], nks), idesc_s, 0);
+          tc::mma_commit(&sm.bar_s_full[slot]);
+        }
+        if (j > 0) {
+          const int jj = j - 1, st = jj % PP_STAGES, slot = jj & 1;
+          const uint32_t tslot = tmem + 192 * slot;
+          tc::mbar_wait(&sm.bar_p_ready[slot], (jj >> 1) & 1);
+          tc::tc_fence_after();
+          const uint32_t v_base = smem_u32(sm.strm[st][C1 >> 6]) + (C1 & 63) * 2;
+          const uint32_t q_base = smem_u32(sm.strm[st][0]);
+          for (int ks = 0; ks < PP_BN / 16; ++ks) {
+            tc::mma_ts(tmem + COL_DV, tslot + 128 + ks * 8, desc_mn(v_base + ks * 2048, PP_BN * 128), idesc_dv, (jj > 0 || ks > 0) ? 1u : 0u);
+            tc::mma_ts(tmem + COL_DK, tslot + 160 + ks * 8, desc_mn(q_base + ks * 2048, PP_BN * 128), idesc_dk, (jj > 0 || ks > 0) ? 1u : 0u);
+          }
+          tc::mma_commit(&sm.bar_empty[st]);
+          tc::mma_commit(&sm.bar_mma_done[slot]);
+        }
+      }
+    }
+  } else {
+    // ===================== math warpgroups: thread == key row == TMEM lane =====================
+    const int wg = warp >> 2;
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t tslot = tlane + 192 * wg;
+    uint32_t rs[32], rd[32], pp[16], pd[16];
+    for (int j = wg; j < ntiles; j += 2) {
+      const int it = j >> 1;
+      tc::mbar_wait(&sm.bar_s_full[wg], it & 1);
+      tc::tc_fence_after();
+      if (it > 0) tc::mbar_wait(&sm.bar_mma_done[wg], (it - 1) & 1);   // previous P^T/dS^T of this slot consumed
+#pragma unroll
+      for (int c = 0; c < PP_BN / 32; ++c) {
+        tc::tmem_ld_x32(tslot + c * 32, rs);
+        tc::tmem_ld_x32(tslot + 64 + c * 32, rd);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = tc::ex2f(__uint_as_float(rs[2 * i])), p1 = tc::ex2f(__uint_as_float(rs[2 * i + 1]));
+          pp[i] = tc::pack_bf16x2(p0, p1);
+          pd[i] = tc::pack_bf16x2(p0 * __uint_as_float(rd[2 * i]), p1 * __uint_as_float(rd[2 * i + 1]));
+        }
+        tc::tmem_st_x16(tslot + 128 + c * 16, pp);
+        tc::tmem_st_x16(tslot + 160 + c * 16, pd);
+      }
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      tc::mbar_arrive(&sm.bar_p_ready[wg]);
+    }
+    // epilogue: wait for the last gradient MMAs of both slots, then WG0 writes dK, WG1 writes dV
+    for (int s = 0; s < 2; ++s) {
+      const int n_s = (ntiles - s + 1) / 2;              // tiles handled by slot s
+      if (n_s > 0) tc::mbar_wait(&sm.bar_mma_done[s], (n_s - 1) & 1);
+    }
+    tc::tc_fence_after();
+    const int kj = k0 + (warp & 3) * 32 + lane;
+    const size_t row = (size_t)bn * L + kj;
+    const float LN2 = 0.6931471805599453f;               // Qa carries log2(e)*q
+    if (wg == 0) {
+      tc::tmem_ld_x32(tlane + COL_DK, rs);
+      tc::tmem_ld_wait();
+      if (kj < L) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (e < dkh) dk[row * dkh + e] = __uint_as_float(rs[e]) * LN2;
+      }
+    } else {
+      tc::tmem_ld_x16(tlane + COL_DV, pp);
+      tc::tmem_ld_wait();
+      if (kj < L) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (e < dvh) dv[row * dvh + e] = __uint_as_float(pp[e]);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tc::tmem_dealloc<512>(tmem);
+}
+
+// ---- query-stationary: dQa (content gradient + gradients of the relative rows Aq, Bq) ---------------
+// TMEM columns: slot s at 160*s: S' [0,64) dP' [64,128) dS [128,160);  dQa at 320 (NQ <= 160 columns).
+template <int KATOMS>
+__global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dq_tc_kernel(
+    const __grid_constant__ CUtensorMap tm_q_stat, const __grid_constant__ CUtensorMap tm_k_strm,
+    float* __restrict__ dqa, int L, int KD, int NQ, int C1) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  PPSmem<KATOMS>& sm = *reinterpret_cast<PPSmem<KATOMS>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bn = blockIdx.y, q0 = blockIdx.x * PP_BM;
+  const int ntiles = (L + PP_BN - 1) / PP_BN;
+  const int nks = C1 >> 4;
+  constexpr uint32_t COL_DQ = 320;
+
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&sm.bar_stat, 1);
+    for (int s = 0; s < PP_STAGES; ++s) { tc::mbar_init(&sm.bar_full[s], 1); tc::mbar_init(&sm.bar_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&sm.bar_s_full[s], 1);
+      tc::mbar_init(&sm.bar_p_ready[s], 128);
+      tc::mbar_init(&sm.bar_mma_done[s], 1);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 8 && lane == 0) { tc::tma_prefetch_desc(&tm_q_stat); tc::tma_prefetch_desc(&tm_k_strm); }
+  if (warp == 9) tc::tmem_alloc<512>(&sm.tmem_base);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      tc::mbar_arrive_expect_tx(&sm.bar_stat, KATOMS * PP_BM * 64 * 2);
+      for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.stat[a], &tm_q_stat, &sm.bar_stat, a * 64, q0, bn);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j % PP_STAGES, ph = (j / PP_STAGES) & 1;
+        tc::mbar_wait(&sm.bar_empty[s], ph ^ 1);
+        tc::mbar_arrive_expect_tx(&sm.bar_full[s], KATOMS * PP_BN * 64 * 2);
+        for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.strm[s][a], &tm_k_strm, &sm.bar_full[s], a * 64, j * PP_BN, bn);
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = tc::idesc_bf16_f32(PP_BM, PP_BN);
+      const uint32_t idesc_dq = idesc_bmn(PP_BM, NQ);
+      tc::mbar_wait(&sm.bar_stat, 0);
+      for (int j = 0; j <= ntiles; ++j) {
+        if (j < ntiles) {
+          const int st = j % PP_STAGES, slot = j & 1;
+          const uint32_t tslot = tmem + 160 * slot;
+          tc::mbar_wait(&sm.bar_full[st], (j / PP_STAGES) & 1);
+          tc::tc_fence_after();
+          for (int ks = 0; ks < nks; ++ks)
+            tc::mma_ss(tslot, desc_k(sm.stat[ks >> 2], ks), desc_k(sm.strm[st][ks >> 2], ks), idesc_s, ks > 0);
+          tc::mma_ss(tslot + 64, desc_k(sm.stat[nks >> 2], nks), desc_k(sm.strm[st][nks >> 2], nks), idesc_s, 0);
+          tc::mma_commit(&sm.bar_s_full[slot]);
+        }
+        if (j > 0) {
+          const int jj = j - 1, st = jj % PP_STAGES, slot = jj & 1;
+          const uint32_t tslot = tmem + 160 * slot;
+          tc::mbar_wait(&sm.bar_p_ready[slot], (jj >> 1) & 1);
+          tc::tc_fence_after();
+          const uint32_t k_base = smem_u32(sm.strm[st][0]);
+          for (int ks = 0; ks < PP_BN / 16; ++ks)
+            tc::mma_ts(tmem + COL_DQ, tslot + 128 + ks * 8, desc_mn(k_base + ks * 2048, PP_BN * 128), idesc_dq, (jj > 0 || ks > 0) ? 1u : 0u);
+          tc::mma_commit(&sm.bar_empty[st]);
+          tc::mma_commit(&sm.bar_mma_done[slot]);
+        }
+      }
+    }
+  } else {
+    const int wg = warp >> 2;
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t tslot = tlane + 160 * wg;
+    uint32_t rs[32], rd[32], pd[16];
+    for (int j = wg; j < ntiles; j += 2) {
+      const int it = j >> 1;
+      tc::mbar_wait(&sm.bar_s_full[wg], it & 1);
+      tc::tc_fence_after();
+      if (it > 0) tc::mbar_wait(&sm.bar_mma_done[wg], (it - 1) & 1);
+#pragma unroll
+      for (int c = 0; c < PP_BN / 32; ++c) {
+        tc::tmem_ld_x32(tslot + c * 32, rs);
+        tc::tmem_ld_x32(tslot + 64 + c * 32, rd);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = tc::ex2f(__uint_as_float(rs[2 * i])), p1 = tc::ex2f(__uint_as_float(rs[2 * i + 1]));
+          pd[i] = tc::pack_bf16x2(p0 * __uint_as_float(rd[2 * i]), p1 * __uint_as_float(rd[2 * i + 1]));
+        }
+        tc::tmem_st_x16(tslot + 128 + c * 16, pd);
+      }
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      tc::mbar_arrive(&sm.bar_p_ready[wg]);
+    }
+    for (int s = 0; s < 2; ++s) {
+      const int n_s = (ntiles - s + 1) / 2;
+      if (n_s > 0) tc::mbar_wait(&sm.bar_mma_done[s], (n_s - 1) & 1);
+    }
+    tc::tc_fence_after();
+    // dQa rows -> global (B,nh,L,KD) fp32; the two warpgroups split the columns in 32-wide chunks
+    const int qi = q0 + (warp & 3) * 32 + lane;
+    const size_t row = (size_t)bn * L + qi;
+    for (int c0 = wg * 32; c0 < NQ; c0 += 64) {
+      tc::tmem_ld_x32(tlane + COL_DQ + c0, rs);
+      tc::tmem_ld_wait();
+      if (qi < L) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (c0 + e < KD) dqa[row * KD + c0 + e] = __uint_as_float(rs[e]);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tc::tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int make_aug_maps(const Dims& d, const void* t, int KP, uint32_t box_rows, CUtensorMap* out) {
+  const uint64_t dims[3] = {(uint64_t)KP, (uint64_t)d.L, (uint64_t)d.BN};
+  const uint64_t strides[2] = {(uint64_t)KP * 2, (uint64_t)d.L * KP * 2};
+  const uint32_t box[3] = {64, box_rows, 1};
+  return make_tmap_bf16(out, t, 3, dims, strides, box, nullptr);
+}
+
+template <int KATOMS>
+static int launch_bwd(const Dims& d, const AugLayout& a, const void* qa, const void* ka, float* dqa, float* dk,
+                      float* dv, cudaStream_t st) {
+  CUtensorMap tq_stat, tk_strm, tk_stat, tq_strm;
+  AACONV_TRY(make_aug_maps(d, qa, a.KP, PP_BM, &tq_stat));
+  AACONV_TRY(make_aug_maps(d, ka, a.KP, PP_BN, &tk_strm));
+  AACONV_TRY(make_aug_maps(d, ka, a.KP, PP_BM, &tk_stat));
+  AACONV_TRY(make_aug_maps(d, qa, a.KP, PP_BN, &tq_strm));
+  const size_t smem = sizeof(PPSmem<KATOMS>) + 1024;
+  dim3 grid(cdiv(d.L, PP_BM), d.BN);
+  {
+    auto kern = attn_bwd_dkv_tc_kernel<KATOMS>;
+    AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, PP_THREADS, smem, st>>>(tk_stat, tq_strm, dk, dv, d.L, d.dkh, d.dvh, a.C1);
+    AACONV_LAUNCH_OK("attn_bwd_dkv_tc");
+  }
+  {
+    auto kern = attn_bwd_dq_tc_kernel<KATOMS>;
+    AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, PP_THREADS, smem, st>>>(tq_stat, tk_strm, dqa, d.L, a.KD, a.NQ, a.C1);
+    AACONV_LAUNCH_OK("attn_bwd_dq_tc");
+  }
+  return 0;
+}
+
+// qa/ka: mode-1 augmented operands.  dqa (B,nh,L,KD) fp32; dk (B,nh,L,dkh); dv (B,nh,L,dvh).
+int tc_attn_bwd(const Dims& d, const void* qa, const void* ka, float* dqa, float* dk, float* dv, cudaStream_t st) {
+  AACONV_TRY(aug_supported(d));
+  const AugLayout a = aug_layout(d);
+  switch (a.KP / 64) {
+    case 1: return launch_bwd<1>(d, a, qa, ka, dqa, dk, dv, st);
+    case 2: return launch_bwd<2>(d, a, qa, ka, dqa, dk, dv, st);
+    default: return launch_bwd<3>(d, a, qa, ka, dqa, dk, dv, st);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// post-processing of dQa: total dq, and the abs->rel scatter for the key_rel gradients
+// ------------------------------------------------------------------------------------------------
+// dq[row, e] = dQa[row, e] + sum_x' krw[e, x'-x+W-1] dQa[row, dkh+x'] + sum_y' krh[e, y'-y+H-1] dQa[row, dkh+W+y']
+__global__ void aug_bwd_dq_kernel(const float* __restrict__ dqa, const float* __restrict__ krw,
+                                  const float* __restrict__ krh, float* __restrict__ dq, size_t rows, int L, int H,
+                                  int W, int dkh, int KD, int relative) {
+  extern __shared__ float sm[];
+  const int RW = 2 * W - 1, RH = 2 * H - 1;
+  float* kw = sm;
+  float* kh = sm + (relative ? dkh * RW : 0);
+  if (relative) {
+    for (int i = threadIdx.x; i < dkh * RW; i += blockDim.x) kw[i] = krw[i];
+    for (int i = threadIdx.x; i < dkh * RH; i += blockDim.x) kh[i] = krh[i];
+  }
+  __syncthreads();
+  const size_t total = rows * dkh;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / dkh;
+    const int e = (int)(i - row * dkh);
+    const float* g = dqa + row * KD;
+    float s = __ldg(g + e);
+    if (relative) {
+      const int l = (int)(row % L), y = l / W, x = l - y * W;
+      const float* tw = kw + e * RW + (W - 1 - x);
+      const float* th = kh + e * RH + (H - 1 - y);
+      for (int xp = 0; xp < W; ++xp) s = fmaf(tw[xp], __ldg(g + dkh + xp), s);
+      for (int yp = 0; yp < H; ++yp) s = fmaf(th[yp], __ldg(g + dkh + W + yp), s);
+    }
+    dq[i] = s;
+  }
+}
+
+int aug_bwd_dq(const Dims& d, const float* dqa, const float* krw, const float* krh, float* dq, cudaStream_t st) {
+  const AugLayout a = aug_layout(d);
+  const size_t rows = (size_t)d.BN * d.L;
+  const size_t smem = d.relative ? (size_t)d.dkh * (d.RW + d.RH) * sizeof(float) : 0;
+  AACONV_CUDA_OK(cudaFuncSetAttribute(aug_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)std::min<size_t>((rows * d.dkh + 255) / 256, 148 * 16);
+  aug_bwd_dq_kernel<<<grid, 256, smem, st>>>(dqa, krw, krh, dq, rows, d.L, d.H, d.W, d.dkh, a.KD, d.relative);
+  AACONV_LAUNCH_OK("aug_bwd_dq");
+  return 0;
+}
+
+}  // namespace aaconv

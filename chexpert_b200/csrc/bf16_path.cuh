@@ -3,15 +3,37 @@
 #include "common.cuh"
 
 namespace aaconv {
-// attn_tc.cu
+
+// Column layout of the augmented attention operands (see attn_tc_bwd.cu).
+struct AugLayout {
+  int KD;   // dkh (+ W + H when relative): columns that form the logit
+  int C1;   // start of the V block = roundup16(KD + 2)
+  int KP;   // padded row length (multiple of 64)
+  int NQ;   // roundup16(KD): width of the dQa accumulator
+};
+constexpr float AUG_BIG = 64.f;   // log2-units shift of in-range logits in forward (out-of-range keys -> 2^-64)
+
+AugLayout aug_layout(const Dims& d);
+int aug_supported(const Dims& d);
+int aug_build(const Dims& d, int mode, const float* q, const float* k, const float* v, const float* krw,
+              const float* krh, const float* lse, const float* d_o, const float* delta, void* qa, void* ka,
+              cudaStream_t st);
+int tc_attn_bwd(const Dims& d, const void* qa, const void* ka, float* dqa, float* dk, float* dv, cudaStream_t st);
+int aug_bwd_dq(const Dims& d, const float* dqa, const float* krw, const float* krh, float* dq, cudaStream_t st);
+
+// attn_tc.cu (forward)
 int tc_attn_supported(const Dims& d);
 size_t tc_attn_operand_bytes(const Dims& d, size_t* qa_off, size_t* ka_off, size_t* vt_off);
 int tc_attn_fwd(const Dims& d, const float* q, const float* k, const float* v, const float* krw, const float* krh,
                 void* operands, float* o, float* lse, cudaStream_t st);
 
+// fp32_gemms.cu
+int aug_rel_weight_grad(const Dims& d, const float* q, const float* dqa, int KD, int axis, float* dkr, float* partial,
+                        cudaStream_t st);
+
 // bf16_path.cu
 size_t bf16_saved_bytes(const Dims& d);
-size_t bf16_scratch_bytes(const Dims& d);
+size_t bf16_scratch_bytes(const Dims& d, int want_weights);
 int64_t bf16_saved_offset(const Dims& d, const char* name);
 int bf16_forward(const Dims& d, const float* x, const aaconv_params* p, float* y, float* weights, void* saved,
                  void* scratch, cudaStream_t st);

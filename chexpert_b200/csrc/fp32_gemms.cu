@@ -2,6 +2,7 @@
 // Reference rows: a2 qkv projection, a9 out_proj, a10 conv branch, and their adjoints.
 #include "fp32_path.cuh"
 #include "simt_gemm.cuh"
+#include "bf16_path.cuh"
 
 namespace aaconv {
 
@@ -404,6 +405,42 @@ int f32_rel_weight_grad(const Dims& d, const float* q, const float* dr, int R, f
   splits = cdiv(p.K, p.k_chunk);
   p.q = q; p.dr = dr; p.partial = partial; p.dkh = d.dkh; p.R = R;
   AACONV_TRY(launch_simt_gemm(p, splits, st, "rel_weight_grad_f32"));
+  return splitk_reduce(partial, dkr, p.M * p.N, splits, st);
+}
+
+// d key_rel[e, r] from the abs-indexed gradients of the augmented rows (bf16 path):
+//   axis 0 (W): dkr[e, r] = sum_rows q[row, e] * dQa[row, dkh + (r - (W-1) + x_row)]   (term absent when out of range)
+//   axis 1 (H): same with y_row and the H block.
+struct AugRelWeightGradP {
+  int M, N, K, k_chunk;
+  const float* q; const float* dqa; float* partial;
+  int dkh, KD, L, W, n_axis, col0, is_w;
+  static constexpr bool A_K_CONTIG = true, B_K_CONTIG = true;
+  struct ARow { const float* p; };
+  struct BCol { int shift; };
+  __device__ ARow a_row(int m) const { return {q + m}; }
+  __device__ float a(const ARow& r, int k) const { return __ldg(r.p + (size_t)k * dkh); }
+  __device__ BCol b_col(int n) const { return {n - (n_axis - 1)}; }
+  __device__ float b(const BCol& c, int k) const {
+    const int l = k % L, y = l / W, x = l - y * W;
+    const int pos = c.shift + (is_w ? x : y);
+    return (pos >= 0 && pos < n_axis) ? __ldg(dqa + (size_t)k * KD + col0 + pos) : 0.f;
+  }
+  __device__ void store(int m, int n, float v, int split) const {
+    partial[(size_t)split * M * N + (size_t)m * N + n] = v;
+  }
+};
+
+int aug_rel_weight_grad(const Dims& d, const float* q, const float* dqa, int KD, int axis, float* dkr, float* partial,
+                        cudaStream_t st) {
+  AugRelWeightGradP p;
+  p.M = d.dkh; p.N = axis ? d.RH : d.RW; p.K = d.BN * d.L;
+  int splits = pick_splits(p.M, p.N, p.K);
+  p.k_chunk = chunk_for(p.K, splits);
+  splits = cdiv(p.K, p.k_chunk);
+  p.q = q; p.dqa = dqa; p.partial = partial; p.dkh = d.dkh; p.KD = KD; p.L = d.L; p.W = d.W;
+  p.n_axis = axis ? d.H : d.W; p.col0 = axis ? d.dkh + d.W : d.dkh; p.is_w = axis ? 0 : 1;
+  AACONV_TRY(launch_simt_gemm(p, splits, st, "aug_rel_weight_grad"));
   return splitk_reduce(partial, dkr, p.M * p.N, splits, st);
 }
 

@@ -51,7 +51,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef AACONV_MBAR_SPIN_LIMIT
 #define AACONV_MBAR_SPIN_LIMIT (1u << 26)
 #endif
-__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
   printf("aaconv: mbarrier timeout block (%d,%d) thread %d bar 0x%x parity %u\n", blockIdx.x, blockIdx.y, threadIdx.x,
          bar, parity);
   __trap();

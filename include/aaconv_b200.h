@@ -72,7 +72,8 @@ int aaconv_validate(const aaconv_dims* d, int precision);
 
 /* Sizes of the caller-owned work buffers (bytes; multiples of 256). */
 size_t aaconv_saved_bytes(const aaconv_dims* d, int precision);     /* forward -> backward state       */
-size_t aaconv_scratch_bytes(const aaconv_dims* d, int precision);   /* transient, either direction     */
+size_t aaconv_scratch_bytes(const aaconv_dims* d, int precision, int want_weights);  /* transient, either direction;
+                                                           want_weights: forward will also fill `weights` */
 
 /* Byte offsets of the named blocks inside the saved buffer (for tests and the visualise path).
  * names: "q","k","v","o","lse" (fp32 path: q,k (B,nh,L,dkh) with q pre-scaled; v,o (B,nh,L,dvh);
