@@ -10,6 +10,8 @@ namespace {
 struct Scratch {
   float *d_o, *delta, *dq, *dk, *dv, *partial, *dqa, *rw, *rh, *o_tmp, *lse_tmp;
   void *qa, *ka, *fwd_operands;
+  TcGemmBufs gemm;
+  bool gemm_ok;
   size_t bytes;
   Scratch(const Dims& d, void* base, int want_weights) {
     Carver c(base);
@@ -25,6 +27,11 @@ struct Scratch {
     qa = c.take<uint16_t>(rows * a.KP);
     ka = c.take<uint16_t>(rows * a.KP);
     fwd_operands = c.take<char>(tc_attn_operand_bytes(d, nullptr, nullptr, nullptr));
+    gemm_ok = tc_gemm_supported(d) == 0;
+    {
+      char* gb = c.take<char>(gemm_ok ? tc_gemm_bufs(d, nullptr).bytes : 0);
+      gemm = tc_gemm_bufs(d, gb);
+    }
     const bool w = want_weights && d.relative;
     rw = c.take<float>(w ? rows * d.RW : 0);
     rh = c.take<float>(w ? rows * d.RH : 0);
@@ -54,8 +61,12 @@ int bf16_forward(const Dims& d, const float* x, const aaconv_params* p, float* y
   float* v = at<float>(saved, f32_saved_offset(d, "v"));
   float* o = at<float>(saved, f32_saved_offset(d, "o"));
   float* lse = at<float>(saved, f32_saved_offset(d, "lse"));
-  AACONV_TRY(f32_conv_fwd(d, x, p->conv_w, y, st));
-  AACONV_TRY(f32_qkv_fwd(d, x, p->qkv_w, q, k, v, st));
+  if (w.gemm_ok) {
+    AACONV_TRY(tc_fprop(d, w.gemm, x, p->conv_w, p->qkv_w, y, q, k, v, st));
+  } else {   // geometry outside the TMA tiling (e.g. rows wider than 128 pixels): FFMA implicit GEMM
+    AACONV_TRY(f32_conv_fwd(d, x, p->conv_w, y, st));
+    AACONV_TRY(f32_qkv_fwd(d, x, p->qkv_w, q, k, v, st));
+  }
   AACONV_TRY(tc_attn_fwd(d, q, k, v, p->key_rel_w, p->key_rel_h, w.fwd_operands, o, lse, st));
   if (weights) {   // visualise path only: exact fp32 map (own fp32 statistics), independent of the bf16 kernel
     AACONV_TRY(f32_rel_fwd(d, q, p->key_rel_w, p->key_rel_h, w.rw, w.rh, st));
@@ -85,6 +96,12 @@ int bf16_backward(const Dims& d, const float* x, const aaconv_params* p, const f
     if (g->key_rel_h) AACONV_TRY(aug_rel_weight_grad(d, q, w.dqa, a.KD, 1, g->key_rel_h, w.partial, st));
   }
   AACONV_TRY(aug_bwd_dq(d, w.dqa, p->key_rel_w, p->key_rel_h, w.dq, st));
+  if (w.gemm_ok) {
+    if (dx) AACONV_TRY(tc_dgrad(d, w.gemm, dy, p->conv_w, p->qkv_w, w.dq, w.dk, w.dv, dx, st));
+    if (d.Cc) AACONV_TRY(f32_conv_bwd(d, x, p->conv_w, dy, nullptr, g->conv_w, w.partial, st));
+    AACONV_TRY(f32_qkv_bwd(d, x, p->qkv_w, w.dq, w.dk, w.dv, g->qkv_w, nullptr, 0, w.partial, st));
+    return 0;
+  }
   if (d.Cc) {
     AACONV_TRY(f32_conv_bwd(d, x, p->conv_w, dy, dx, g->conv_w, w.partial, st));
   } else if (dx) {

@@ -27,6 +27,21 @@ size_t tc_attn_operand_bytes(const Dims& d, size_t* qa_off, size_t* ka_off, size
 int tc_attn_fwd(const Dims& d, const float* q, const float* k, const float* v, const float* krw, const float* krh,
                 void* operands, float* o, float* lse, cudaStream_t st);
 
+// gemm_tc.cu (tcgen05 implicit GEMMs)
+struct TcGemmBufs {
+  void *xh, *dyh, *dqkvh, *wf, *wd, *wq;
+  int NPc, NPq, CinP, CinK, KPc, KPq;
+  size_t bytes;
+};
+int tc_gemm_supported(const Dims& d);
+TcGemmBufs tc_gemm_bufs(const Dims& d, void* base);
+int pack_nhwc_bf16(const float* in, void* out, int B, int C, int Cp, int HW, cudaStream_t st);
+int tc_fprop(const Dims& d, const TcGemmBufs& t, const float* x, const float* conv_w, const float* qkv_w, float* y,
+             float* q, float* k, float* v, cudaStream_t st);
+int tc_dgrad(const Dims& d, const TcGemmBufs& t, const float* dy, const float* conv_w, const float* qkv_w,
+             const float* dq, const float* dk, const float* dv, float* dx, cudaStream_t st);
+int tc_zero_class(const Dims& d, float* dx, int rh, int rw, cudaStream_t st);
+
 // fp32_gemms.cu
 int aug_rel_weight_grad(const Dims& d, const float* q, const float* dqa, int KD, int axis, float* dkr, float* partial,
                         cudaStream_t st);

@@ -1,0 +1,430 @@
+// bf16 tcgen05 implicit GEMMs for the dense contractions of AAConv2d:
+//   fprop : y[:, :Cc] = conv3x3_s2(x)  and  qkv = 1x1_s2(x)   in ONE kernel (the 1x1 projection is the centre
+//           tap of the 3x3 stencil, attn_aug_conv.py:34-35, so both read the same TMA boxes of x)
+//   dgrad : dx = conv^T(dy[:, :Cc]) + scatter(Wqkv^T dqkv), one launch per input-pixel residue class
+// Activations are packed once to channels-last bf16 (NHWC); a tile of M = r x Wt output pixels is one TMA box
+// [64 ch, Wt, r, 1] per (tap, 64-channel atom), landing K-major / 128B-swizzled exactly as tcgen05 wants it.
+// Strided taps are addressed through per-residue tensor maps (dims = pixels of one (h%s, w%s) class) so that
+// every box has unit element strides and image borders are TMA zero-fill.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+#include "tc_common.cuh"
+#include "bf16_path.cuh"
+
+namespace aaconv {
+
+using tc::smem_u32;
+typedef __nv_bfloat16 bf16;
+
+constexpr int PG_THREADS = 192;     // warps 0-3 epilogue, warp 4 TMA, warp 5 MMA
+constexpr int PG_STAGES = 6;
+constexpr int PG_MAX_SEGS = 16;
+constexpr int PG_MAX_CHUNKS = 4;    // 4 x 128 fp32 accumulator columns = all of TMEM
+
+struct PGSeg { int amap, dw, dh, katoms, bmap, brow; };       // one K-segment: a tap (or the qkv "tap")
+struct PGChunk { int n0, seg_begin, seg_end, kind; };          // one 128-wide accumulator
+
+struct PGParams {
+  CUtensorMap amaps[5];
+  CUtensorMap bmaps[2];
+  PGSeg segs[PG_MAX_SEGS];
+  PGChunk chunks[PG_MAX_CHUNKS];
+  int nchunks;
+  int r, Wt, Ht, tiles_h;          // tile = r rows x Wt pixels of the (Ht x Wt) pixel grid this launch covers
+  // epilogue
+  int mode;                        // 0 fprop, 1 dgrad
+  float* out0; float* q; float* k; float* v;
+  int Cout, Cc, H, W, L, nh, dk, dkh, dvh, Nqkv; float qscale;           // fprop
+  int Cin, Hin, Win, stride, rh, rw;                                      // dgrad
+};
+
+struct __align__(1024) PGSmem {
+  bf16 a[PG_STAGES][128 * 64];
+  bf16 b[PG_STAGES][128 * 64];
+  uint64_t bar_full[PG_STAGES], bar_empty[PG_STAGES], bar_acc;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_tc_kernel(const __grid_constant__ PGParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  PGSmem& sm = *reinterpret_cast<PGSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / p.tiles_h, h0 = (blockIdx.x % p.tiles_h) * p.r;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PG_STAGES; ++s) { tc::mbar_init(&sm.bar_full[s], 1); tc::mbar_init(&sm.bar_empty[s], 1); }
+    tc::mbar_init(&sm.bar_acc, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 5) tc::tmem_alloc<512>(&sm.tmem_base);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+  const uint32_t a_bytes = (uint32_t)p.r * p.Wt * 64 * 2, b_bytes = 128 * 64 * 2;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      int it = 0;
+      for (int c = 0; c < p.nchunks; ++c) {
+        const PGChunk ch = p.chunks[c];
+        for (int s = ch.seg_begin; s < ch.seg_end; ++s) {
+          const PGSeg sg = p.segs[s];
+          for (int a = 0; a < sg.katoms; ++a, ++it) {
+            const int st = it % PG_STAGES, ph = (it / PG_STAGES) & 1;
+            tc::mbar_wait(&sm.bar_empty[st], ph ^ 1);
+            tc::mbar_arrive_expect_tx(&sm.bar_full[st], a_bytes + b_bytes);
+            tc::tma_load_4d(sm.a[st], &p.amaps[sg.amap], &sm.bar_full[st], a * 64, sg.dw, h0 + sg.dh, b);
+            tc::tma_load_2d(sm.b[st], &p.bmaps[sg.bmap], &sm.bar_full[st], a * 64, sg.brow + ch.n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::idesc_bf16_f32(128, 128);
+      int it = 0;
+      for (int c = 0; c < p.nchunks; ++c) {
+        const PGChunk ch = p.chunks[c];
+        uint32_t acc = 0;
+        for (int s = ch.seg_begin; s < ch.seg_end; ++s) {
+          const int katoms = p.segs[s].katoms;
+          for (int a = 0; a < katoms; ++a, ++it) {
+            const int st = it % PG_STAGES, ph = (it / PG_STAGES) & 1;
+            tc::mbar_wait(&sm.bar_full[st], ph);
+            tc::tc_fence_after();
+            const uint64_t da = tc::smem_desc_sw128_kmajor(smem_u32(sm.a[st]));
+            const uint64_t db = tc::smem_desc_sw128_kmajor(smem_u32(sm.b[st]));
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              tc::mma_ss(tmem + c * 128, tc::desc_advance(da, ks * 32), tc::desc_advance(db, ks * 32), idesc, acc);
+              acc = 1;
+            }
+            tc::mma_commit(&sm.bar_empty[st]);
+          }
+        }
+      }
+      tc::mma_commit(&sm.bar_acc);
+    }
+  } else {
+    // ===================== epilogue: thread == tile pixel == TMEM lane =====================
+    tc::mbar_wait(&sm.bar_acc, 0);
+    tc::tc_fence_after();
+    const int m = threadIdx.x;                       // 0..127
+    const int hh = m / p.Wt, ww = m - hh * p.Wt;
+    const int hrow = h0 + hh;
+    const bool valid = m < p.r * p.Wt && hrow < p.Ht;
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t rr[32];
+    for (int c = 0; c < p.nchunks; ++c) {
+      const PGChunk ch = p.chunks[c];
+      for (int cb = 0; cb < 4; ++cb) {
+        tc::tmem_ld_x32(tlane + c * 128 + cb * 32, rr);
+        tc::tmem_ld_wait();
+        if (!valid) continue;
+        if (p.mode == 0) {
+          const int l = hrow * p.W + ww;
+          if (ch.kind == 0) {                        // conv channels -> y NCHW (lanes = consecutive pixels: coalesced)
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int n = ch.n0 + cb * 32 + e;
+              if (n < p.Cc) p.out0[((size_t)b * p.Cout + n) * p.L + l] = __uint_as_float(rr[e]);
+            }
+          } else {                                   // qkv channels -> head-split q (scaled), k, v
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int n = ch.n0 + cb * 32 + e;
+              const float val = __uint_as_float(rr[e]);
+              if (n < p.dk) {
+                const int hd = n / p.dkh, ee = n - hd * p.dkh;
+                p.q[((size_t)(b * p.nh + hd) * p.L + l) * p.dkh + ee] = val * p.qscale;
+              } else if (n < 2 * p.dk) {
+                const int cc = n - p.dk, hd = cc / p.dkh, ee = cc - hd * p.dkh;
+                p.k[((size_t)(b * p.nh + hd) * p.L + l) * p.dkh + ee] = val;
+              } else if (n < p.Nqkv) {
+                const int cc = n - 2 * p.dk, hd = cc / p.dvh, ee = cc - hd * p.dvh;
+                p.v[((size_t)(b * p.nh + hd) * p.L + l) * p.dvh + ee] = val;
+              }
+            }
+          }
+        } else {                                     // dgrad -> dx NCHW at the pixels of this residue class
+          const int hi = hrow * p.stride + p.rh, wi = ww * p.stride + p.rw;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int n = ch.n0 + cb * 32 + e;
+            if (n < p.Cin) p.out0[(((size_t)b * p.Cin + n) * p.Hin + hi) * p.Win + wi] = __uint_as_float(rr[e]);
+          }
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tc::tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// packing kernels
+// ------------------------------------------------------------------------------------------------
+// (B, C, HW) fp32 -> (B, HW, Cp) bf16, channels [C, Cp) zero
+__global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int C, int Cp, int HW) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const float* src = in + (size_t)b * C * HW;
+  bf16* dst = out + (size_t)b * HW * Cp;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, px = p0 + threadIdx.x;
+    t[i][threadIdx.x] = (c < C && px < HW) ? src[(size_t)c * HW + px] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int px = p0 + i, c = c0 + threadIdx.x;
+    if (px < HW && c < Cp) dst[(size_t)px * Cp + c] = __float2bfloat16(t[threadIdx.x][i]);
+  }
+}
+
+int pack_nhwc_bf16(const float* in, void* out, int B, int C, int Cp, int HW, cudaStream_t st) {
+  dim3 grid(cdiv(HW, 32), cdiv(Cp, 32), B), block(32, 8);
+  nchw_to_nhwc_bf16_kernel<<<grid, block, 0, st>>>(in, static_cast<bf16*>(out), C, Cp, HW);
+  AACONV_LAUNCH_OK("pack_nhwc_bf16");
+  return 0;
+}
+
+// fprop B operand: rows [t*NPc + n] = conv_w[n, :, t] (n < Cc, else 0), then rows [T*NPc + n] = qkv_w[n, :]; K = Cin
+__global__ void pack_wf_kernel(const float* __restrict__ conv_w, const float* __restrict__ qkv_w, bf16* __restrict__ out,
+                               int Cc, int Cin, int CinK, int T, int NPc, int Nqkv, int NPq) {
+  const size_t total = ((size_t)T * NPc + NPq) * CinK;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cin = (int)(i % CinK);
+    const size_t row = i / CinK;
+    float val = 0.f;
+    if (cin >= Cin) {
+    } else if (row < (size_t)T * NPc) {
+      const int t = (int)(row / NPc), n = (int)(row - (size_t)t * NPc);
+      if (n < Cc) val = conv_w[((size_t)n * Cin + cin) * T + t];
+    } else {
+      const int n = (int)(row - (size_t)T * NPc);
+      if (n < Nqkv) val = qkv_w[(size_t)n * Cin + cin];
+    }
+    out[i] = __float2bfloat16(val);
+  }
+}
+
+// dgrad B operands: wd rows [t*CinP + cin] = conv_w[:, cin, t] over K = co (KPc cols, zero padded);
+//                   wq rows [cin] = qkv_w[:, cin] over K = n (KPq cols, zero padded)
+__global__ void pack_wd_kernel(const float* __restrict__ conv_w, const float* __restrict__ qkv_w, bf16* __restrict__ wd,
+                               bf16* __restrict__ wq, int Cc, int Cin, int T, int CinP, int KPc, int Nqkv, int KPq) {
+  const size_t n1 = (size_t)T * CinP * KPc, n2 = (size_t)CinP * KPq;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < n1) {
+      const int co = (int)(i % KPc);
+      const size_t row = i / KPc;
+      const int t = (int)(row / CinP), cin = (int)(row - (size_t)t * CinP);
+      wd[i] = __float2bfloat16((co < Cc && cin < Cin) ? conv_w[((size_t)co * Cin + cin) * T + t] : 0.f);
+    } else {
+      const size_t j = i - n1;
+      const int n = (int)(j % KPq), cin = (int)(j / KPq);
+      wq[j] = __float2bfloat16((n < Nqkv && cin < Cin) ? qkv_w[(size_t)n * Cin + cin] : 0.f);
+    }
+  }
+}
+
+// dqkv (B*L, KPq) bf16 = concat(dq * qscale, dk, dv) from the head-split fp32 gradients
+__global__ void pack_dqkv_kernel(const float* __restrict__ dq, const float* __restrict__ dk, const float* __restrict__ dv,
+                                 bf16* __restrict__ out, size_t pixels, int L, int nh, int dk_, int dkh, int dvh, int Nqkv,
+                                 int KPq, float qscale) {
+  const size_t total = pixels * KPq;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i % KPq);
+    const size_t pix = i / KPq;
+    const int b = (int)(pix / L), l = (int)(pix - (size_t)b * L);
+    float val = 0.f;
+    if (n < dk_) {
+      const int h = n / dkh, e = n - h * dkh;
+      val = dq[((size_t)(b * nh + h) * L + l) * dkh + e] * qscale;
+    } else if (n < 2 * dk_) {
+      const int c = n - dk_, h = c / dkh, e = c - h * dkh;
+      val = dk[((size_t)(b * nh + h) * L + l) * dkh + e];
+    } else if (n < Nqkv) {
+      const int c = n - 2 * dk_, h = c / dvh, e = c - h * dvh;
+      val = dv[((size_t)(b * nh + h) * L + l) * dvh + e];
+    }
+    out[i] = __float2bfloat16(val);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: geometry, buffers, launches
+// ------------------------------------------------------------------------------------------------
+static int rows_per_tile(int Wt, int Ht) {
+  int r = 128 / Wt;
+  if (r > Ht) r = Ht;
+  return r;
+}
+
+int tc_gemm_supported(const Dims& d) {
+  if (d.stride > 2 || d.dil != 1) return fail(AACONV_E_UNSUPPORTED, "tcgen05 conv path supports stride 1|2, dilation 1");
+  if (d.W > 128 || cdiv(d.Win, d.stride) > 128) return fail(AACONV_E_UNSUPPORTED, "tcgen05 conv path needs rows of <= 128 pixels");
+  if (d.ks * d.ks + 1 > PG_MAX_SEGS) return fail(AACONV_E_UNSUPPORTED, "kernel_size too large for the tcgen05 conv path");
+  return 0;
+}
+
+TcGemmBufs tc_gemm_bufs(const Dims& d, void* base) {
+  TcGemmBufs t;
+  Carver c(base);
+  const int T = d.ks * d.ks;
+  t.NPc = cdiv(d.Cc, 128) * 128;
+  t.NPq = cdiv(d.Nqkv, 128) * 128;
+  t.CinP = cdiv(d.Cin, 128) * 128;
+  t.CinK = cdiv(d.Cin, 64) * 64;
+  t.KPc = cdiv(d.Cout, 64) * 64;       // dy is packed with all Cout channels; weight rows past Cc are zero
+  t.KPq = cdiv(d.Nqkv, 64) * 64;
+  t.xh = c.take<uint16_t>((size_t)d.B * d.Hin * d.Win * t.CinK);
+  t.dyh = c.take<uint16_t>((size_t)d.B * d.L * t.KPc);
+  t.dqkvh = c.take<uint16_t>((size_t)d.B * d.L * t.KPq);
+  t.wf = c.take<uint16_t>(((size_t)T * t.NPc + t.NPq) * t.CinK);
+  t.wd = c.take<uint16_t>((size_t)T * t.CinP * t.KPc);
+  t.wq = c.take<uint16_t>((size_t)t.CinP * t.KPq);
+  t.bytes = c.off;
+  return t;
+}
+
+static int launch_pg(const PGParams& p, int B, cudaStream_t st, const char* name) {
+  const size_t smem = sizeof(PGSmem) + 1024;
+  AACONV_CUDA_OK(cudaFuncSetAttribute(pixel_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pixel_gemm_tc_kernel<<<B * p.tiles_h, PG_THREADS, smem, st>>>(p);
+  AACONV_LAUNCH_OK(name);
+  return 0;
+}
+
+// channels-last 4D map over the pixels of one residue class (ph, pw) of an (B, Hs, Ws, C) tensor
+static int make_nhwc_map(CUtensorMap* out, const void* base, int B, int Hs, int Ws, int C, int s, int ph, int pw, int r,
+                         int Wt) {
+  const int Hc = Hs > ph ? (Hs - ph + s - 1) / s : 0, Wc = Ws > pw ? (Ws - pw + s - 1) / s : 0;
+  const uint64_t dims[4] = {(uint64_t)C, (uint64_t)std::max(Wc, 1), (uint64_t)std::max(Hc, 1), (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)s * C * 2, (uint64_t)s * Ws * C * 2, (uint64_t)Hs * Ws * C * 2};
+  const uint32_t box[4] = {64, (uint32_t)Wt, (uint32_t)r, 1};
+  const char* p = static_cast<const char*>(base) + ((size_t)ph * Ws + pw) * C * 2;
+  return make_tmap_bf16(out, p, 4, dims, strides, box, nullptr);
+}
+
+static int make_2d_map(CUtensorMap* out, const void* base, int K, size_t rows) {
+  const uint64_t dims[2] = {(uint64_t)K, (uint64_t)rows};
+  const uint64_t strides[1] = {(uint64_t)K * 2};
+  const uint32_t box[2] = {64, 128};
+  return make_tmap_bf16(out, base, 2, dims, strides, box, nullptr);
+}
+
+static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// conv fprop + qkv projection.  y: conv channels of (B,Cout,H,W); q,k,v head-split fp32.
+int tc_fprop(const Dims& d, const TcGemmBufs& t, const float* x, const float* conv_w, const float* qkv_w, float* y,
+             float* q, float* k, float* v, cudaStream_t st) {
+  const int T = d.ks * d.ks, s = d.stride;
+  AACONV_TRY(pack_nhwc_bf16(x, t.xh, d.B, d.Cin, t.CinK, d.Hin * d.Win, st));
+  pack_wf_kernel<<<148 * 4, 256, 0, st>>>(conv_w, qkv_w, static_cast<bf16*>(t.wf), d.Cc, d.Cin, t.CinK, T, t.NPc, d.Nqkv,
+                                           t.NPq);
+  AACONV_LAUNCH_OK("pack_wf");
+
+  PGParams p;
+  memset(&p, 0, sizeof p);
+  p.Wt = d.W; p.Ht = d.H; p.r = rows_per_tile(d.W, d.H); p.tiles_h = cdiv(d.H, p.r);
+  for (int ph = 0; ph < s; ++ph)
+    for (int pw = 0; pw < s; ++pw)
+      AACONV_TRY(make_nhwc_map(&p.amaps[ph * s + pw], t.xh, d.B, d.Hin, d.Win, t.CinK, s, ph, pw, p.r, p.Wt));
+  AACONV_TRY(make_2d_map(&p.bmaps[0], t.wf, t.CinK, (size_t)T * t.NPc + t.NPq));
+  const int katoms = t.CinK / 64;
+  int ns = 0;
+  for (int kh = 0; kh < d.ks; ++kh)
+    for (int kw = 0; kw < d.ks; ++kw) {          // input row = s*i + (kh - pad): residue + whole-pixel shift
+      const int th = kh - d.pad, tw = kw - d.pad;
+      const int ph = ((th % s) + s) % s, pw = ((tw % s) + s) % s;
+      p.segs[ns++] = {ph * s + pw, floordiv(tw - pw, s), floordiv(th - ph, s), katoms, 0, (kh * d.ks + kw) * t.NPc};
+    }
+  const int seg_qkv = ns;
+  p.segs[ns++] = {0, 0, 0, katoms, 0, T * t.NPc};
+  p.mode = 0; p.out0 = y; p.q = q; p.k = k; p.v = v;
+  p.Cout = d.Cout; p.Cc = d.Cc; p.H = d.H; p.W = d.W; p.L = d.L; p.nh = d.nh; p.dk = d.dk; p.dkh = d.dkh; p.dvh = d.dvh;
+  p.Nqkv = d.Nqkv; p.qscale = d.qscale;
+  // accumulator chunks, up to PG_MAX_CHUNKS per launch
+  struct C { int n0, kind; };
+  std::vector<C> all;
+  for (int n0 = 0; n0 < d.Cc; n0 += 128) all.push_back({n0, 0});
+  for (int n0 = 0; n0 < d.Nqkv; n0 += 128) all.push_back({n0, 1});
+  for (size_t i = 0; i < all.size(); i += PG_MAX_CHUNKS) {
+    p.nchunks = (int)std::min<size_t>(PG_MAX_CHUNKS, all.size() - i);
+    for (int c = 0; c < p.nchunks; ++c) {
+      const C& a = all[i + c];
+      p.chunks[c] = a.kind == 0 ? PGChunk{a.n0, 0, T, 0} : PGChunk{a.n0, seg_qkv, seg_qkv + 1, 1};
+    }
+    AACONV_TRY(launch_pg(p, d.B, st, "conv_qkv_fprop_tc"));
+  }
+  return 0;
+}
+
+// dx = conv dgrad + qkv dgrad.  dq,dk,dv head-split fp32 (dq w.r.t. the scaled q).
+int tc_dgrad(const Dims& d, const TcGemmBufs& t, const float* dy, const float* conv_w, const float* qkv_w,
+             const float* dq, const float* dk, const float* dv, float* dx, cudaStream_t st) {
+  const int T = d.ks * d.ks, s = d.stride;
+  AACONV_TRY(pack_nhwc_bf16(dy, t.dyh, d.B, d.Cout, t.KPc, d.L, st));
+  pack_wd_kernel<<<148 * 4, 256, 0, st>>>(conv_w, qkv_w, static_cast<bf16*>(t.wd), static_cast<bf16*>(t.wq), d.Cc, d.Cin, T,
+                                           t.CinP, t.KPc, d.Nqkv, t.KPq);
+  AACONV_LAUNCH_OK("pack_wd");
+  pack_dqkv_kernel<<<148 * 8, 256, 0, st>>>(dq, dk, dv, static_cast<bf16*>(t.dqkvh), (size_t)d.B * d.L, d.L, d.nh, d.dk,
+                                             d.dkh, d.dvh, d.Nqkv, t.KPq, d.qscale);
+  AACONV_LAUNCH_OK("pack_dqkv");
+
+  for (int rh = 0; rh < s; ++rh)
+    for (int rw = 0; rw < s; ++rw) {
+      const int Hc = d.Hin > rh ? (d.Hin - rh + s - 1) / s : 0, Wc = d.Win > rw ? (d.Win - rw + s - 1) / s : 0;
+      if (Hc == 0 || Wc == 0) continue;
+      PGParams p;
+      memset(&p, 0, sizeof p);
+      p.Wt = Wc; p.Ht = Hc; p.r = rows_per_tile(Wc, Hc); p.tiles_h = cdiv(Hc, p.r);
+      AACONV_TRY(make_nhwc_map(&p.amaps[0], t.dyh, d.B, d.H, d.W, t.KPc, 1, 0, 0, p.r, p.Wt));
+      AACONV_TRY(make_nhwc_map(&p.amaps[1], t.dqkvh, d.B, d.H, d.W, t.KPq, 1, 0, 0, p.r, p.Wt));
+      AACONV_TRY(make_2d_map(&p.bmaps[0], t.wd, t.KPc, (size_t)T * t.CinP));
+      AACONV_TRY(make_2d_map(&p.bmaps[1], t.wq, t.KPq, (size_t)t.CinP));
+      int ns = 0;
+      if (d.Cc)
+        for (int kh = 0; kh < d.ks; ++kh)
+          for (int kw = 0; kw < d.ks; ++kw) {    // input pixel h = s*hc + rh receives dy[(h + pad - kh)/s] when divisible
+            const int nh_ = rh + d.pad - kh, nw_ = rw + d.pad - kw;
+            if (((nh_ % s) + s) % s || ((nw_ % s) + s) % s) continue;
+            p.segs[ns++] = {0, floordiv(nw_, s), floordiv(nh_, s), t.KPc / 64, 0, (kh * d.ks + kw) * t.CinP};
+          }
+      if (rh == 0 && rw == 0) p.segs[ns++] = {1, 0, 0, t.KPq / 64, 1, 0};   // 1x1 stride-s projection touches class (0,0)
+      p.mode = 1; p.out0 = dx; p.Cin = d.Cin; p.Hin = d.Hin; p.Win = d.Win; p.stride = s; p.rh = rh; p.rw = rw;
+      if (ns == 0) {   // no tap reaches this class (e.g. 1x1 conv with stride 2): gradient is zero there
+        AACONV_TRY(tc_zero_class(d, dx, rh, rw, st));
+        continue;
+      }
+      for (int n0 = 0; n0 < d.Cin; n0 += 128 * PG_MAX_CHUNKS) {
+        p.nchunks = std::min(PG_MAX_CHUNKS, cdiv(d.Cin - n0, 128));
+        for (int c = 0; c < p.nchunks; ++c) p.chunks[c] = {n0 + c * 128, 0, ns, 0};
+        AACONV_TRY(launch_pg(p, d.B, st, "conv_qkv_dgrad_tc"));
+      }
+    }
+  return 0;
+}
+
+__global__ void zero_class_kernel(float* __restrict__ dx, size_t planes, int Hin, int Win, int s, int rh, int rw) {
+  const int Hc = (Hin - rh + s - 1) / s, Wc = (Win - rw + s - 1) / s;
+  const size_t total = planes * Hc * Wc;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int wc = (int)(i % Wc);
+    const size_t t = i / Wc;
+    const int hc = (int)(t % Hc);
+    const size_t pl = t / Hc;
+    dx[(pl * Hin + hc * s + rh) * Win + wc * s + rw] = 0.f;
+  }
+}
+
+int tc_zero_class(const Dims& d, float* dx, int rh, int rw, cudaStream_t st) {
+  zero_class_kernel<<<148 * 4, 256, 0, st>>>(dx, (size_t)d.B * d.Cin, d.Hin, d.Win, d.stride, rh, rw);
+  AACONV_LAUNCH_OK("zero_class");
+  return 0;
+}
+
+}  // namespace aaconv
