@@ -1,5 +1,6 @@
 // Orchestration of the bf16 tensor-core path.  Stages not yet moved to tcgen05 run the fp32 FFMA kernels
 // (same layouts), so the path is always complete; DESIGN.md lists which stage runs where.
+#include <algorithm>
 #include <cstring>
 #include "bf16_path.cuh"
 #include "fp32_path.cuh"
@@ -22,7 +23,7 @@ struct Scratch {
     dq = c.take<float>(rows * d.dkh);
     dk = c.take<float>(rows * d.dkh);
     dv = c.take<float>(rows * d.dvh);
-    partial = c.take<float>(f32_partial_floats(d));
+    partial = c.take<float>(std::max(f32_partial_floats(d), tc_gemm_supported(d) == 0 ? tc_wgrad_partial_floats(d) : 0));
     dqa = c.take<float>(rows * a.KD);
     qa = c.take<uint16_t>(rows * a.KP);
     ka = c.take<uint16_t>(rows * a.KP);
@@ -97,9 +98,17 @@ int bf16_backward(const Dims& d, const float* x, const aaconv_params* p, const f
   }
   AACONV_TRY(aug_bwd_dq(d, w.dqa, p->key_rel_w, p->key_rel_h, w.dq, st));
   if (w.gemm_ok) {
-    if (dx) AACONV_TRY(tc_dgrad(d, w.gemm, dy, p->conv_w, p->qkv_w, w.dq, w.dk, w.dv, dx, st));
-    if (d.Cc) AACONV_TRY(f32_conv_bwd(d, x, p->conv_w, dy, nullptr, g->conv_w, w.partial, st));
-    AACONV_TRY(f32_qkv_bwd(d, x, p->qkv_w, w.dq, w.dk, w.dv, g->qkv_w, nullptr, 0, w.partial, st));
+    AACONV_TRY(tc_pack_grads(d, w.gemm, dy, w.dq, w.dk, w.dv, st));
+    if (dx) AACONV_TRY(tc_dgrad(d, w.gemm, p->conv_w, p->qkv_w, dx, st));
+    if (g->conv_w || g->qkv_w) {
+      if (tc_wgrad_supported(d) == 0) {
+        AACONV_TRY(pack_nhwc_bf16(x, w.gemm.xh, d.B, d.Cin, w.gemm.CinK, d.Hin * d.Win, st));
+        AACONV_TRY(tc_wgrad(d, w.gemm, d.Cc ? g->conv_w : nullptr, g->qkv_w, w.partial, st));
+      } else {
+        if (d.Cc) AACONV_TRY(f32_conv_bwd(d, x, p->conv_w, dy, nullptr, g->conv_w, w.partial, st));
+        AACONV_TRY(f32_qkv_bwd(d, x, p->qkv_w, w.dq, w.dk, w.dv, g->qkv_w, nullptr, 0, w.partial, st));
+      }
+    }
     return 0;
   }
   if (d.Cc) {

@@ -38,9 +38,13 @@ TcGemmBufs tc_gemm_bufs(const Dims& d, void* base);
 int pack_nhwc_bf16(const float* in, void* out, int B, int C, int Cp, int HW, cudaStream_t st);
 int tc_fprop(const Dims& d, const TcGemmBufs& t, const float* x, const float* conv_w, const float* qkv_w, float* y,
              float* q, float* k, float* v, cudaStream_t st);
-int tc_dgrad(const Dims& d, const TcGemmBufs& t, const float* dy, const float* conv_w, const float* qkv_w,
-             const float* dq, const float* dk, const float* dv, float* dx, cudaStream_t st);
+int tc_pack_grads(const Dims& d, const TcGemmBufs& t, const float* dy, const float* dq, const float* dk, const float* dv,
+                  cudaStream_t st);
+int tc_dgrad(const Dims& d, const TcGemmBufs& t, const float* conv_w, const float* qkv_w, float* dx, cudaStream_t st);
 int tc_zero_class(const Dims& d, float* dx, int rh, int rw, cudaStream_t st);
+int tc_wgrad_supported(const Dims& d);
+size_t tc_wgrad_partial_floats(const Dims& d);
+int tc_wgrad(const Dims& d, const TcGemmBufs& t, float* dwc, float* dwq, float* partial, cudaStream_t st);
 
 // fp32_gemms.cu
 int aug_rel_weight_grad(const Dims& d, const float* q, const float* dqa, int KD, int axis, float* dkr, float* partial,

@@ -363,18 +363,22 @@ int tc_fprop(const Dims& d, const TcGemmBufs& t, const float* x, const float* co
   return 0;
 }
 
-// dx = conv dgrad + qkv dgrad.  dq,dk,dv head-split fp32 (dq w.r.t. the scaled q).
-int tc_dgrad(const Dims& d, const TcGemmBufs& t, const float* dy, const float* conv_w, const float* qkv_w,
-             const float* dq, const float* dk, const float* dv, float* dx, cudaStream_t st) {
-  const int T = d.ks * d.ks, s = d.stride;
+// packed backward operands shared by dgrad and wgrad: dyh (B,L,KPc) and dqkvh (B,L,KPq) = concat(dq*scale, dk, dv)
+int tc_pack_grads(const Dims& d, const TcGemmBufs& t, const float* dy, const float* dq, const float* dk, const float* dv,
+                  cudaStream_t st) {
   AACONV_TRY(pack_nhwc_bf16(dy, t.dyh, d.B, d.Cout, t.KPc, d.L, st));
-  pack_wd_kernel<<<148 * 4, 256, 0, st>>>(conv_w, qkv_w, static_cast<bf16*>(t.wd), static_cast<bf16*>(t.wq), d.Cc, d.Cin, T,
-                                           t.CinP, t.KPc, d.Nqkv, t.KPq);
-  AACONV_LAUNCH_OK("pack_wd");
   pack_dqkv_kernel<<<148 * 8, 256, 0, st>>>(dq, dk, dv, static_cast<bf16*>(t.dqkvh), (size_t)d.B * d.L, d.L, d.nh, d.dk,
                                              d.dkh, d.dvh, d.Nqkv, t.KPq, d.qscale);
   AACONV_LAUNCH_OK("pack_dqkv");
+  return 0;
+}
 
+// dx = conv dgrad + qkv dgrad (needs tc_pack_grads first).
+int tc_dgrad(const Dims& d, const TcGemmBufs& t, const float* conv_w, const float* qkv_w, float* dx, cudaStream_t st) {
+  const int T = d.ks * d.ks, s = d.stride;
+  pack_wd_kernel<<<148 * 4, 256, 0, st>>>(conv_w, qkv_w, static_cast<bf16*>(t.wd), static_cast<bf16*>(t.wq), d.Cc, d.Cin, T,
+                                           t.CinP, t.KPc, d.Nqkv, t.KPq);
+  AACONV_LAUNCH_OK("pack_wd");
   for (int rh = 0; rh < s; ++rh)
     for (int rw = 0; rw < s; ++rw) {
       const int Hc = d.Hin > rh ? (d.Hin - rh + s - 1) / s : 0, Wc = d.Win > rw ? (d.Win - rw + s - 1) / s : 0;
@@ -424,6 +428,214 @@ __global__ void zero_class_kernel(float* __restrict__ dx, size_t planes, int Hin
 int tc_zero_class(const Dims& d, float* dx, int rh, int rw, cudaStream_t st) {
   zero_class_kernel<<<148 * 4, 256, 0, st>>>(dx, (size_t)d.B * d.Cin, d.Hin, d.Win, d.stride, rh, rw);
   AACONV_LAUNCH_OK("zero_class");
+  return 0;
+}
+
+}  // namespace aaconv
+
+// ================================================================================================
+// wgrad: dW[m, n] = sum_pixels A[pixel, m] * B[pixel, n]   (A = dy or dqkv, B = x at one tap)
+// Both operands are channels-last, i.e. MN-major for this contraction: a K-chunk of kr x W pixels is one TMA
+// box per 64-channel atom, [pixels x 128 B], consumed through MN-major UMMA descriptors.  Split-K over pixel
+// chunks; partial tiles are summed by a second kernel in a fixed order (deterministic).
+// ================================================================================================
+namespace aaconv {
+
+constexpr int WG_THREADS = 192;
+constexpr int WG_STAGES = 2;
+constexpr int WG_KMAX = 128;        // pixels per K-chunk (rows of the smem tiles)
+constexpr int WG_N = 256;           // accumulator width (input channels per task)
+
+struct WGTap { int bmap, dw, dh; };
+struct WGShape {                    // task index -> (n chunk, conv (m chunk, tap) | qkv m chunk)
+  int conv_m, T, qkv_m, n_chunks, CinK;
+  __host__ __device__ int per_n() const { return conv_m * T + qkv_m; }
+  __host__ __device__ int ntasks() const { return per_n() * n_chunks; }
+  __host__ __device__ void decode(int task, int& kind, int& m0, int& tap, int& n0, int& nn) const {
+    const int nc = task / per_n(), r = task - nc * per_n();
+    n0 = nc * WG_N;
+    nn = min(WG_N, CinK - n0);
+    if (r < conv_m * T) { kind = 0; m0 = (r / T) * 128; tap = r % T; }
+    else { kind = 1; m0 = (r - conv_m * T) * 128; tap = 0; }
+  }
+};
+struct WGParams {
+  CUtensorMap amaps[2];
+  CUtensorMap bmaps[4];
+  WGTap taps[16];
+  WGShape shape;
+  int kr, Wt, kpix, chunks_per_image, nchunks_total, chunks_per_split;
+  float* partial;
+};
+
+struct __align__(1024) WGSmem {
+  bf16 a[WG_STAGES][2][WG_KMAX * 64];
+  bf16 b[WG_STAGES][4][WG_KMAX * 64];
+  uint64_t bar_full[WG_STAGES], bar_empty[WG_STAGES], bar_acc;
+  uint32_t tmem_base;
+};
+
+__host__ __device__ constexpr uint32_t idesc_mn_mn(int M, int N) { return tc::idesc_bf16_f32(M, N) | (1u << 15) | (1u << 16); }
+
+__device__ __forceinline__ uint64_t desc_mn_tile(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WGParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  WGSmem& sm = *reinterpret_cast<WGSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int kind, m0, tap, n0, nn;
+  p.shape.decode(blockIdx.x, kind, m0, tap, n0, nn);
+  const WGTap tp = kind == 0 ? p.taps[tap] : p.taps[15];     // slot 15: the 1x1 strided projection
+  const int split = blockIdx.y;
+  const int g0 = split * p.chunks_per_split, g1 = min(p.nchunks_total, g0 + p.chunks_per_split);
+  const int natoms_b = nn >> 6;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) { tc::mbar_init(&sm.bar_full[s], 1); tc::mbar_init(&sm.bar_empty[s], 1); }
+    tc::mbar_init(&sm.bar_acc, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 5) tc::tmem_alloc<256>(&sm.tmem_base);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+  const uint32_t atom_bytes = (uint32_t)p.kpix * 128;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int g = g0, it = 0; g < g1; ++g, ++it) {
+        const int st = it % WG_STAGES, ph = (it / WG_STAGES) & 1;
+        const int b = g / p.chunks_per_image, h0 = (g % p.chunks_per_image) * p.kr;
+        tc::mbar_wait(&sm.bar_empty[st], ph ^ 1);
+        tc::mbar_arrive_expect_tx(&sm.bar_full[st], atom_bytes * (2 + natoms_b));
+        for (int a = 0; a < 2; ++a) tc::tma_load_4d(sm.a[st][a], &p.amaps[kind], &sm.bar_full[st], m0 + a * 64, 0, h0, b);
+        for (int a = 0; a < natoms_b; ++a)
+          tc::tma_load_4d(sm.b[st][a], &p.bmaps[tp.bmap], &sm.bar_full[st], n0 + a * 64, tp.dw, h0 + tp.dh, b);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_mn_mn(128, nn);
+      const int ksteps = p.kpix >> 4;
+      uint32_t acc = 0;
+      for (int g = g0, it = 0; g < g1; ++g, ++it) {
+        const int st = it % WG_STAGES, ph = (it / WG_STAGES) & 1;
+        tc::mbar_wait(&sm.bar_full[st], ph);
+        tc::tc_fence_after();
+        const uint32_t a0 = smem_u32(sm.a[st][0]), b0 = smem_u32(sm.b[st][0]);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          tc::mma_ss(tmem, desc_mn_tile(a0 + ks * 2048, WG_KMAX * 128), desc_mn_tile(b0 + ks * 2048, WG_KMAX * 128), idesc, acc);
+          acc = 1;
+        }
+        tc::mma_commit(&sm.bar_empty[st]);
+      }
+      tc::mma_commit(&sm.bar_acc);
+    }
+  } else {
+    float* out = p.partial + ((size_t)(split * gridDim.x + blockIdx.x) * 128 + threadIdx.x) * WG_N;
+    if (g0 < g1) {
+      tc::mbar_wait(&sm.bar_acc, 0);
+      tc::tc_fence_after();
+      const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+      uint32_t rr[32];
+      for (int cb = 0; cb < nn / 32; ++cb) {
+        tc::tmem_ld_x32(tlane + cb * 32, rr);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; e += 4)
+          *reinterpret_cast<float4*>(out + cb * 32 + e) =
+              make_float4(__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3]));
+      }
+    } else {   // empty split: contributes zeros
+      for (int e = 0; e < nn; e += 4) *reinterpret_cast<float4*>(out + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tc::tmem_dealloc<256>(tmem);
+}
+
+// sum the split-K partials into the parameter-gradient layouts
+//   conv task (tap t, m0, n0): dWc[(co*Cin + cin)*T + t];   qkv task (m0, n0): dWq[n*Cin + cin]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, WGShape shape, int splits, float* __restrict__ dwc,
+                                    float* __restrict__ dwq, int Cc, int Cin, int Nqkv) {
+  const int task = blockIdx.y, ntasks = gridDim.y;
+  int kind, m0, tap, n0, nn;
+  shape.decode(task, kind, m0, tap, n0, nn);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 128 * WG_N; i += gridDim.x * blockDim.x) {
+    const int m = m0 + i / WG_N, nl = i % WG_N, n = n0 + nl;
+    if (nl >= nn || n >= Cin || m >= (kind == 0 ? Cc : Nqkv)) continue;
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += partial[((size_t)(sp * ntasks + task) * 128) * WG_N + i];
+    if (kind == 0) dwc[((size_t)m * Cin + n) * shape.T + tap] = s;
+    else dwq[(size_t)m * Cin + n] = s;
+  }
+}
+
+static int wgrad_kr(int W) {
+  int best = 0;
+  for (int kr = 1; kr * W <= WG_KMAX; ++kr)
+    if ((kr * W) % 16 == 0) best = kr;
+  return best;
+}
+
+int tc_wgrad_supported(const Dims& d) {
+  if (tc_gemm_supported(d)) return AACONV_E_UNSUPPORTED;
+  if (wgrad_kr(d.W) == 0) return fail(AACONV_E_UNSUPPORTED, "no pixel chunk of W=%d rows is a multiple of 16 within 128", d.W);
+  return 0;
+}
+
+size_t tc_wgrad_partial_floats(const Dims& d) {
+  const int T = d.ks * d.ks, nch = cdiv(d.Cin, WG_N);
+  const int ntasks = (cdiv(d.Cc, 128) * T + cdiv(d.Nqkv, 128)) * nch;
+  return (size_t)std::max(ntasks, 148) * 128 * WG_N;
+}
+
+// xh, dyh (and dqkvh when dwq != NULL) must already hold the packed operands of this step.
+int tc_wgrad(const Dims& d, const TcGemmBufs& t, float* dwc, float* dwq, float* partial, cudaStream_t st) {
+  const int T = d.ks * d.ks, s = d.stride;
+  WGParams p;
+  memset(&p, 0, sizeof p);
+  p.kr = wgrad_kr(d.W); p.Wt = d.W; p.kpix = p.kr * d.W;
+  p.chunks_per_image = cdiv(d.H, p.kr); p.nchunks_total = d.B * p.chunks_per_image;
+  AACONV_TRY(make_nhwc_map(&p.amaps[0], t.dyh, d.B, d.H, d.W, t.KPc, 1, 0, 0, p.kr, p.Wt));
+  AACONV_TRY(make_nhwc_map(&p.amaps[1], t.dqkvh, d.B, d.H, d.W, t.KPq, 1, 0, 0, p.kr, p.Wt));
+  for (int ph = 0; ph < s; ++ph)
+    for (int pw = 0; pw < s; ++pw)
+      AACONV_TRY(make_nhwc_map(&p.bmaps[ph * s + pw], t.xh, d.B, d.Hin, d.Win, t.CinK, s, ph, pw, p.kr, p.Wt));
+  for (int kh = 0; kh < d.ks; ++kh)
+    for (int kw = 0; kw < d.ks; ++kw) {
+      const int th = kh - d.pad, tw = kw - d.pad;
+      const int ph = ((th % s) + s) % s, pw = ((tw % s) + s) % s;
+      p.taps[kh * d.ks + kw] = {ph * s + pw, floordiv(tw - pw, s), floordiv(th - ph, s)};
+    }
+  p.taps[15] = {0, 0, 0};
+  p.shape.conv_m = (dwc && d.Cc) ? cdiv(d.Cc, 128) : 0;
+  p.shape.T = T;
+  p.shape.qkv_m = dwq ? cdiv(d.Nqkv, 128) : 0;
+  p.shape.n_chunks = cdiv(d.Cin, WG_N);
+  p.shape.CinK = t.CinK;
+  const int nt = p.shape.ntasks();
+  if (nt == 0) return 0;
+  int splits = std::max(1, 148 / nt);
+  p.chunks_per_split = cdiv(p.nchunks_total, splits);
+  splits = cdiv(p.nchunks_total, p.chunks_per_split);
+  p.partial = partial;
+  const size_t smem = sizeof(WGSmem) + 1024;
+  AACONV_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  wgrad_tc_kernel<<<dim3(nt, splits), WG_THREADS, smem, st>>>(p);
+  AACONV_LAUNCH_OK("conv_qkv_wgrad_tc");
+  wgrad_reduce_kernel<<<dim3(16, nt), 256, 0, st>>>(partial, p.shape, splits, dwc, dwq, d.Cc, d.Cin, d.Nqkv);
+  AACONV_LAUNCH_OK("wgrad_reduce");
   return 0;
 }
 
