@@ -1,0 +1,96 @@
+"""Data-parallel training plumbing: one process per GPU, batch sharded across ranks, gradients exchanged as flat
+buckets with an NCCL all-reduce that overlaps the rest of backward.
+
+The reference is single-process / single-device (chexpert.py:38,453); this is the one new subsystem SURVEY.md
+section 8(e) asks for.  The batch dimension is the only shard: every AAConv2d kernel runs unsharded on its rank.
+
+Design (deliberately small, no torch DDP wrapper):
+  * parameters are laid out, in REVERSE registration order (the order backward produces gradients), into flat
+    fp32 buckets of ~``bucket_mb``; ``p.grad`` of every parameter is a view into its bucket, so autograd accumulates
+    straight into the communication buffer and no gather/scatter copies exist;
+  * a post-accumulate hook per parameter counts the bucket down; the last one issues ``all_reduce(async_op=True)``,
+    which NCCL runs on its own stream over NVLink 5 / NVSwitch while backward continues on the compute stream;
+  * ``finish()`` waits for the outstanding work and scales by 1/world (mean over the global batch, the reference's
+    ``.mean(0)``, chexpert.py:160).
+Works with the gloo backend on CPU, which is how tests/ covers world_size 2 without GPUs.
+"""
+import torch
+import torch.distributed as dist
+
+
+class GradientBuckets:
+    def __init__(self, module, bucket_mb=25.0, process_group=None, broadcast_from=0):
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        if not self.params:
+            raise ValueError('module has no trainable parameters')
+        if self.world > 1 and broadcast_from is not None:   # identical replicas before the first step
+            for t in list(module.parameters()) + list(module.buffers()):
+                dist.broadcast(t.data, broadcast_from, group=process_group)
+        cap = max(1, int(bucket_mb * (1 << 20) / 4))
+        self.buckets = []          # (flat tensor, [params])
+        self._bucket_of = {}
+        self._view = {}
+        cur, cur_n = [], 0
+        for p in reversed(self.params):
+            if cur and cur_n + p.numel() > cap:
+                self._seal(cur)
+                cur, cur_n = [], 0
+            cur.append(p)
+            cur_n += p.numel()
+        if cur:
+            self._seal(cur)
+        self._pending = [0] * len(self.buckets)
+        self._works = []
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self.reset()
+
+    def _seal(self, params):
+        dev = params[0].device
+        flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+        off = 0
+        for p in params:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise ValueError('GradientBuckets expects fp32 master parameters on one device')
+            self._view[p] = p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+            self._bucket_of[p] = len(self.buckets)
+        self.buckets.append((flat, params))
+
+    def reset(self):
+        """Zero the buckets (replaces optimizer.zero_grad(); keeps the grad views alive)."""
+        for flat, _ in self.buckets:
+            flat.zero_()
+        self._pending = [len(ps) for _, ps in self.buckets]
+        self._works = []
+
+    def _on_grad(self, p):
+        b = self._bucket_of[p]
+        view = self._view[p]
+        if p.grad.data_ptr() != view.data_ptr():     # someone replaced .grad (e.g. set_to_none): copy back in
+            view.copy_(p.grad)
+            p.grad = view
+        self._pending[b] -= 1
+        if self._pending[b] == 0 and self.world > 1:
+            self._works.append(dist.all_reduce(self.buckets[b][0], group=self.group, async_op=True))
+
+    def finish(self):
+        """Wait for the exchange and turn sums into means.  Call after backward(), before optimizer.step()."""
+        if self.world > 1:
+            for b, n in enumerate(self._pending):     # parameters that received no gradient this step
+                if n > 0:
+                    self._works.append(dist.all_reduce(self.buckets[b][0], group=self.group, async_op=True))
+            for w in self._works:
+                w.wait()
+            for flat, _ in self.buckets:
+                flat.div_(self.world)
+        self._works = []
+
+    @property
+    def nbytes(self):
+        return sum(f.numel() * 4 for f, _ in self.buckets)
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()

@@ -121,3 +121,98 @@ def test_bce_raw_uones_labels():
     want, _ = O.bce_train_loss(z, t)
     got = cb.BCEWithLogitsLoss('train', raw_labels=True)(z.cuda(), raw.cuda())
     assert torch.allclose(got.cpu(), want, rtol=1e-5)
+
+
+# bf16 tensor-core mode: north_star tolerance rtol 2e-2 / atol 1e-2 (element-wise, torch.allclose semantics) on outputs
+# and gradients.  Gradient tensors are mostly far below 1e-2 in magnitude, which would make that check vacuous for
+# them, so they additionally have to stay within BF16_REL_TO_MAX of the tensor's max-abs value.
+BF16_RTOL, BF16_ATOL, BF16_REL_TO_MAX = 2e-2, 1e-2, 4e-2
+
+
+def _bf16_close(got, want, what):
+    got, want = got.double().cpu(), want.double()
+    assert torch.allclose(got, want, rtol=BF16_RTOL, atol=BF16_ATOL), f'{what}: allclose(rtol 2e-2, atol 1e-2) failed'
+    assert rel_err(got, want) < BF16_REL_TO_MAX, f'{what}: {rel_err(got, want):.3e} of max'
+
+
+@pytest.mark.parametrize('name', golden_cases('f64'))
+def test_bf16_matches_reference_fixture(name):
+    s, p, g, t = load_case(name, 'f64')
+    m = _module(s, p, 'bf16')
+    x = t['x'].float().cuda().requires_grad_(True)
+    y, w = m(x, return_attn=True)
+    y.backward(t['dy'].float().cuda())
+    _bf16_close(y, t['y'], 'y')
+    _bf16_close(w, t['weights'], 'weights')
+    _bf16_close(x.grad, g['x'], 'dx')
+    for n, prm in m.named_parameters():
+        _bf16_close(prm.grad, g[n], n)
+
+
+@pytest.mark.parametrize('tag,shape,B,hin', [
+    ('T3', O.AAConvShape(1024, 512, 3, 2, 160, 48, 8, True, (10, 10)), 4, 20),
+    ('T2', O.AAConvShape(512, 256, 3, 2, 160, 24, 8, True, (20, 20)), 2, 40),
+    ('T1', O.AAConvShape(256, 128, 3, 2, 160, 8, 8, True, (40, 40)), 1, 80),
+])
+def test_bf16_transition_shapes_vs_oracle(tag, shape, B, hin):
+    p = O.init_params(shape, seed=0)
+    g0 = torch.Generator().manual_seed(1)
+    x = torch.relu(torch.randn(B, shape.in_channels, hin, hin, generator=g0))
+    dy = torch.randn(B, shape.out_channels, *shape.input_dims, generator=g0)
+    y_ref, g_ref = O.aaconv_backward_closed(x.double(), {k: v.double() for k, v in p.items()}, shape, dy.double())
+    m = _module(shape, p, 'bf16')
+    xc = x.cuda().requires_grad_(True)
+    y = m(xc)
+    y.backward(dy.cuda())
+    _bf16_close(y, y_ref, 'y')
+    _bf16_close(xc.grad, g_ref['x'], 'dx')
+    for n, prm in m.named_parameters():
+        _bf16_close(prm.grad, g_ref[n], n)
+
+
+def test_full_size_T1_properties_bf16():
+    """BASELINE size (B=16, 256ch, 80x80): size-independent properties instead of an O(L^2) oracle run --
+    batch independence (sample b of the batched call == the same sample run alone, bit for bit: no cross-sample
+    coupling, no atomics-order dependence) and linearity of backward in dy."""
+    shape = O.AAConvShape(256, 128, 3, 2, 160, 8, 8, True, (40, 40))
+    p = O.init_params(shape, seed=0)
+    m = _module(shape, p, 'bf16')
+    g0 = torch.Generator().manual_seed(5)
+    x = torch.relu(torch.randn(16, 256, 80, 80, generator=g0)).cuda()
+    dy = torch.randn(16, 128, 40, 40, generator=g0).cuda()
+    xa = x.clone().requires_grad_(True)
+    ya = m(xa)
+    ya.backward(dy)
+    xb = x[3:4].clone().requires_grad_(True)
+    yb = m(xb)
+    yb.backward(dy[3:4])
+    assert torch.equal(ya[3:4], yb)
+    assert torch.equal(xa.grad[3:4], xb.grad)
+    assert torch.isfinite(ya).all() and torch.isfinite(xa.grad).all()
+    gw = m.key_rel_w.grad.clone()
+    m.zero_grad()
+    xc = x.clone().requires_grad_(True)
+    m(xc).backward(2.0 * dy)
+    assert torch.allclose(xc.grad, 2.0 * xa.grad, rtol=1e-2, atol=1e-4)
+    assert rel_err(m.key_rel_w.grad, 2.0 * gw) < 2e-2
+
+
+def test_tiny_densenet_matches_reference_fixture():
+    """Whole-model anchor: the reference DenseNet(16,(2,2,2,2),32, k=v=0.5) forward/backward on one batch
+    (fixture written by oracle/gen_golden.py), fp32 kernels, strict state_dict load."""
+    from chexpert_b200.densenet import DenseNet
+    import chexpert_b200 as cb
+    z = np.load(os.path.join(GOLDEN, 'tiny_densenet.npz'))
+    m = DenseNet(16, (2, 2, 2, 2), 32, num_classes=5,
+                 attn_params={'k': 0.5, 'v': 0.5, 'nh': 8, 'relative': True, 'input_dims': (64, 64)}, precision='fp32')
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('sd.')}
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().train()
+    out = m(torch.from_numpy(z['x']).cuda())
+    loss = cb.BCEWithLogitsLoss('train')(out, torch.from_numpy(z['t']).cuda())
+    loss.backward()
+    assert torch.allclose(out.cpu(), torch.from_numpy(z['out']), rtol=1e-3, atol=1e-4)
+    assert torch.allclose(loss.cpu(), torch.from_numpy(z['loss']), rtol=1e-4)
+    for k, prm in m.named_parameters():
+        if 'g.' + k in z.files:
+            assert rel_err(prm.grad.cpu(), torch.from_numpy(z['g.' + k])) < 2e-3, k
