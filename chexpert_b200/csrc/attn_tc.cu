@@ -76,27 +76,34 @@ __global__ void __launch_bounds__(FA_THREADS) attn_fwd_tc_kernel(
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_s = tc::idesc_bf16_f32(FA_BM, FA_BN);
     constexpr uint32_t idesc_o = tc::idesc_bf16_f32(FA_BM, FA_DV);
-    if (lane == 0) {
-      tc::mbar_wait(&sm.bar_q, 0);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j % FA_STAGES, ph = (j / FA_STAGES) & 1;
-        tc::mbar_wait(&sm.bar_kv_full[s], ph);
-        tc::tc_fence_after();
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t da = tc::desc_advance(tc::smem_desc_sw128_kmajor(smem_u32(sm.q[ks >> 2])), (ks & 3) * 32);
-          const uint64_t db = tc::desc_advance(tc::smem_desc_sw128_kmajor(smem_u32(sm.k[s][ks >> 2])), (ks & 3) * 32);
-          tc::mma_ss(tmem + FA_COL_S, da, db, idesc_s, ks > 0);
-        }
+    constexpr uint32_t Q_ATOM = (FA_BM * 128) >> 4, K_ATOM = (FA_BN * 128) >> 4, K_STAGE = KATOMS * K_ATOM;
+    constexpr uint32_t V_ATOM = (FA_DV * 128) >> 4, V_STAGE = 2 * V_ATOM;
+    const uint32_t q_lo = tc::desc_lo_k(smem_u32(sm.q[0]));
+    const uint32_t k_lo = tc::desc_lo_k(smem_u32(sm.k[0][0]));
+    const uint32_t v_lo = tc::desc_lo_k(smem_u32(sm.v[0][0]));
+    tc::mbar_wait(&sm.bar_q, 0);
+    for (int j = 0; j < ntiles; ++j) {
+      const int s = j % FA_STAGES, ph = (j / FA_STAGES) & 1;
+      tc::mbar_wait(&sm.bar_kv_full[s], ph);
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+        for (int ks = 0; ks < ksteps; ++ks)
+          tc::mma_ss(tmem + FA_COL_S, tc::desc64(q_lo + (ks >> 2) * Q_ATOM + (ks & 3) * 2),
+                     tc::desc64(k_lo + s * K_STAGE + (ks >> 2) * K_ATOM + (ks & 3) * 2), idesc_s, ks > 0);
         tc::mma_commit(&sm.bar_s_full);
-        tc::mbar_wait(&sm.bar_p_ready, j & 1);
-        tc::tc_fence_after();
-        for (int ks = 0; ks < FA_BN / 16; ++ks) {
-          const uint64_t db = tc::desc_advance(tc::smem_desc_sw128_kmajor(smem_u32(sm.v[s][ks >> 2])), (ks & 3) * 32);
-          tc::mma_ts(tmem + FA_COL_O, tmem + FA_COL_P + ks * 8, db, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
-        }
+      }
+      __syncwarp();
+      tc::mbar_wait(&sm.bar_p_ready, j & 1);
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < FA_BN / 16; ++ks)
+          tc::mma_ts(tmem + FA_COL_O, tmem + FA_COL_P + ks * 8,
+                     tc::desc64(v_lo + s * V_STAGE + (ks >> 2) * V_ATOM + (ks & 3) * 2), idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
         tc::mma_commit(&sm.bar_kv_empty[s]);
         tc::mma_commit(&sm.bar_o_done);
       }
+      __syncwarp();
     }
   } else {
     // ===================== softmax warps (thread == query row == TMEM lane) =====================

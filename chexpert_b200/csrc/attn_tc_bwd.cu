@@ -208,37 +208,51 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dkv_tc_kernel(
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = tc::idesc_bf16_f32(PP_BM, PP_BN);
-      constexpr uint32_t idesc_dv = idesc_bmn(PP_BM, 16);
-      constexpr uint32_t idesc_dk = idesc_bmn(PP_BM, 32);
-      tc::mbar_wait(&sm.bar_stat, 0);
-      // software pipeline: scores of tile j are issued before the gradient MMAs of tile j-1
-      for (int j = 0; j <= ntiles; ++j) {
-        if (j < ntiles) {
-          const int st = j % PP_STAGES, slot = j & 1;
-          const uint32_t tslot = tmem + 192 * slot;
-          tc::mbar_wait(&sm.bar_full[st], (j / PP_STAGES) & 1);
-          tc::tc_fence_after();
+    // MMA issue: the whole warp runs the (uniform) loop and waits; one elected lane issues.  Descriptors are
+    // 32-bit adds on precomputed low words -- the issuing thread is the critical resource of this kernel.
+    constexpr uint32_t idesc_s = tc::idesc_bf16_f32(PP_BM, PP_BN);
+    constexpr uint32_t idesc_dv = idesc_bmn(PP_BM, 16);
+    constexpr uint32_t idesc_dk = idesc_bmn(PP_BM, 32);
+    constexpr uint32_t STAT_ATOM = (PP_BM * 128) >> 4, STRM_ATOM = (PP_BN * 128) >> 4, STAGE = KATOMS * STRM_ATOM;
+    const uint32_t stat_lo = tc::desc_lo_k(smem_u32(sm.stat[0]));
+    const uint32_t strm_lo = tc::desc_lo_k(smem_u32(sm.strm[0][0]));
+    const uint32_t v_lo = tc::desc_lo_mn(smem_u32(sm.strm[0][C1 >> 6]) + (C1 & 63) * 2, PP_BN * 128);
+    const uint32_t q_lo = tc::desc_lo_mn(smem_u32(sm.strm[0][0]), PP_BN * 128);
+    tc::mbar_wait(&sm.bar_stat, 0);
+    // software pipeline: scores of tile j are issued before the gradient MMAs of tile j-1
+    for (int j = 0; j <= ntiles; ++j) {
+      if (j < ntiles) {
+        const int st = j % PP_STAGES, slot = j & 1;
+        const uint32_t tslot = tmem + 192 * slot;
+        tc::mbar_wait(&sm.bar_full[st], (j / PP_STAGES) & 1);
+        tc::tc_fence_after();
+        if (tc::elect_one()) {
+          const uint32_t b0 = strm_lo + st * STAGE;
           for (int ks = 0; ks < nks; ++ks)
-            tc::mma_ss(tslot, desc_k(sm.stat[ks >> 2], ks), desc_k(sm.strm[st][ks >> 2], ks), idesc_s, ks > 0);
-          tc::mma_ss(tslot + 64, desc_k(sm.stat[nks >> 2], nks), desc_k(sm.strm[st][nks >> 2], nks), idesc_s, 0);
+            tc::mma_ss(tslot, tc::desc64(stat_lo + (ks >> 2) * STAT_ATOM + (ks & 3) * 2),
+                       tc::desc64(b0 + (ks >> 2) * STRM_ATOM + (ks & 3) * 2), idesc_s, ks > 0);
+          tc::mma_ss(tslot + 64, tc::desc64(stat_lo + (nks >> 2) * STAT_ATOM + (nks & 3) * 2),
+                     tc::desc64(b0 + (nks >> 2) * STRM_ATOM + (nks & 3) * 2), idesc_s, 0);
           tc::mma_commit(&sm.bar_s_full[slot]);
         }
-        if (j > 0) {
-          const int jj = j - 1, st = jj % PP_STAGES, slot = jj & 1;
-          const uint32_t tslot = tmem + 192 * slot;
-          tc::mbar_wait(&sm.bar_p_ready[slot], (jj >> 1) & 1);
-          tc::tc_fence_after();
-          const uint32_t v_base = smem_u32(sm.strm[st][C1 >> 6]) + (C1 & 63) * 2;
-          const uint32_t q_base = smem_u32(sm.strm[st][0]);
+        __syncwarp();
+      }
+      if (j > 0) {
+        const int jj = j - 1, st = jj % PP_STAGES, slot = jj & 1;
+        const uint32_t tslot = tmem + 192 * slot;
+        tc::mbar_wait(&sm.bar_p_ready[slot], (jj >> 1) & 1);
+        tc::tc_fence_after();
+        if (tc::elect_one()) {
+          const uint32_t vb = v_lo + st * STAGE, qb = q_lo + st * STAGE;
+#pragma unroll
           for (int ks = 0; ks < PP_BN / 16; ++ks) {
-            tc::mma_ts(tmem + COL_DV, tslot + 128 + ks * 8, desc_mn(v_base + ks * 2048, PP_BN * 128), idesc_dv, (jj > 0 || ks > 0) ? 1u : 0u);
-            tc::mma_ts(tmem + COL_DK, tslot + 160 + ks * 8, desc_mn(q_base + ks * 2048, PP_BN * 128), idesc_dk, (jj > 0 || ks > 0) ? 1u : 0u);
+            tc::mma_ts(tmem + COL_DV, tslot + 128 + ks * 8, tc::desc64(vb + ks * 128), idesc_dv, (jj > 0 || ks > 0) ? 1u : 0u);
+            tc::mma_ts(tmem + COL_DK, tslot + 160 + ks * 8, tc::desc64(qb + ks * 128), idesc_dk, (jj > 0 || ks > 0) ? 1u : 0u);
           }
           tc::mma_commit(&sm.bar_empty[st]);
           tc::mma_commit(&sm.bar_mma_done[slot]);
         }
+        __syncwarp();
       }
     }
   } else {
@@ -345,32 +359,44 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dq_tc_kernel(
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = tc::idesc_bf16_f32(PP_BM, PP_BN);
-      const uint32_t idesc_dq = idesc_bmn(PP_BM, NQ);
-      tc::mbar_wait(&sm.bar_stat, 0);
-      for (int j = 0; j <= ntiles; ++j) {
-        if (j < ntiles) {
-          const int st = j % PP_STAGES, slot = j & 1;
-          const uint32_t tslot = tmem + 160 * slot;
-          tc::mbar_wait(&sm.bar_full[st], (j / PP_STAGES) & 1);
-          tc::tc_fence_after();
+    constexpr uint32_t idesc_s = tc::idesc_bf16_f32(PP_BM, PP_BN);
+    const uint32_t idesc_dq = idesc_bmn(PP_BM, NQ);
+    constexpr uint32_t STAT_ATOM = (PP_BM * 128) >> 4, STRM_ATOM = (PP_BN * 128) >> 4, STAGE = KATOMS * STRM_ATOM;
+    const uint32_t stat_lo = tc::desc_lo_k(smem_u32(sm.stat[0]));
+    const uint32_t strm_lo = tc::desc_lo_k(smem_u32(sm.strm[0][0]));
+    const uint32_t k_lo = tc::desc_lo_mn(smem_u32(sm.strm[0][0]), PP_BN * 128);
+    tc::mbar_wait(&sm.bar_stat, 0);
+    for (int j = 0; j <= ntiles; ++j) {
+      if (j < ntiles) {
+        const int st = j % PP_STAGES, slot = j & 1;
+        const uint32_t tslot = tmem + 160 * slot;
+        tc::mbar_wait(&sm.bar_full[st], (j / PP_STAGES) & 1);
+        tc::tc_fence_after();
+        if (tc::elect_one()) {
+          const uint32_t b0 = strm_lo + st * STAGE;
           for (int ks = 0; ks < nks; ++ks)
-            tc::mma_ss(tslot, desc_k(sm.stat[ks >> 2], ks), desc_k(sm.strm[st][ks >> 2], ks), idesc_s, ks > 0);
-          tc::mma_ss(tslot + 64, desc_k(sm.stat[nks >> 2], nks), desc_k(sm.strm[st][nks >> 2], nks), idesc_s, 0);
+            tc::mma_ss(tslot, tc::desc64(stat_lo + (ks >> 2) * STAT_ATOM + (ks & 3) * 2),
+                       tc::desc64(b0 + (ks >> 2) * STRM_ATOM + (ks & 3) * 2), idesc_s, ks > 0);
+          tc::mma_ss(tslot + 64, tc::desc64(stat_lo + (nks >> 2) * STAT_ATOM + (nks & 3) * 2),
+                     tc::desc64(b0 + (nks >> 2) * STRM_ATOM + (nks & 3) * 2), idesc_s, 0);
           tc::mma_commit(&sm.bar_s_full[slot]);
         }
-        if (j > 0) {
-          const int jj = j - 1, st = jj % PP_STAGES, slot = jj & 1;
-          const uint32_t tslot = tmem + 160 * slot;
-          tc::mbar_wait(&sm.bar_p_ready[slot], (jj >> 1) & 1);
-          tc::tc_fence_after();
-          const uint32_t k_base = smem_u32(sm.strm[st][0]);
+        __syncwarp();
+      }
+      if (j > 0) {
+        const int jj = j - 1, st = jj % PP_STAGES, slot = jj & 1;
+        const uint32_t tslot = tmem + 160 * slot;
+        tc::mbar_wait(&sm.bar_p_ready[slot], (jj >> 1) & 1);
+        tc::tc_fence_after();
+        if (tc::elect_one()) {
+          const uint32_t kb = k_lo + st * STAGE;
+#pragma unroll
           for (int ks = 0; ks < PP_BN / 16; ++ks)
-            tc::mma_ts(tmem + COL_DQ, tslot + 128 + ks * 8, desc_mn(k_base + ks * 2048, PP_BN * 128), idesc_dq, (jj > 0 || ks > 0) ? 1u : 0u);
+            tc::mma_ts(tmem + COL_DQ, tslot + 128 + ks * 8, tc::desc64(kb + ks * 128), idesc_dq, (jj > 0 || ks > 0) ? 1u : 0u);
           tc::mma_commit(&sm.bar_empty[st]);
           tc::mma_commit(&sm.bar_mma_done[slot]);
         }
+        __syncwarp();
       }
     }
   } else {

@@ -82,31 +82,34 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_tc_kernel(const __gr
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::idesc_bf16_f32(128, 128);
-      int it = 0;
-      for (int c = 0; c < p.nchunks; ++c) {
-        const PGChunk ch = p.chunks[c];
-        uint32_t acc = 0;
-        for (int s = ch.seg_begin; s < ch.seg_end; ++s) {
-          const int katoms = p.segs[s].katoms;
-          for (int a = 0; a < katoms; ++a, ++it) {
-            const int st = it % PG_STAGES, ph = (it / PG_STAGES) & 1;
-            tc::mbar_wait(&sm.bar_full[st], ph);
-            tc::tc_fence_after();
-            const uint64_t da = tc::smem_desc_sw128_kmajor(smem_u32(sm.a[st]));
-            const uint64_t db = tc::smem_desc_sw128_kmajor(smem_u32(sm.b[st]));
+    // whole warp runs the uniform loop; one elected lane issues (keeps descriptors in uniform registers)
+    constexpr uint32_t idesc = tc::idesc_bf16_f32(128, 128);
+    constexpr uint32_t STAGE = (128 * 128) >> 4;
+    const uint32_t a_lo = tc::desc_lo_k(smem_u32(sm.a[0])), b_lo = tc::desc_lo_k(smem_u32(sm.b[0]));
+    int it = 0;
+    for (int c = 0; c < p.nchunks; ++c) {
+      const PGChunk ch = p.chunks[c];
+      uint32_t acc = 0;
+      for (int s = ch.seg_begin; s < ch.seg_end; ++s) {
+        const int katoms = p.segs[s].katoms;
+        for (int a = 0; a < katoms; ++a, ++it) {
+          const int st = it % PG_STAGES, ph = (it / PG_STAGES) & 1;
+          tc::mbar_wait(&sm.bar_full[st], ph);
+          tc::tc_fence_after();
+          if (tc::elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              tc::mma_ss(tmem + c * 128, tc::desc_advance(da, ks * 32), tc::desc_advance(db, ks * 32), idesc, acc);
-              acc = 1;
-            }
+            for (int ks = 0; ks < 4; ++ks)
+              tc::mma_ss(tmem + c * 128, tc::desc64(a_lo + st * STAGE + ks * 2), tc::desc64(b_lo + st * STAGE + ks * 2), idesc,
+                         (acc | ks) ? 1u : 0u);
             tc::mma_commit(&sm.bar_empty[st]);
           }
+          __syncwarp();
+          acc = 1;
         }
       }
-      tc::mma_commit(&sm.bar_acc);
     }
+    if (tc::elect_one()) tc::mma_commit(&sm.bar_acc);
+    __syncwarp();
   } else {
     // ===================== epilogue: thread == tile pixel == TMEM lane =====================
     tc::mbar_wait(&sm.bar_acc, 0);
@@ -523,23 +526,26 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
-      const uint32_t idesc = idesc_mn_mn(128, nn);
-      const int ksteps = p.kpix >> 4;
-      uint32_t acc = 0;
-      for (int g = g0, it = 0; g < g1; ++g, ++it) {
-        const int st = it % WG_STAGES, ph = (it / WG_STAGES) & 1;
-        tc::mbar_wait(&sm.bar_full[st], ph);
-        tc::tc_fence_after();
-        const uint32_t a0 = smem_u32(sm.a[st][0]), b0 = smem_u32(sm.b[st][0]);
-        for (int ks = 0; ks < ksteps; ++ks) {
-          tc::mma_ss(tmem, desc_mn_tile(a0 + ks * 2048, WG_KMAX * 128), desc_mn_tile(b0 + ks * 2048, WG_KMAX * 128), idesc, acc);
-          acc = 1;
-        }
+    const uint32_t idesc = idesc_mn_mn(128, nn);
+    const int ksteps = p.kpix >> 4;
+    constexpr uint32_t A_STAGE = (2 * WG_KMAX * 128) >> 4, B_STAGE = (4 * WG_KMAX * 128) >> 4;
+    const uint32_t a_lo = tc::desc_lo_mn(smem_u32(sm.a[0][0]), WG_KMAX * 128), b_lo = tc::desc_lo_mn(smem_u32(sm.b[0][0]), WG_KMAX * 128);
+    uint32_t acc = 0;
+    for (int g = g0, it = 0; g < g1; ++g, ++it) {
+      const int st = it % WG_STAGES, ph = (it / WG_STAGES) & 1;
+      tc::mbar_wait(&sm.bar_full[st], ph);
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+        for (int ks = 0; ks < ksteps; ++ks)
+          tc::mma_ss(tmem, tc::desc64(a_lo + st * A_STAGE + ks * 128), tc::desc64(b_lo + st * B_STAGE + ks * 128), idesc,
+                     (acc | ks) ? 1u : 0u);
         tc::mma_commit(&sm.bar_empty[st]);
       }
-      tc::mma_commit(&sm.bar_acc);
+      __syncwarp();
+      acc = 1;
     }
+    if (tc::elect_one()) tc::mma_commit(&sm.bar_acc);
+    __syncwarp();
   } else {
     float* out = p.partial + ((size_t)(split * gridDim.x + blockIdx.x) * 128 + threadIdx.x) * WG_N;
     if (g0 < g1) {

@@ -169,6 +169,15 @@ __device__ __forceinline__ uint64_t smem_desc_sw128_kmajor(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                          // layout type SWIZZLE_128B, bits [61,64)
   return d;
 }
+// The same descriptors as (lo, hi) halves: hi is constant for every SWIZZLE_128B tile with 1024 B row groups, so
+// the MMA issue loop only does 32-bit adds on `lo` (start address >> 4 in bits [0,14), LBO >> 4 in bits [16,30)).
+constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo_k(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_lo_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)DESC_HI_SW128 << 32) | lo; }
+
 // advance the start address by `bytes` (a multiple of 16; used to step K by 16 bf16 = 32 B inside the atom)
 __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); }
 
