@@ -24,115 +24,6 @@ using tc::smem_u32;
 typedef __nv_bfloat16 bf16;
 
 // ------------------------------------------------------------------------------------------------
-// layout of the augmented operands
-// ------------------------------------------------------------------------------------------------
-AugLayout aug_layout(const Dims& d) {
-  AugLayout a;
-  a.KD = d.dkh + (d.relative ? d.W + d.H : 0);
-  a.C1 = cdiv(a.KD + 2, 16) * 16;
-  a.KP = cdiv(a.C1 + 16, 64) * 64;
-  a.NQ = cdiv(a.KD, 16) * 16;
-  return a;
-}
-
-int aug_supported(const Dims& d) {
-  const AugLayout a = aug_layout(d);
-  if (d.dvh + 2 > 16) return fail(AACONV_E_UNSUPPORTED, "bf16 attention kernels support dv/nh <= 14 (got %d)", d.dvh);
-  if (a.KP > 192 || d.dkh > 32)
-    return fail(AACONV_E_UNSUPPORTED, "bf16 attention kernels support dk/nh <= 32 and dk/nh + H + W <= 158 (got %d, %d)",
-                d.dkh, a.KD);
-  return 0;
-}
-
-__device__ __forceinline__ void split_bf16(float x, bf16& hi, bf16& lo) {
-  hi = __float2bfloat16(x);
-  lo = __float2bfloat16(x - __bfloat162float(hi));
-}
-
-// mode 0 (forward): the lse columns of Qa carry +BIG / 0 (shifts every in-range logit, so zero-filled
-// out-of-range keys fall 2^-BIG below: masking without a compare); dO/delta columns are zero.
-// mode 1 (backward): full layout.
-__global__ void aug_build_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
-                                 const float* __restrict__ krw, const float* __restrict__ krh,
-                                 const float* __restrict__ lse, const float* __restrict__ d_o,
-                                 const float* __restrict__ delta, bf16* __restrict__ qa, bf16* __restrict__ ka,
-                                 size_t rows, int L, int H, int W, int dkh, int dvh, int KD, int C1, int KP, int relative,
-                                 int mode, float big) {
-  extern __shared__ float sm[];
-  const float LOG2E = 1.4426950408889634f;
-  const int RW = 2 * W - 1, RH = 2 * H - 1;
-  float* kw = sm;                                   // dkh x RW
-  float* kh = kw + (relative ? dkh * RW : 0);       // dkh x RH
-  float* qs = kh + (relative ? dkh * RH : 0);       // 16 x dkh
-  float* ks = qs + 16 * dkh;
-  if (relative) {
-    for (int i = threadIdx.x; i < dkh * RW; i += blockDim.x) kw[i] = krw[i];
-    for (int i = threadIdx.x; i < dkh * RH; i += blockDim.x) kh[i] = krh[i];
-  }
-  const int c = threadIdx.x;                        // blockDim.x == KP
-  for (size_t r0 = (size_t)blockIdx.x * 16; r0 < rows; r0 += (size_t)gridDim.x * 16) {
-    __syncthreads();
-    const int nr = (int)min((size_t)16, rows - r0);
-    for (int i = threadIdx.x; i < nr * dkh; i += blockDim.x) { qs[i] = q[r0 * dkh + i]; ks[i] = k[r0 * dkh + i]; }
-    __syncthreads();
-    for (int rr = 0; rr < nr; ++rr) {
-      const size_t row = r0 + rr;
-      const int l = (int)(row % L), y = l / W, x = l - y * W;
-      float qv = 0.f, kv = 0.f;
-      if (c < dkh) {
-        qv = qs[rr * dkh + c] * LOG2E;
-        kv = ks[rr * dkh + c];
-      } else if (c < KD) {
-        const bool isw = c < dkh + W;
-        const int pos = isw ? c - dkh : c - dkh - W;
-        const float* tab = isw ? kw + (pos - x + W - 1) : kh + (pos - y + H - 1);
-        const int R = isw ? RW : RH;
-        float a = 0.f;
-        for (int e = 0; e < dkh; ++e) a = fmaf(qs[rr * dkh + e], tab[e * R], a);
-        qv = a * LOG2E;
-        kv = (pos == (isw ? x : y)) ? 1.f : 0.f;
-      } else if (c < KD + 2) {
-        kv = 1.f;
-        if (mode == 0) {
-          qv = (c == KD) ? big : 0.f;
-        } else {
-          bf16 hi, lo;
-          split_bf16(-lse[row] * LOG2E, hi, lo);
-          qv = __bfloat162float(c == KD ? hi : lo);
-        }
-      } else if (c >= C1 && c < C1 + dvh) {
-        kv = v[row * dvh + (c - C1)];
-        qv = mode ? d_o[row * dvh + (c - C1)] : 0.f;
-      } else if (c >= C1 + dvh && c < C1 + dvh + 2) {
-        kv = 1.f;
-        if (mode) {
-          bf16 hi, lo;
-          split_bf16(-delta[row], hi, lo);
-          qv = __bfloat162float(c == C1 + dvh ? hi : lo);
-        }
-      }
-      qa[row * KP + c] = __float2bfloat16(qv);
-      ka[row * KP + c] = __float2bfloat16(kv);
-    }
-  }
-}
-
-int aug_build(const Dims& d, int mode, const float* q, const float* k, const float* v, const float* krw,
-              const float* krh, const float* lse, const float* d_o, const float* delta, void* qa, void* ka,
-              cudaStream_t st) {
-  const AugLayout a = aug_layout(d);
-  const size_t rows = (size_t)d.BN * d.L;
-  const size_t smem = sizeof(float) * ((d.relative ? (size_t)d.dkh * (d.RW + d.RH) : 0) + 32 * (size_t)d.dkh);
-  AACONV_CUDA_OK(cudaFuncSetAttribute(aug_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (int)std::min<size_t>((rows + 15) / 16, 148 * 16);
-  aug_build_kernel<<<grid, a.KP, smem, st>>>(q, k, v, krw, krh, lse, d_o, delta, static_cast<bf16*>(qa),
-                                            static_cast<bf16*>(ka), rows, d.L, d.H, d.W, d.dkh, d.dvh, a.KD, a.C1, a.KP,
-                                            d.relative, mode, AUG_BIG);
-  AACONV_LAUNCH_OK(mode ? "aug_build_bwd" : "aug_build_fwd");
-  return 0;
-}
-
-// ------------------------------------------------------------------------------------------------
 // ping-pong kernel skeleton: 8 math warps (two warpgroups, one TMEM slot each), 1 TMA warp, 1 MMA warp
 // ------------------------------------------------------------------------------------------------
 constexpr int PP_THREADS = 320;
@@ -170,7 +61,8 @@ __host__ __device__ constexpr uint32_t idesc_bmn(int M, int N) { return tc::ides
 template <int KATOMS>
 __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dkv_tc_kernel(
     const __grid_constant__ CUtensorMap tm_k_stat, const __grid_constant__ CUtensorMap tm_q_strm,
-    float* __restrict__ dk, float* __restrict__ dv, int L, int dkh, int dvh, int C1) {
+    float* __restrict__ dk, float* __restrict__ dv, bf16* __restrict__ dqkvh, int KPq, int nh, int L, int dkh, int dvh,
+    int C1) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   PPSmem<KATOMS>& sm = *reinterpret_cast<PPSmem<KATOMS>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -293,21 +185,49 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dkv_tc_kernel(
     const int kj = k0 + (warp & 3) * 32 + lane;
     const size_t row = (size_t)bn * L + kj;
     const float LN2 = 0.6931471805599453f;               // Qa carries log2(e)*q
+    // packed bf16 destination: pixel (b, kj), columns [nh*dkh + n*dkh, ..) for dk and [2*nh*dkh + n*dvh, ..) for dv
+    const int b = bn / nh, n = bn - b * nh;
+    bf16* prow = dqkvh ? dqkvh + ((size_t)b * L + kj) * KPq : nullptr;
     if (wg == 0) {
       tc::tmem_ld_x32(tlane + COL_DK, rs);
       tc::tmem_ld_wait();
       if (kj < L) {
+        if (prow) {
+          bf16* dst = prow + nh * dkh + n * dkh;
+          if (((dkh | KPq) & 3) == 0) {                    // 8-byte aligned groups of four
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if (e < dkh) dk[row * dkh + e] = __uint_as_float(rs[e]) * LN2;
+            for (int e = 0; e < 32; e += 4)
+              if (e < dkh) {
+                uint2 w;
+                w.x = tc::pack_bf16x2(__uint_as_float(rs[e]) * LN2, __uint_as_float(rs[e + 1]) * LN2);
+                w.y = tc::pack_bf16x2(__uint_as_float(rs[e + 2]) * LN2, __uint_as_float(rs[e + 3]) * LN2);
+                *reinterpret_cast<uint2*>(dst + e) = w;
+              }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (e < dkh) dst[e] = __float2bfloat16(__uint_as_float(rs[e]) * LN2);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (e < dkh) dk[row * dkh + e] = __uint_as_float(rs[e]) * LN2;
+        }
       }
     } else {
       tc::tmem_ld_x16(tlane + COL_DV, pp);
       tc::tmem_ld_wait();
       if (kj < L) {
+        if (prow) {
+          bf16* dst = prow + 2 * nh * dkh + n * dvh;
 #pragma unroll
-        for (int e = 0; e < 16; ++e)
-          if (e < dvh) dv[row * dvh + e] = __uint_as_float(pp[e]);
+          for (int e = 0; e < 16; ++e)
+            if (e < dvh) dst[e] = __float2bfloat16(__uint_as_float(pp[e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (e < dvh) dv[row * dvh + e] = __uint_as_float(pp[e]);
+        }
       }
     }
   }
@@ -460,7 +380,7 @@ static int make_aug_maps(const Dims& d, const void* t, int KP, uint32_t box_rows
 
 template <int KATOMS>
 static int launch_bwd(const Dims& d, const AugLayout& a, const void* qa, const void* ka, float* dqa, float* dk,
-                      float* dv, cudaStream_t st) {
+                      float* dv, void* dqkvh, int KPq, cudaStream_t st) {
   CUtensorMap tq_stat, tk_strm, tk_stat, tq_strm;
   AACONV_TRY(make_aug_maps(d, qa, a.KP, PP_BM, &tq_stat));
   AACONV_TRY(make_aug_maps(d, ka, a.KP, PP_BN, &tk_strm));
@@ -471,7 +391,7 @@ static int launch_bwd(const Dims& d, const AugLayout& a, const void* qa, const v
   {
     auto kern = attn_bwd_dkv_tc_kernel<KATOMS>;
     AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, PP_THREADS, smem, st>>>(tk_stat, tq_strm, dk, dv, d.L, d.dkh, d.dvh, a.C1);
+    kern<<<grid, PP_THREADS, smem, st>>>(tk_stat, tq_strm, dk, dv, static_cast<bf16*>(dqkvh), KPq, d.nh, d.L, d.dkh, d.dvh, a.C1);
     AACONV_LAUNCH_OK("attn_bwd_dkv_tc");
   }
   {
@@ -484,13 +404,14 @@ static int launch_bwd(const Dims& d, const AugLayout& a, const void* qa, const v
 }
 
 // qa/ka: mode-1 augmented operands.  dqa (B,nh,L,KD) fp32; dk (B,nh,L,dkh); dv (B,nh,L,dvh).
-int tc_attn_bwd(const Dims& d, const void* qa, const void* ka, float* dqa, float* dk, float* dv, cudaStream_t st) {
+int tc_attn_bwd(const Dims& d, const void* qa, const void* ka, float* dqa, float* dk, float* dv, void* dqkvh, int KPq,
+                cudaStream_t st) {
   AACONV_TRY(aug_supported(d));
   const AugLayout a = aug_layout(d);
   switch (a.KP / 64) {
-    case 1: return launch_bwd<1>(d, a, qa, ka, dqa, dk, dv, st);
-    case 2: return launch_bwd<2>(d, a, qa, ka, dqa, dk, dv, st);
-    default: return launch_bwd<3>(d, a, qa, ka, dqa, dk, dv, st);
+    case 1: return launch_bwd<1>(d, a, qa, ka, dqa, dk, dv, dqkvh, KPq, st);
+    case 2: return launch_bwd<2>(d, a, qa, ka, dqa, dk, dv, dqkvh, KPq, st);
+    default: return launch_bwd<3>(d, a, qa, ka, dqa, dk, dv, dqkvh, KPq, st);
   }
 }
 

@@ -1,0 +1,571 @@
+// Operand builders and relative-logit adjoints around the tcgen05 attention kernels (bf16 path).
+//
+//   aug_build_fwd   q,k,v (fp32, head-split) -> augmented bf16 operands Qa, Ka (layout in attn_tc_bwd.cu)
+//   aug_patch_bwd   fills the backward-only columns of Qa in place: -lse (hi/lo), dO, -delta (hi/lo), delta = dO.o
+//   rel_bwd         dQa -> total dq (content + relative part) written as bf16 into the packed dqkv operand of the
+//                   projection GEMMs, and the key_rel_w / key_rel_h gradients
+//
+// The relative logits are rel_to_abs as an index computation (attn_aug_conv.py:43-63):
+//   Aq[row, x'] = sum_e q[row,e] key_rel_w[e, x' - x(row) + W-1],   Bq[row, y'] = sum_e q[row,e] key_rel_h[e, y' - y(row) + H-1]
+// i.e. a rank-dkh product R = q . key_rel followed by a per-row shift.  The products are small (K = dkh) and the
+// shift is per row, so they run on mma.sync m16n8k8 TF32 (fp32 operands, 10-bit mantissa, far inside the bf16
+// budget of the operands they feed), with the shift applied when fragments are scattered / gathered in shared
+// memory; the three contractions are
+//   forward   R[rows x 2N-1]   = Q[rows x dkh] . T[dkh x 2N-1]            -> shift -> Aq / Bq columns of Qa
+//   dq_rel    [rows x dkh]     = dR[rows x 2N-1] . T^T                      dR[row, r] = dAq[row, r + x - (N-1)]
+//   dT^T      [2N-1 x dkh]    += dR^T[2N-1 x rows] . Q[rows x dkh]          (accumulated in registers, fixed order)
+#include <algorithm>
+#include <cuda_bf16.h>
+#include "bf16_path.cuh"
+
+namespace aaconv {
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------------
+// layout of the augmented operands
+// ------------------------------------------------------------------------------------------------
+AugLayout aug_layout(const Dims& d) {
+  AugLayout a;
+  a.KD = d.dkh + (d.relative ? d.W + d.H : 0);
+  a.C1 = cdiv(a.KD + 2, 16) * 16;
+  a.KP = cdiv(a.C1 + 16, 64) * 64;
+  a.NQ = cdiv(a.KD, 16) * 16;
+  return a;
+}
+
+int aug_supported(const Dims& d) {
+  const AugLayout a = aug_layout(d);
+  if (d.dvh + 2 > 16) return fail(AACONV_E_UNSUPPORTED, "bf16 attention kernels support dv/nh <= 14 (got %d)", d.dvh);
+  if (a.KP > 192 || d.dkh > 32)
+    return fail(AACONV_E_UNSUPPORTED, "bf16 attention kernels support dk/nh <= 32 and dk/nh + H + W <= 158 (got %d, %d)",
+                d.dkh, a.KD);
+  return 0;
+}
+
+namespace {
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr int TR = 64;             // rows per tile (4 row groups of 16)
+constexpr int PQ = 36;             // q tile pitch (floats): == 4 (mod 32) -> conflict-free A-fragment loads (row = g)
+
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+// D += A(16x8, row) * B(8x8, col), TF32 inputs, fp32 accumulate.
+// A: a0=(g,t) a1=(g+8,t) a2=(g,t+4) a3=(g+8,t+4);  B: b0=(k=t,n=g) b1=(k=t+4,n=g);  C: c0=(g,2t) c1=(g,2t+1) c2=(g+8,2t) c3=(g+8,2t+1)
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+__device__ __forceinline__ void split_bf16(float x, bf16& hi, bf16& lo) {
+  hi = __float2bfloat16(x);
+  lo = __float2bfloat16(x - __bfloat162float(hi));
+}
+
+inline int table_pitch(int R) {   // >= roundup8(R) and == 8 (mod 32): conflict-free B-fragment loads (k = t, n = g)
+  const int r8 = cdiv(R, 8) * 8;
+  int p = r8;
+  while (p % 32 != 8) ++p;
+  return p;
+}
+
+struct BuildP {
+  const float *q, *k, *v, *krw, *krh;
+  bf16 *qa, *ka;
+  int L, H, W, dkh, dvh, KD, C1, KP, relative;
+  int DK8, RW, RH, PBW, PBH;       // padded K, table extents and pitches
+  int tiles_per_bn, ntiles;
+};
+
+// ------------------------------------------------------------------------------------------------
+// forward builder
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) aug_build_fwd_kernel(const BuildP p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint32_t* tabw = reinterpret_cast<uint32_t*>(smem_raw);                 // [DK8][PBW] tf32
+  uint32_t* tabh = tabw + (p.relative ? p.DK8 * p.PBW : 0);               // [DK8][PBH]
+  float* qs = reinterpret_cast<float*>(tabh + (p.relative ? p.DK8 * p.PBH : 0));   // [TR][PQ]  q (zero padded)
+  float* ks = qs + TR * PQ;                                               // [TR][dkh]
+  float* vs = ks + TR * p.dkh;                                            // [TR][dvh]
+  const int PT = p.KP + 8;
+  bf16* tq = reinterpret_cast<bf16*>(vs + ((TR * p.dvh + 3) & ~3));       // [TR][PT]
+  bf16* tk = tq + TR * PT;
+  int* rx = reinterpret_cast<int*>(tk + TR * PT);                         // [TR] x and y of each tile row
+  int* ry = rx + TR;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int CP = p.KP >> 1, rows_per_pass = 256 / CP, cp = threadIdx.x % CP, rsub = threadIdx.x / CP;
+  if (p.relative) {
+    for (int i = threadIdx.x; i < p.DK8 * p.PBW; i += blockDim.x) {
+      const int e = i / p.PBW, r = i - e * p.PBW;
+      tabw[i] = (e < p.dkh && r < p.RW) ? f2tf32(p.krw[e * p.RW + r]) : 0u;
+    }
+    for (int i = threadIdx.x; i < p.DK8 * p.PBH; i += blockDim.x) {
+      const int e = i / p.PBH, r = i - e * p.PBH;
+      tabh[i] = (e < p.dkh && r < p.RH) ? f2tf32(p.krh[e * p.RH + r]) : 0u;
+    }
+  }
+  for (int i = threadIdx.x; i < TR * PQ; i += blockDim.x) qs[i] = 0.f;
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const int bn = tile / p.tiles_per_bn, l0 = (tile - bn * p.tiles_per_bn) * TR;
+    const int nrows = min(TR, p.L - l0);
+    const size_t row0 = (size_t)bn * p.L + l0;
+    __syncthreads();                                   // previous tile fully copied out; tables visible
+    if (threadIdx.x < TR) {
+      const int l = l0 + threadIdx.x, y = l / p.W;
+      rx[threadIdx.x] = l - y * p.W;
+      ry[threadIdx.x] = y;
+    }
+    // asynchronous tile loads (LDGSTS): no register staging, no load->store ordering stalls.  Pad columns of qs were
+    // zeroed once; rows past the end of the image (last tile only) are zeroed here.
+    for (int r = warp; r < TR; r += 8) {
+      if (r < nrows) {
+        if (lane < p.dkh) {
+          cp_async4(qs + r * PQ + lane, p.q + (row0 + r) * p.dkh + lane);
+          cp_async4(ks + r * p.dkh + lane, p.k + (row0 + r) * p.dkh + lane);
+        }
+        if (lane < p.dvh) cp_async4(vs + r * p.dvh + lane, p.v + (row0 + r) * p.dvh + lane);
+      } else if (lane < p.dkh) {
+        qs[r * PQ + lane] = 0.f;
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    // ---- relative columns of Qa: warps 0-3 the W axis, warps 4-7 the H axis, 16 rows each ----
+    if (p.relative) {
+      const int axis = warp >> 2, rg = (warp & 3) * 16;
+      const int N = axis ? p.H : p.W, R = axis ? p.RH : p.RW, PB = axis ? p.PBH : p.PBW;
+      const uint32_t* tab = axis ? tabh : tabw;
+      const int colbase = p.dkh + (axis ? p.W : 0);
+      const int ra = rg + g, rb = rg + g + 8;
+      const int pos_a = axis ? ry[ra] : rx[ra], pos_b = axis ? ry[rb] : rx[rb];
+      uint32_t af[4][4];
+      const int nks = p.DK8 >> 3;
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+        if (s < nks) {
+          af[s][0] = f2tf32(qs[ra * PQ + 8 * s + t] * LOG2E);
+          af[s][1] = f2tf32(qs[rb * PQ + 8 * s + t] * LOG2E);
+          af[s][2] = f2tf32(qs[ra * PQ + 8 * s + t + 4] * LOG2E);
+          af[s][3] = f2tf32(qs[rb * PQ + 8 * s + t + 4] * LOG2E);
+        }
+      const int NT = (R + 7) >> 3;
+      for (int nt = 0; nt < NT; ++nt) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          if (s < nks) mma_tf32(c, af[s][0], af[s][1], af[s][2], af[s][3], tab[(8 * s + t) * PB + 8 * nt + g],
+                                tab[(8 * s + t + 4) * PB + 8 * nt + g]);
+        const int r = 8 * nt + 2 * t;                  // R[row, r], R[row, r+1];  abs position = r + pos - (N-1)
+        const int xa = r + pos_a - (N - 1), xb = r + pos_b - (N - 1);
+        if ((unsigned)xa < (unsigned)N) tq[ra * PT + colbase + xa] = __float2bfloat16(c[0]);
+        if ((unsigned)(xa + 1) < (unsigned)N) tq[ra * PT + colbase + xa + 1] = __float2bfloat16(c[1]);
+        if ((unsigned)xb < (unsigned)N) tq[rb * PT + colbase + xb] = __float2bfloat16(c[2]);
+        if ((unsigned)(xb + 1) < (unsigned)N) tq[rb * PT + colbase + xb + 1] = __float2bfloat16(c[3]);
+      }
+    }
+    // ---- everything else: q columns and zero tail of Qa, all of Ka.  A thread owns one column pair (its kind is
+    //      loop invariant) and walks down the rows; bf16x2 stores ----
+    if (rsub < rows_per_pass) {
+      const int c0 = 2 * cp;
+      for (int r = rsub; r < TR; r += rows_per_pass) {
+        const int x = rx[r], y = ry[r];
+        const bool rv = r < nrows;
+        float kv[2], qv[2];
+        bool qw[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = c0 + h;
+          kv[h] = 0.f; qv[h] = 0.f; qw[h] = true;
+          if (c < p.dkh) {
+            qv[h] = qs[r * PQ + c] * LOG2E;
+            kv[h] = rv ? ks[r * p.dkh + c] : 0.f;
+          } else if (c < p.KD) {
+            qw[h] = false;                                 // relative column: written by the MMA phase
+            kv[h] = (c < p.dkh + p.W) ? (c - p.dkh == x ? 1.f : 0.f) : (c - p.dkh - p.W == y ? 1.f : 0.f);
+          } else if (c < p.KD + 2) {
+            kv[h] = 1.f;
+          } else if (c >= p.C1 && c < p.C1 + p.dvh) {
+            kv[h] = rv ? vs[r * p.dvh + (c - p.C1)] : 0.f;
+          } else if (c >= p.C1 + p.dvh && c < p.C1 + p.dvh + 2) {
+            kv[h] = 1.f;
+          }
+        }
+        *reinterpret_cast<__nv_bfloat162*>(tk + r * PT + c0) = __floats2bfloat162_rn(kv[0], kv[1]);
+        if (qw[0] && qw[1]) {
+          *reinterpret_cast<__nv_bfloat162*>(tq + r * PT + c0) = __floats2bfloat162_rn(qv[0], qv[1]);
+        } else {
+          if (qw[0]) tq[r * PT + c0] = __float2bfloat16(qv[0]);
+          if (qw[1]) tq[r * PT + c0 + 1] = __float2bfloat16(qv[1]);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- coalesced copy-out: rows of KP bf16 are contiguous in global memory ----
+    const int vec_per_row = p.KP >> 3;                 // uint4 = 8 bf16
+    uint4* gq = reinterpret_cast<uint4*>(p.qa + row0 * p.KP);
+    uint4* gk = reinterpret_cast<uint4*>(p.ka + row0 * p.KP);
+    for (int i = threadIdx.x; i < nrows * vec_per_row; i += blockDim.x) {
+      const int r = i / vec_per_row, c = i - r * vec_per_row;
+      gq[i] = *reinterpret_cast<const uint4*>(tq + r * PT + c * 8);
+      gk[i] = *reinterpret_cast<const uint4*>(tk + r * PT + c * 8);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward patch of Qa
+// ------------------------------------------------------------------------------------------------
+__global__ void aug_patch_bwd_kernel(const float* __restrict__ lse, const float* __restrict__ d_o,
+                                     const float* __restrict__ o, bf16* __restrict__ qa, size_t rows, int dvh, int KD,
+                                     int C1, int KP) {
+  const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  bf16* dst = qa + row * KP;
+  bf16 hi, lo;
+  split_bf16(-lse[row] * LOG2E, hi, lo);
+  dst[KD] = hi;
+  dst[KD + 1] = lo;
+  float delta = 0.f;
+  for (int e = 0; e < dvh; ++e) {
+    const float g = d_o[row * dvh + e];
+    delta = fmaf(g, o[row * dvh + e], delta);
+    dst[C1 + e] = __float2bfloat16(g);
+  }
+  split_bf16(-delta, hi, lo);
+  dst[C1 + dvh] = hi;
+  dst[C1 + dvh + 1] = lo;
+}
+}  // namespace
+
+size_t aug_build_smem(const Dims& d) {
+  const AugLayout a = aug_layout(d);
+  const int DK8 = cdiv(d.dkh, 8) * 8;
+  size_t s = 0;
+  if (d.relative) s += sizeof(uint32_t) * DK8 * (size_t)(table_pitch(d.RW) + table_pitch(d.RH));
+  s += sizeof(float) * (TR * PQ + TR * d.dkh + ((TR * d.dvh + 3) & ~3));
+  s += sizeof(bf16) * 2 * TR * (size_t)(a.KP + 8);
+  s += sizeof(int) * 2 * TR;
+  return s;
+}
+
+int aug_build_fwd(const Dims& d, const float* q, const float* k, const float* v, const float* krw, const float* krh,
+                  void* qa, void* ka, cudaStream_t st) {
+  AACONV_TRY(aug_supported(d));
+  const AugLayout a = aug_layout(d);
+  BuildP p;
+  p.q = q; p.k = k; p.v = v; p.krw = krw; p.krh = krh;
+  p.qa = static_cast<bf16*>(qa); p.ka = static_cast<bf16*>(ka);
+  p.L = d.L; p.H = d.H; p.W = d.W; p.dkh = d.dkh; p.dvh = d.dvh; p.KD = a.KD; p.C1 = a.C1; p.KP = a.KP;
+  p.relative = d.relative;
+  p.DK8 = cdiv(d.dkh, 8) * 8; p.RW = d.RW; p.RH = d.RH; p.PBW = table_pitch(d.RW); p.PBH = table_pitch(d.RH);
+  p.tiles_per_bn = cdiv(d.L, TR); p.ntiles = p.tiles_per_bn * d.BN;
+  const size_t smem = aug_build_smem(d);
+  if (smem > 200 * 1024) return fail(AACONV_E_UNSUPPORTED, "aug_build: %zu B of shared memory needed", smem);
+  AACONV_CUDA_OK(cudaFuncSetAttribute(aug_build_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_sm = std::max(1, std::min(4, (int)(220 * 1024 / (smem + 1024))));
+  const int grid = std::min(p.ntiles, 148 * per_sm);
+  aug_build_fwd_kernel<<<grid, 256, smem, st>>>(p);
+  AACONV_LAUNCH_OK("aug_build_fwd");
+  return 0;
+}
+
+int aug_patch_bwd(const Dims& d, const float* lse, const float* d_o, const float* o, void* qa, cudaStream_t st) {
+  const AugLayout a = aug_layout(d);
+  const size_t rows = (size_t)d.BN * d.L;
+  const unsigned grid = (unsigned)((rows + 255) / 256);
+  aug_patch_bwd_kernel<<<grid, 256, 0, st>>>(lse, d_o, o, static_cast<bf16*>(qa), rows, d.dvh, a.KD, a.C1, a.KP);
+  AACONV_LAUNCH_OK("aug_patch_bwd");
+  return 0;
+}
+
+}  // namespace aaconv
+
+// ================================================================================================
+// rel_bwd: dQa -> dq (content + relative) and the key_rel_w / key_rel_h gradients
+// ================================================================================================
+namespace aaconv {
+namespace {
+
+struct RelBwdP {
+  const float *dqa, *q, *krw, *krh;
+  float* dq;            // fp32 (B,nh,L,dkh) or NULL
+  bf16* dqkvh;          // packed bf16 (B*L, KPq) or NULL: dq * qscale lands at column n*dkh + e
+  float* partial;       // [grid][2][RP * DK8] key_rel gradient partials (transposed: [r][e])
+  int L, H, W, nh, dkh, KD, KPq, relative;
+  int DK8, RW, RH, PBW, PBH, PTW, PTH, PA, RP;
+  int tiles_per_bn, ntiles;
+  float qscale;
+};
+
+constexpr int PQ2 = 40;   // q tile pitch == 8 (mod 32): conflict-free B-fragment loads with k = row = t
+
+inline int pitch_mod32(int n, int want) {
+  int p = n;
+  while (p % 32 != want) ++p;
+  return p;
+}
+
+// MT = 16-row tiles of the relative axis (2N-1 <= 16*MT), NTE = 8-column tiles of dkh (dkh <= 8*NTE)
+template <int MT, int NTE>
+__global__ void __launch_bounds__(256) rel_bwd_kernel(const RelBwdP p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint32_t* tabw = reinterpret_cast<uint32_t*>(smem_raw);        // [DK8][PTW]  pitch == 4 (mod 32): B frags with n = e = g, k = r = t
+  uint32_t* tabh = tabw + p.DK8 * p.PTW;                         // [DK8][PTH]
+  float* da = reinterpret_cast<float*>(tabh + p.DK8 * p.PTH);    // [TR][PA]    dQa rows of the tile
+  float* qs = da + TR * p.PA;                                    // [TR][PQ2]   q (zero padded)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+
+  for (int i = threadIdx.x; i < p.DK8 * p.PTW; i += blockDim.x) {
+    const int e = i / p.PTW, r = i - e * p.PTW;
+    tabw[i] = (e < p.dkh && r < p.RW) ? f2tf32(p.krw[e * p.RW + r]) : 0u;
+  }
+  for (int i = threadIdx.x; i < p.DK8 * p.PTH; i += blockDim.x) {
+    const int e = i / p.PTH, r = i - e * p.PTH;
+    tabh[i] = (e < p.dkh && r < p.RH) ? f2tf32(p.krh[e * p.RH + r]) : 0u;
+  }
+  for (int i = threadIdx.x; i < TR * PQ2; i += blockDim.x) qs[i] = 0.f;   // pad columns stay zero
+  float acc[MT][NTE][4];                                         // G role: dT^T[r][e] of this warp's axis / row half
+#pragma unroll
+  for (int a = 0; a < MT; ++a)
+#pragma unroll
+    for (int b = 0; b < NTE; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const int bn = tile / p.tiles_per_bn, l0 = (tile - bn * p.tiles_per_bn) * TR;
+    const int nrows = min(TR, p.L - l0);
+    const size_t row0 = (size_t)bn * p.L + l0;
+    __syncthreads();
+    for (int r = warp; r < TR; r += 8) {               // one warp per row, asynchronous (LDGSTS)
+      if (r < nrows) {
+        for (int c = lane; c < p.KD; c += 32) cp_async4(da + r * p.PA + c, p.dqa + (row0 + r) * p.KD + c);
+        if (lane < p.dkh) cp_async4(qs + r * PQ2 + lane, p.q + (row0 + r) * p.dkh + lane);
+      } else {
+        for (int c = lane; c < p.KD; c += 32) da[r * p.PA + c] = 0.f;
+        if (lane < p.dkh) qs[r * PQ2 + lane] = 0.f;
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    if (warp < 4) {
+      // ---------------- dq role: 16 rows, both axes ----------------
+      const int ra = warp * 16 + g, rb = ra + 8;
+      const int la = l0 + ra, lb = l0 + rb;
+      float c[NTE][4];
+#pragma unroll
+      for (int nt = 0; nt < NTE; ++nt) { c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f; }
+      for (int axis = 0; axis < 2; ++axis) {
+        const int N = axis ? p.H : p.W, R = axis ? p.RH : p.RW, PT = axis ? p.PTH : p.PTW;
+        const uint32_t* tab = axis ? tabh : tabw;
+        const int colbase = p.dkh + (axis ? p.W : 0);
+        const int pos_a = axis ? la / p.W : la % p.W, pos_b = axis ? lb / p.W : lb % p.W;
+        const float* rowa = da + ra * p.PA + colbase + pos_a - (N - 1);
+        const float* rowb = da + rb * p.PA + colbase + pos_b - (N - 1);
+        const int lo_a = N - 1 - pos_a, lo_b = N - 1 - pos_b;   // valid r: lo <= r < lo + N
+        const int KS = (R + 7) >> 3;
+        for (int ks = 0; ks < KS; ++ks) {
+          const int r0 = 8 * ks + t, r1 = r0 + 4;
+          const uint32_t a0 = (unsigned)(r0 - lo_a) < (unsigned)N ? f2tf32(rowa[r0]) : 0u;
+          const uint32_t a1 = (unsigned)(r0 - lo_b) < (unsigned)N ? f2tf32(rowb[r0]) : 0u;
+          const uint32_t a2 = (unsigned)(r1 - lo_a) < (unsigned)N ? f2tf32(rowa[r1]) : 0u;
+          const uint32_t a3 = (unsigned)(r1 - lo_b) < (unsigned)N ? f2tf32(rowb[r1]) : 0u;
+#pragma unroll
+          for (int nt = 0; nt < NTE; ++nt)
+            mma_tf32(c[nt], a0, a1, a2, a3, tab[(8 * nt + g) * PT + r0], tab[(8 * nt + g) * PT + r1]);
+        }
+      }
+      const int b = bn / p.nh, n = bn - b * p.nh;
+#pragma unroll
+      for (int nt = 0; nt < NTE; ++nt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = h ? rb : ra, e = 8 * nt + 2 * t;
+          if (r < nrows && e < p.dkh) {
+            const float v0 = c[nt][2 * h] + da[r * p.PA + e];
+            const float v1 = (e + 1 < p.dkh) ? c[nt][2 * h + 1] + da[r * p.PA + e + 1] : 0.f;
+            if (p.dq) {
+              p.dq[(row0 + r) * p.dkh + e] = v0;
+              if (e + 1 < p.dkh) p.dq[(row0 + r) * p.dkh + e + 1] = v1;
+            }
+            if (p.dqkvh) {
+              bf16* dst = p.dqkvh + ((size_t)b * p.L + l0 + r) * p.KPq + n * p.dkh + e;
+              if (((p.dkh | p.KPq) & 1) == 0) {              // e is even: 4-byte aligned pair
+                *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(v0 * p.qscale, v1 * p.qscale);
+              } else {
+                dst[0] = __float2bfloat16(v0 * p.qscale);
+                if (e + 1 < p.dkh) dst[1] = __float2bfloat16(v1 * p.qscale);
+              }
+            }
+          }
+        }
+    } else {
+      // ---------------- G role: one axis, 32 rows ----------------
+      const int axis = (warp - 4) >> 1, rh = ((warp - 4) & 1) * 32;
+      const int N = axis ? p.H : p.W, R = axis ? p.RH : p.RW;
+      const int colbase = p.dkh + (axis ? p.W : 0);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int k0 = rh + 8 * ks + t, k1 = k0 + 4;
+        const int l_0 = l0 + k0, l_1 = l0 + k1;
+        const int pos0 = axis ? l_0 / p.W : l_0 % p.W, pos1 = axis ? l_1 / p.W : l_1 % p.W;
+        const float* row0p = da + k0 * p.PA + colbase + pos0 - (N - 1);
+        const float* row1p = da + k1 * p.PA + colbase + pos1 - (N - 1);
+        const int lo0 = N - 1 - pos0, lo1 = N - 1 - pos1;
+        uint32_t b0[NTE], b1[NTE];
+#pragma unroll
+        for (int nt = 0; nt < NTE; ++nt) {
+          b0[nt] = f2tf32(qs[k0 * PQ2 + 8 * nt + g]);
+          b1[nt] = f2tf32(qs[k1 * PQ2 + 8 * nt + g]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int r_a = 16 * mt + g, r_b = r_a + 8;
+          if (16 * mt < R) {
+            const uint32_t a0 = (unsigned)(r_a - lo0) < (unsigned)N ? f2tf32(row0p[r_a]) : 0u;
+            const uint32_t a1 = (unsigned)(r_b - lo0) < (unsigned)N ? f2tf32(row0p[r_b]) : 0u;
+            const uint32_t a2 = (unsigned)(r_a - lo1) < (unsigned)N ? f2tf32(row1p[r_a]) : 0u;
+            const uint32_t a3 = (unsigned)(r_b - lo1) < (unsigned)N ? f2tf32(row1p[r_b]) : 0u;
+#pragma unroll
+            for (int nt = 0; nt < NTE; ++nt) mma_tf32(acc[mt][nt], a0, a1, a2, a3, b0[nt], b1[nt]);
+          }
+        }
+      }
+    }
+  }
+  // ---- CTA partial of the key_rel gradients: sum the two row-half warps of each axis in a fixed order ----
+  __syncthreads();
+  float* red = da;                                   // [4 warps][RP * DK8]  (fits: RP*DK8 <= 128*32 floats per warp ... checked on host)
+  if (warp >= 4) {
+    float* mine = red + (warp - 4) * p.RP * p.DK8;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NTE; ++nt) {
+        const int r = 16 * mt + g, e = 8 * nt + 2 * t;
+        if (r < p.RP && e < p.DK8) {
+          mine[r * p.DK8 + e] = acc[mt][nt][0];
+          mine[r * p.DK8 + e + 1] = acc[mt][nt][1];
+        }
+        if (r + 8 < p.RP && e < p.DK8) {
+          mine[(r + 8) * p.DK8 + e] = acc[mt][nt][2];
+          mine[(r + 8) * p.DK8 + e + 1] = acc[mt][nt][3];
+        }
+      }
+  }
+  __syncthreads();
+  const int per_axis = p.RP * p.DK8;
+  float* out = p.partial + (size_t)blockIdx.x * 2 * per_axis;
+  for (int i = threadIdx.x; i < 2 * per_axis; i += blockDim.x) {
+    const int axis = i / per_axis, j = i - axis * per_axis;
+    out[i] = red[(2 * axis) * per_axis + j] + red[(2 * axis + 1) * per_axis + j];
+  }
+}
+
+// dkr[e, r] = sum over CTAs of partial[cta][axis][r][e]   (fixed order: deterministic).  Block = 32 outputs x 8 slices of parts.
+__global__ void __launch_bounds__(256) rel_bwd_reduce_kernel(const float* __restrict__ partial, int nparts, int RP, int DK8,
+                                                             int dkh, int RW, int RH, float* __restrict__ dkrw,
+                                                             float* __restrict__ dkrh) {
+  __shared__ float red[8][33];
+  const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + o;
+  const int per_axis = RP * DK8;
+  float s = 0.f;
+  if (i < 2 * per_axis)
+    for (int c = sl; c < nparts; c += 8) s += partial[(size_t)c * 2 * per_axis + i];
+  red[sl][o] = s;
+  __syncthreads();
+  if (sl == 0 && i < 2 * per_axis) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += red[k][o];
+    const int axis = i / per_axis, j = i - axis * per_axis, r = j / DK8, e = j - r * DK8;
+    float* dst = axis ? dkrh : dkrw;
+    const int R = axis ? RH : RW;
+    if (dst && r < R && e < dkh) dst[e * R + r] = tot;
+  }
+}
+
+template <int MT, int NTE>
+int launch_rel_bwd(const RelBwdP& p, int grid, size_t smem, cudaStream_t st) {
+  auto kern = rel_bwd_kernel<MT, NTE>;
+  AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, 256, smem, st>>>(p);
+  AACONV_LAUNCH_OK("rel_bwd");
+  return 0;
+}
+
+template <int NTE>
+int dispatch_rel_bwd(int mt, const RelBwdP& p, int grid, size_t smem, cudaStream_t st) {
+  if (mt <= 1) return launch_rel_bwd<1, NTE>(p, grid, smem, st);
+  if (mt <= 2) return launch_rel_bwd<2, NTE>(p, grid, smem, st);
+  if (mt <= 3) return launch_rel_bwd<3, NTE>(p, grid, smem, st);
+  if (mt <= 5) return launch_rel_bwd<5, NTE>(p, grid, smem, st);
+  return launch_rel_bwd<8, NTE>(p, grid, smem, st);
+}
+
+constexpr int REL_BWD_GRID = 148 * 2;
+
+}  // namespace
+
+int rel_bwd_supported(const Dims& d) {
+  if (!d.relative) return AACONV_E_UNSUPPORTED;
+  if (std::max(d.RW, d.RH) > 128 || d.dkh > 32) return AACONV_E_UNSUPPORTED;
+  return 0;
+}
+
+size_t rel_bwd_partial_floats(const Dims& d) {
+  if (rel_bwd_supported(d)) return 0;
+  const int RP = cdiv(std::max(d.RW, d.RH), 16) * 16, DK8 = cdiv(d.dkh, 8) * 8;
+  return (size_t)REL_BWD_GRID * 2 * RP * DK8;
+}
+
+// dqa (B,nh,L,KD) fp32, q (B,nh,L,dkh) fp32 (scaled q).  Writes dq (fp32, optional), dqkvh (bf16 packed, optional),
+// and the key_rel gradients (optional).
+int rel_bwd(const Dims& d, const float* dqa, const float* q, const float* krw, const float* krh, float* dq, void* dqkvh,
+            int KPq, float* dkrw, float* dkrh, float* partial, cudaStream_t st) {
+  AACONV_TRY(rel_bwd_supported(d));
+  const AugLayout a = aug_layout(d);
+  RelBwdP p;
+  p.dqa = dqa; p.q = q; p.krw = krw; p.krh = krh; p.dq = dq; p.dqkvh = static_cast<bf16*>(dqkvh); p.partial = partial;
+  p.L = d.L; p.H = d.H; p.W = d.W; p.nh = d.nh; p.dkh = d.dkh; p.KD = a.KD; p.KPq = KPq; p.relative = d.relative;
+  p.DK8 = cdiv(d.dkh, 8) * 8; p.RW = d.RW; p.RH = d.RH;
+  p.PBW = p.PBH = 0;
+  p.PTW = pitch_mod32(cdiv(d.RW, 8) * 8, 4); p.PTH = pitch_mod32(cdiv(d.RH, 8) * 8, 4);
+  p.PA = pitch_mod32(a.KD, 3);
+  p.RP = cdiv(std::max(d.RW, d.RH), 16) * 16;
+  p.tiles_per_bn = cdiv(d.L, TR); p.ntiles = p.tiles_per_bn * d.BN;
+  p.qscale = d.qscale;
+  const int mt = p.RP / 16, nte = p.DK8 / 8;
+  size_t tile_floats = (size_t)TR * p.PA + (size_t)TR * PQ2;
+  tile_floats = std::max(tile_floats, (size_t)4 * p.RP * p.DK8);       // the reduction buffer aliases the tile
+  const size_t smem = sizeof(uint32_t) * p.DK8 * (size_t)(p.PTW + p.PTH) + sizeof(float) * tile_floats;
+  if (smem > 200 * 1024) return fail(AACONV_E_UNSUPPORTED, "rel_bwd: %zu B of shared memory needed", smem);
+  const int grid = std::min(p.ntiles, REL_BWD_GRID);
+  if (nte <= 3) AACONV_TRY(dispatch_rel_bwd<3>(mt, p, grid, smem, st));
+  else AACONV_TRY(dispatch_rel_bwd<4>(mt, p, grid, smem, st));
+  if (dkrw || dkrh) {
+    const int n = 2 * p.RP * p.DK8;
+    rel_bwd_reduce_kernel<<<cdiv(n, 32), 256, 0, st>>>(partial, grid, p.RP, p.DK8, d.dkh, d.RW, d.RH, dkrw, dkrh);
+    AACONV_LAUNCH_OK("rel_bwd_reduce");
+  }
+  return 0;
+}
+
+}  // namespace aaconv

@@ -9,8 +9,7 @@ namespace aaconv {
 
 namespace {
 struct Scratch {
-  float *d_o, *delta, *dq, *dk, *dv, *partial, *dqa, *rw, *rh, *o_tmp, *lse_tmp;
-  void *qa, *ka, *fwd_operands;
+  float *d_o, *dq, *dk, *dv, *partial, *relpart, *dqa, *rw, *rh, *o_tmp, *lse_tmp;
   TcGemmBufs gemm;
   bool gemm_ok;
   size_t bytes;
@@ -19,15 +18,12 @@ struct Scratch {
     const size_t rows = (size_t)d.BN * d.L;
     const AugLayout a = aug_layout(d);
     d_o = c.take<float>(rows * d.dvh);
-    delta = c.take<float>(rows);
     dq = c.take<float>(rows * d.dkh);
     dk = c.take<float>(rows * d.dkh);
     dv = c.take<float>(rows * d.dvh);
     partial = c.take<float>(std::max(f32_partial_floats(d), tc_gemm_supported(d) == 0 ? tc_wgrad_partial_floats(d) : 0));
+    relpart = c.take<float>(rel_bwd_partial_floats(d));
     dqa = c.take<float>(rows * a.KD);
-    qa = c.take<uint16_t>(rows * a.KP);
-    ka = c.take<uint16_t>(rows * a.KP);
-    fwd_operands = c.take<char>(tc_attn_operand_bytes(d, nullptr, nullptr, nullptr));
     gemm_ok = tc_gemm_supported(d) == 0;
     {
       char* gb = c.take<char>(gemm_ok ? tc_gemm_bufs(d, nullptr).bytes : 0);
@@ -43,9 +39,25 @@ struct Scratch {
 };
 template <class T>
 T* at(const void* base, int64_t off) { return reinterpret_cast<T*>(static_cast<char*>(const_cast<void*>(base)) + off); }
+
+// saved block = the fp32 block (q,k,v,o,lse; same offsets as the fp32 path) followed by the augmented operands
+struct SavedAug {
+  void *qa, *ka, *xh;       // xh: channels-last bf16 copy of x (fprop operand, reused by wgrad)
+  size_t bytes;
+  SavedAug(const Dims& d, const void* base) {
+    Carver c(const_cast<void*>(base));
+    c.take<char>(f32_saved_bytes(d));
+    const size_t rows = (size_t)d.BN * d.L;
+    const AugLayout a = aug_layout(d);
+    qa = c.take<uint16_t>(rows * a.KP);
+    ka = c.take<uint16_t>(rows * a.KP);
+    xh = c.take<uint16_t>(tc_gemm_supported(d) == 0 ? (size_t)d.B * d.Hin * d.Win * (cdiv(d.Cin, 64) * 64) : 0);
+    bytes = c.off;
+  }
+};
 }  // namespace
 
-size_t bf16_saved_bytes(const Dims& d) { return f32_saved_bytes(d); }
+size_t bf16_saved_bytes(const Dims& d) { return SavedAug(d, nullptr).bytes; }
 size_t bf16_scratch_bytes(const Dims& d, int want_weights) {
   if (aug_supported(d) || tc_attn_supported(d)) return 0;
   return Scratch(d, nullptr, want_weights).bytes;
@@ -62,13 +74,16 @@ int bf16_forward(const Dims& d, const float* x, const aaconv_params* p, float* y
   float* v = at<float>(saved, f32_saved_offset(d, "v"));
   float* o = at<float>(saved, f32_saved_offset(d, "o"));
   float* lse = at<float>(saved, f32_saved_offset(d, "lse"));
+  SavedAug sa(d, saved);
   if (w.gemm_ok) {
+    w.gemm.xh = sa.xh;
     AACONV_TRY(tc_fprop(d, w.gemm, x, p->conv_w, p->qkv_w, y, q, k, v, st));
   } else {   // geometry outside the TMA tiling (e.g. rows wider than 128 pixels): FFMA implicit GEMM
     AACONV_TRY(f32_conv_fwd(d, x, p->conv_w, y, st));
     AACONV_TRY(f32_qkv_fwd(d, x, p->qkv_w, q, k, v, st));
   }
-  AACONV_TRY(tc_attn_fwd(d, q, k, v, p->key_rel_w, p->key_rel_h, w.fwd_operands, o, lse, st));
+  AACONV_TRY(aug_build_fwd(d, q, k, v, p->key_rel_w, p->key_rel_h, sa.qa, sa.ka, st));
+  AACONV_TRY(tc_attn_fwd(d, sa.qa, sa.ka, o, lse, st));
   if (weights) {   // visualise path only: exact fp32 map (own fp32 statistics), independent of the bf16 kernel
     AACONV_TRY(f32_rel_fwd(d, q, p->key_rel_w, p->key_rel_h, w.rw, w.rh, st));
     AACONV_TRY(f32_attn_fwd(d, q, k, v, w.rw, w.rh, w.o_tmp, w.lse_tmp, st));
@@ -89,20 +104,31 @@ int bf16_backward(const Dims& d, const float* x, const aaconv_params* p, const f
   const float* o = at<float>(saved, f32_saved_offset(d, "o"));
   const float* lse = at<float>(saved, f32_saved_offset(d, "lse"));
   AACONV_TRY(f32_out_bwd(d, dy, o, p->out_w, w.d_o, g->out_w, w.partial, st));
-  AACONV_TRY(f32_delta(d, w.d_o, o, w.delta, st));
-  AACONV_TRY(aug_build(d, 1, q, k, v, p->key_rel_w, p->key_rel_h, lse, w.d_o, w.delta, w.qa, w.ka, st));
-  AACONV_TRY(tc_attn_bwd(d, w.qa, w.ka, w.dqa, w.dk, w.dv, st));
-  if (d.relative) {
-    if (g->key_rel_w) AACONV_TRY(aug_rel_weight_grad(d, q, w.dqa, a.KD, 0, g->key_rel_w, w.partial, st));
-    if (g->key_rel_h) AACONV_TRY(aug_rel_weight_grad(d, q, w.dqa, a.KD, 1, g->key_rel_h, w.partial, st));
+  SavedAug sa(d, saved);
+  // the backward-only columns of Qa (-lse, dO, -delta) are filled in place; idempotent, so a retained graph may
+  // run backward again
+  AACONV_TRY(aug_patch_bwd(d, lse, w.d_o, o, sa.qa, st));
+  // fast path: the attention-backward kernels write dq*scale, dk, dv as bf16 straight into the packed (B*L, KPq)
+  // operand of the projection dgrad/wgrad GEMMs; its padding columns must be finite (they meet zero weights)
+  const bool direct = w.gemm_ok && rel_bwd_supported(d) == 0 && tc_wgrad_supported(d) == 0;
+  if (direct) AACONV_CUDA_OK(cudaMemsetAsync(w.gemm.dqkvh, 0, sizeof(uint16_t) * (size_t)d.B * d.L * w.gemm.KPq, st));
+  AACONV_TRY(tc_attn_bwd(d, sa.qa, sa.ka, w.dqa, w.dk, w.dv, direct ? w.gemm.dqkvh : nullptr, w.gemm.KPq, st));
+  if (direct) {
+    AACONV_TRY(rel_bwd(d, w.dqa, q, p->key_rel_w, p->key_rel_h, nullptr, w.gemm.dqkvh, w.gemm.KPq, g->key_rel_w, g->key_rel_h,
+                       w.relpart, st));
+  } else {
+    if (d.relative) {
+      if (g->key_rel_w) AACONV_TRY(aug_rel_weight_grad(d, q, w.dqa, a.KD, 0, g->key_rel_w, w.partial, st));
+      if (g->key_rel_h) AACONV_TRY(aug_rel_weight_grad(d, q, w.dqa, a.KD, 1, g->key_rel_h, w.partial, st));
+    }
+    AACONV_TRY(aug_bwd_dq(d, w.dqa, p->key_rel_w, p->key_rel_h, w.dq, st));
   }
-  AACONV_TRY(aug_bwd_dq(d, w.dqa, p->key_rel_w, p->key_rel_h, w.dq, st));
   if (w.gemm_ok) {
-    AACONV_TRY(tc_pack_grads(d, w.gemm, dy, w.dq, w.dk, w.dv, st));
+    AACONV_TRY(tc_pack_grads(d, w.gemm, dy, direct ? nullptr : w.dq, w.dk, w.dv, st));
     if (dx) AACONV_TRY(tc_dgrad(d, w.gemm, p->conv_w, p->qkv_w, dx, st));
     if (g->conv_w || g->qkv_w) {
       if (tc_wgrad_supported(d) == 0) {
-        AACONV_TRY(pack_nhwc_bf16(x, w.gemm.xh, d.B, d.Cin, w.gemm.CinK, d.Hin * d.Win, st));
+        w.gemm.xh = sa.xh;             // packed by forward
         AACONV_TRY(tc_wgrad(d, w.gemm, d.Cc ? g->conv_w : nullptr, g->qkv_w, w.partial, st));
       } else {
         if (d.Cc) AACONV_TRY(f32_conv_bwd(d, x, p->conv_w, dy, nullptr, g->conv_w, w.partial, st));

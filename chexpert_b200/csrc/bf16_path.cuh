@@ -15,17 +15,22 @@ constexpr float AUG_BIG = 64.f;   // log2-units shift of in-range logits in forw
 
 AugLayout aug_layout(const Dims& d);
 int aug_supported(const Dims& d);
-int aug_build(const Dims& d, int mode, const float* q, const float* k, const float* v, const float* krw,
-              const float* krh, const float* lse, const float* d_o, const float* delta, void* qa, void* ka,
-              cudaStream_t st);
-int tc_attn_bwd(const Dims& d, const void* qa, const void* ka, float* dqa, float* dk, float* dv, cudaStream_t st);
+// aug_ops.cu
+int aug_build_fwd(const Dims& d, const float* q, const float* k, const float* v, const float* krw, const float* krh,
+                  void* qa, void* ka, cudaStream_t st);
+int aug_patch_bwd(const Dims& d, const float* lse, const float* d_o, const float* o, void* qa, cudaStream_t st);
+int rel_bwd_supported(const Dims& d);
+size_t rel_bwd_partial_floats(const Dims& d);
+int rel_bwd(const Dims& d, const float* dqa, const float* q, const float* krw, const float* krh, float* dq, void* dqkvh,
+            int KPq, float* dkrw, float* dkrh, float* partial, cudaStream_t st);
+// dk/dv go to fp32 head-split tensors, or (dqkvh != NULL) as bf16 straight into the packed (B*L, KPq) projection-gradient operand
+int tc_attn_bwd(const Dims& d, const void* qa, const void* ka, float* dqa, float* dk, float* dv, void* dqkvh, int KPq,
+                cudaStream_t st);
 int aug_bwd_dq(const Dims& d, const float* dqa, const float* krw, const float* krh, float* dq, cudaStream_t st);
 
 // attn_tc.cu (forward)
 int tc_attn_supported(const Dims& d);
-size_t tc_attn_operand_bytes(const Dims& d, size_t* qa_off, size_t* ka_off, size_t* vt_off);
-int tc_attn_fwd(const Dims& d, const float* q, const float* k, const float* v, const float* krw, const float* krh,
-                void* operands, float* o, float* lse, cudaStream_t st);
+int tc_attn_fwd(const Dims& d, const void* qa, const void* ka, float* o, float* lse, cudaStream_t st);
 
 // gemm_tc.cu (tcgen05 implicit GEMMs)
 struct TcGemmBufs {
@@ -39,7 +44,7 @@ int pack_nhwc_bf16(const float* in, void* out, int B, int C, int Cp, int HW, cud
 int tc_fprop(const Dims& d, const TcGemmBufs& t, const float* x, const float* conv_w, const float* qkv_w, float* y,
              float* q, float* k, float* v, cudaStream_t st);
 int tc_pack_grads(const Dims& d, const TcGemmBufs& t, const float* dy, const float* dq, const float* dk, const float* dv,
-                  cudaStream_t st);
+                  cudaStream_t st);   // dq == NULL: dqkvh was already written by the attention backward kernels
 int tc_dgrad(const Dims& d, const TcGemmBufs& t, const float* conv_w, const float* qkv_w, float* dx, cudaStream_t st);
 int tc_zero_class(const Dims& d, float* dx, int rh, int rw, cudaStream_t st);
 int tc_wgrad_supported(const Dims& d);

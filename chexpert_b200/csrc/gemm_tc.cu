@@ -36,13 +36,13 @@ struct PGParams {
   int mode;                        // 0 fprop, 1 dgrad
   float* out0; float* q; float* k; float* v;
   int Cout, Cc, H, W, L, nh, dk, dkh, dvh, Nqkv; float qscale;           // fprop
-  int Cin, Hin, Win, stride, rh, rw;                                      // dgrad
+  int Cin, Hin, Win, stride, rh, rw, pair;                                // dgrad
 };
 
 struct __align__(1024) PGSmem {
   bf16 a[PG_STAGES][128 * 64];
   bf16 b[PG_STAGES][128 * 64];
-  uint64_t bar_full[PG_STAGES], bar_empty[PG_STAGES], bar_acc;
+  uint64_t bar_full[PG_STAGES], bar_empty[PG_STAGES], bar_acc[PG_MAX_CHUNKS];
   uint32_t tmem_base;
 };
 
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_tc_kernel(const __gr
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < PG_STAGES; ++s) { tc::mbar_init(&sm.bar_full[s], 1); tc::mbar_init(&sm.bar_empty[s], 1); }
-    tc::mbar_init(&sm.bar_acc, 1);
+    for (int c = 0; c < PG_MAX_CHUNKS; ++c) tc::mbar_init(&sm.bar_acc[c], 1);
     tc::fence_barrier_init();
   }
   if (warp == 5) tc::tmem_alloc<512>(&sm.tmem_base);
@@ -107,27 +107,29 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_tc_kernel(const __gr
           acc = 1;
         }
       }
+      if (tc::elect_one()) tc::mma_commit(&sm.bar_acc[c]);     // chunk c complete: its epilogue overlaps chunk c+1
+      __syncwarp();
     }
-    if (tc::elect_one()) tc::mma_commit(&sm.bar_acc);
-    __syncwarp();
   } else {
-    // ===================== epilogue: thread == tile pixel == TMEM lane =====================
-    tc::mbar_wait(&sm.bar_acc, 0);
-    tc::tc_fence_after();
+    // ===================== epilogue: thread == tile pixel == TMEM lane; chunk c as soon as its MMAs are done =====================
     const int m = threadIdx.x;                       // 0..127
     const int hh = m / p.Wt, ww = m - hh * p.Wt;
     const int hrow = h0 + hh;
     const bool valid = m < p.r * p.Wt && hrow < p.Ht;
     const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
     uint32_t rr[32];
-    for (int c = 0; c < p.nchunks; ++c) {
-      const PGChunk ch = p.chunks[c];
-      for (int cb = 0; cb < 4; ++cb) {
-        tc::tmem_ld_x32(tlane + c * 128 + cb * 32, rr);
-        tc::tmem_ld_wait();
-        if (!valid) continue;
-        if (p.mode == 0) {
-          const int l = hrow * p.W + ww;
+    if (p.mode == 0) {
+      const int l = hrow * p.W + ww;
+      const bool vec = (p.dkh & 3) == 0;             // aligned groups of 4 columns never straddle a head
+      for (int c = 0; c < p.nchunks; ++c) {
+        const PGChunk ch = p.chunks[c];
+        tc::mbar_wait(&sm.bar_acc[c], 0);
+        tc::tc_fence_after();
+        for (int cb = 0; cb < 4; ++cb) {
+          if (ch.n0 + cb * 32 >= (ch.kind == 0 ? p.Cc : p.Nqkv)) break;   // uniform
+          tc::tmem_ld_x32(tlane + c * 128 + cb * 32, rr);
+          tc::tmem_ld_wait();
+          if (!valid) continue;
           if (ch.kind == 0) {                        // conv channels -> y NCHW (lanes = consecutive pixels: coalesced)
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
@@ -136,27 +138,89 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_tc_kernel(const __gr
             }
           } else {                                   // qkv channels -> head-split q (scaled), k, v
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const int n = ch.n0 + cb * 32 + e;
-              const float val = __uint_as_float(rr[e]);
-              if (n < p.dk) {
-                const int hd = n / p.dkh, ee = n - hd * p.dkh;
-                p.q[((size_t)(b * p.nh + hd) * p.L + l) * p.dkh + ee] = val * p.qscale;
-              } else if (n < 2 * p.dk) {
-                const int cc = n - p.dk, hd = cc / p.dkh, ee = cc - hd * p.dkh;
-                p.k[((size_t)(b * p.nh + hd) * p.L + l) * p.dkh + ee] = val;
-              } else if (n < p.Nqkv) {
-                const int cc = n - 2 * p.dk, hd = cc / p.dvh, ee = cc - hd * p.dvh;
-                p.v[((size_t)(b * p.nh + hd) * p.L + l) * p.dvh + ee] = val;
+            for (int e4 = 0; e4 < 32; e4 += 4) {
+              const int n = ch.n0 + cb * 32 + e4;
+              if (vec && n + 3 < 2 * p.dk) {         // whole group inside q or inside k
+                const bool isq = n < p.dk;
+                const int cc = isq ? n : n - p.dk, hd = cc / p.dkh, ee = cc - hd * p.dkh;
+                const float sc = isq ? p.qscale : 1.f;
+                float* dst = (isq ? p.q : p.k) + ((size_t)(b * p.nh + hd) * p.L + l) * p.dkh + ee;
+                *reinterpret_cast<float4*>(dst) = make_float4(__uint_as_float(rr[e4]) * sc, __uint_as_float(rr[e4 + 1]) * sc,
+                                                              __uint_as_float(rr[e4 + 2]) * sc, __uint_as_float(rr[e4 + 3]) * sc);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int nn = n + j;
+                  const float val = __uint_as_float(rr[e4 + j]);
+                  if (nn < p.dk) {
+                    const int hd = nn / p.dkh, ee = nn - hd * p.dkh;
+                    p.q[((size_t)(b * p.nh + hd) * p.L + l) * p.dkh + ee] = val * p.qscale;
+                  } else if (nn < 2 * p.dk) {
+                    const int cc = nn - p.dk, hd = cc / p.dkh, ee = cc - hd * p.dkh;
+                    p.k[((size_t)(b * p.nh + hd) * p.L + l) * p.dkh + ee] = val;
+                  } else if (nn < p.Nqkv) {
+                    const int cc = nn - 2 * p.dk, hd = cc / p.dvh, ee = cc - hd * p.dvh;
+                    p.v[((size_t)(b * p.nh + hd) * p.L + l) * p.dvh + ee] = val;
+                  }
+                }
               }
             }
           }
-        } else {                                     // dgrad -> dx NCHW at the pixels of this residue class
-          const int hi = hrow * p.stride + p.rh, wi = ww * p.stride + p.rw;
+        }
+      }
+    } else {
+      // dgrad: chunks come in pairs (2i, 2i+1) = the two column-parity classes (rw = 0, 1) of the same 128 channels;
+      // a thread owns input pixels (hi, 2*ww) and (hi, 2*ww+1) -> one 8-byte store per channel, fully coalesced rows.
+      // With stride 1 (pair == 0) every chunk is its own class.
+      const int hi = hrow * p.stride + p.rh;
+      const bool v0 = valid && hi < p.Hin && ww * p.stride + p.rw < p.Win;
+      if (p.pair) {
+        const int wi = ww * 2;
+        const bool v1 = valid && hi < p.Hin && wi + 1 < p.Win;
+        const bool vec2 = (p.Win & 1) == 0;
+        uint32_t r2[32];
+        for (int c = 0; c < p.nchunks; c += 2) {
+          const PGChunk ch = p.chunks[c];
+          tc::mbar_wait(&sm.bar_acc[c], 0);
+          tc::mbar_wait(&sm.bar_acc[c + 1], 0);
+          tc::tc_fence_after();
+          for (int cb = 0; cb < 4; ++cb) {
+            if (ch.n0 + cb * 32 >= p.Cin) break;
+            tc::tmem_ld_x32(tlane + c * 128 + cb * 32, rr);
+            tc::tmem_ld_x32(tlane + (c + 1) * 128 + cb * 32, r2);
+            tc::tmem_ld_wait();
+            if (!v0) continue;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int n = ch.n0 + cb * 32 + e;
-            if (n < p.Cin) p.out0[(((size_t)b * p.Cin + n) * p.Hin + hi) * p.Win + wi] = __uint_as_float(rr[e]);
+            for (int e = 0; e < 32; ++e) {
+              const int n = ch.n0 + cb * 32 + e;
+              if (n < p.Cin) {
+                float* dst = p.out0 + (((size_t)b * p.Cin + n) * p.Hin + hi) * p.Win + wi;
+                if (vec2) {
+                  *reinterpret_cast<float2*>(dst) = make_float2(__uint_as_float(rr[e]), __uint_as_float(r2[e]));
+                } else {
+                  dst[0] = __uint_as_float(rr[e]);
+                  if (v1) dst[1] = __uint_as_float(r2[e]);
+                }
+              }
+            }
+          }
+        }
+      } else {
+        const int wi = ww * p.stride + p.rw;
+        for (int c = 0; c < p.nchunks; ++c) {
+          const PGChunk ch = p.chunks[c];
+          tc::mbar_wait(&sm.bar_acc[c], 0);
+          tc::tc_fence_after();
+          for (int cb = 0; cb < 4; ++cb) {
+            if (ch.n0 + cb * 32 >= p.Cin) break;
+            tc::tmem_ld_x32(tlane + c * 128 + cb * 32, rr);
+            tc::tmem_ld_wait();
+            if (!v0) continue;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int n = ch.n0 + cb * 32 + e;
+              if (n < p.Cin) p.out0[(((size_t)b * p.Cin + n) * p.Hin + hi) * p.Win + wi] = __uint_as_float(rr[e]);
+            }
           }
         }
       }
@@ -187,7 +251,51 @@ __global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, bf16* __r
   }
 }
 
+// Fast path (HW % 4 == 0): tile = 64 channels x 64 pixels; 256 B coalesced reads along pixels (float4), 128 B
+// coalesced writes along channels (4 x bf16 per lane).
+__global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_v4_kernel(const float* __restrict__ in, bf16* __restrict__ out, int C,
+                                                                   int Cp, int HW) {
+  __shared__ float t[64][65];                                   // [pixel][channel]
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  const float* src = in + (size_t)b * C * HW;
+  bf16* dst = out + (size_t)b * HW * Cp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const int px = p0 + (lane & 15) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int cl = warp * 8 + i * 2 + (lane >> 4), c = c0 + cl;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < C && px < HW) v = *reinterpret_cast<const float4*>(src + (size_t)c * HW + px);   // HW % 4 == 0: all-or-nothing
+      const int pl = (lane & 15) * 4;
+      t[pl][cl] = v.x; t[pl + 1][cl] = v.y; t[pl + 2][cl] = v.z; t[pl + 3][cl] = v.w;
+    }
+  }
+  __syncthreads();
+  {
+    const int cl = (lane & 15) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pl = warp * 8 + i * 2 + (lane >> 4), px = p0 + pl;
+      if (px < HW && c0 + cl < Cp) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(t[pl][cl], t[pl][cl + 1]);
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(t[pl][cl + 2], t[pl][cl + 3]);
+        uint2 w;
+        w.x = *reinterpret_cast<const uint32_t*>(&lo);
+        w.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(dst + (size_t)px * Cp + c0 + cl) = w;
+      }
+    }
+  }
+}
+
 int pack_nhwc_bf16(const float* in, void* out, int B, int C, int Cp, int HW, cudaStream_t st) {
+  if (HW % 4 == 0 && Cp % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    dim3 grid(cdiv(HW, 64), cdiv(Cp, 64), B);
+    nchw_to_nhwc_bf16_v4_kernel<<<grid, 256, 0, st>>>(in, static_cast<bf16*>(out), C, Cp, HW);
+    AACONV_LAUNCH_OK("pack_nhwc_bf16");
+    return 0;
+  }
   dim3 grid(cdiv(HW, 32), cdiv(Cp, 32), B), block(32, 8);
   nchw_to_nhwc_bf16_kernel<<<grid, block, 0, st>>>(in, static_cast<bf16*>(out), C, Cp, HW);
   AACONV_LAUNCH_OK("pack_nhwc_bf16");
@@ -283,7 +391,7 @@ TcGemmBufs tc_gemm_bufs(const Dims& d, void* base) {
   t.CinK = cdiv(d.Cin, 64) * 64;
   t.KPc = cdiv(d.Cout, 64) * 64;       // dy is packed with all Cout channels; weight rows past Cc are zero
   t.KPq = cdiv(d.Nqkv, 64) * 64;
-  t.xh = c.take<uint16_t>((size_t)d.B * d.Hin * d.Win * t.CinK);
+  t.xh = nullptr;                        // lives in the saved block (bf16_path.cu)
   t.dyh = c.take<uint16_t>((size_t)d.B * d.L * t.KPc);
   t.dqkvh = c.take<uint16_t>((size_t)d.B * d.L * t.KPq);
   t.wf = c.take<uint16_t>(((size_t)T * t.NPc + t.NPq) * t.CinK);
@@ -370,6 +478,7 @@ int tc_fprop(const Dims& d, const TcGemmBufs& t, const float* x, const float* co
 int tc_pack_grads(const Dims& d, const TcGemmBufs& t, const float* dy, const float* dq, const float* dk, const float* dv,
                   cudaStream_t st) {
   AACONV_TRY(pack_nhwc_bf16(dy, t.dyh, d.B, d.Cout, t.KPc, d.L, st));
+  if (!dq) return 0;
   pack_dqkv_kernel<<<148 * 8, 256, 0, st>>>(dq, dk, dv, static_cast<bf16*>(t.dqkvh), (size_t)d.B * d.L, d.L, d.nh, d.dk,
                                              d.dkh, d.dvh, d.Nqkv, t.KPq, d.qscale);
   AACONV_LAUNCH_OK("pack_dqkv");
