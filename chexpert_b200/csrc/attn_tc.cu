@@ -22,9 +22,10 @@ typedef __nv_bfloat16 bf16;
 
 constexpr int FA_BM = 128;       // queries per CTA (TMEM lanes)
 constexpr int FA_BN = 128;       // keys per tile
-constexpr int FA_STAGES = 3;     // K smem stages
+constexpr int FA_STAGES = 4;     // K smem stages (>= slots + 1)
+constexpr int FA_SLOTS = 3;      // TMEM score slots: the MMA warp runs up to two tiles ahead of the softmax warpgroups
 constexpr int FA_THREADS = 320;  // warps 0-3 softmax WG0, 4-7 softmax WG1, warp 8 TMA, warp 9 MMA (+TMEM alloc)
-constexpr uint32_t FA_SLOT = 208, FA_COL_P = 128, FA_COL_O = 192;   // per slot: S [0,128) P [128,192) O [192,208)
+constexpr uint32_t FA_SLOT = 128, FA_COL_O = 384;   // slot s: S at 128*s (P, bf16, aliases its first 64 columns); O of warpgroup w at 384 + 16*w
 constexpr float FA_RESCALE_THRESHOLD = 8.f;                          // log2 units
 
 template <int KATOMS>
@@ -32,7 +33,7 @@ struct __align__(1024) FwdSmem {
   bf16 q[KATOMS][FA_BM * 64];                 // K-major, 128 B rows, 128B swizzle (one atom = 64 k-elements)
   bf16 k[FA_STAGES][KATOMS][FA_BN * 64];
   float xch[FA_BM][18];                       // WG1 -> WG0 hand-over of (m, O[0..16))
-  uint64_t bar_q, bar_full[FA_STAGES], bar_empty[FA_STAGES], bar_s_full[2], bar_p_ready[2], bar_o_done[2];
+  uint64_t bar_q, bar_full[FA_STAGES], bar_empty[FA_STAGES], bar_s_full[FA_SLOTS], bar_p_ready[FA_SLOTS], bar_o_done[2];
   uint32_t tmem_base;
 };
 
@@ -49,11 +50,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fwd_tc_kernel(
   if (threadIdx.x == 0) {
     tc::mbar_init(&sm.bar_q, 1);
     for (int s = 0; s < FA_STAGES; ++s) { tc::mbar_init(&sm.bar_full[s], 1); tc::mbar_init(&sm.bar_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(&sm.bar_s_full[s], 1);
-      tc::mbar_init(&sm.bar_p_ready[s], 128);
-      tc::mbar_init(&sm.bar_o_done[s], 1);
-    }
+    for (int s = 0; s < FA_SLOTS; ++s) { tc::mbar_init(&sm.bar_s_full[s], 1); tc::mbar_init(&sm.bar_p_ready[s], 128); }
+    for (int s = 0; s < 2; ++s) tc::mbar_init(&sm.bar_o_done[s], 1);
     tc::fence_barrier_init();
   }
   if (warp == 8 && lane == 0) { tc::tma_prefetch_desc(&tm_q); tc::tma_prefetch_desc(&tm_k); }
@@ -85,9 +83,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fwd_tc_kernel(
     const uint32_t v_lo = tc::desc_lo_mn(smem_u32(sm.k[0][C1 >> 6]) + (C1 & 63) * 2, FA_BN * 128);
     const int nks = C1 >> 4;
     tc::mbar_wait(&sm.bar_q, 0);
-    for (int j = 0; j <= ntiles; ++j) {
+    for (int j = 0; j < ntiles + FA_SLOTS - 1; ++j) {
       if (j < ntiles) {
-        const int st = j % FA_STAGES, slot = j & 1;
+        const int st = j % FA_STAGES, slot = j % FA_SLOTS;
         tc::mbar_wait(&sm.bar_full[st], (j / FA_STAGES) & 1);
         tc::tc_fence_after();
         if (tc::elect_one()) {
@@ -99,17 +97,18 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fwd_tc_kernel(
         }
         __syncwarp();
       }
-      if (j > 0) {
-        const int jj = j - 1, st = jj % FA_STAGES, slot = jj & 1;
-        tc::mbar_wait(&sm.bar_p_ready[slot], (jj >> 1) & 1);
+      const int jj = j - (FA_SLOTS - 1);
+      if (jj >= 0) {
+        const int st = jj % FA_STAGES, slot = jj % FA_SLOTS, wgo = jj & 1;
+        tc::mbar_wait(&sm.bar_p_ready[slot], (jj / FA_SLOTS) & 1);
         tc::tc_fence_after();
         if (tc::elect_one()) {
-          const uint32_t vb = v_lo + st * K_STAGE, tslot = tmem + FA_SLOT * slot;
+          const uint32_t vb = v_lo + st * K_STAGE, tp = tmem + FA_SLOT * slot, to = tmem + FA_COL_O + 16 * wgo;
 #pragma unroll
           for (int ks = 0; ks < FA_BN / 16; ++ks)    // 16 keys = 16 rows of 128 B = 2048 B = 128 descriptor units
-            tc::mma_ts(tslot + FA_COL_O, tslot + FA_COL_P + ks * 8, tc::desc64(vb + ks * 128), idesc_o, (jj > 1 || ks > 0) ? 1u : 0u);
+            tc::mma_ts(to, tp + ks * 8, tc::desc64(vb + ks * 128), idesc_o, (jj > 1 || ks > 0) ? 1u : 0u);
           tc::mma_commit(&sm.bar_empty[st]);
-          tc::mma_commit(&sm.bar_o_done[slot]);
+          tc::mma_commit(&sm.bar_o_done[wgo]);
         }
         __syncwarp();
       }
@@ -118,13 +117,15 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fwd_tc_kernel(
     // ===================== softmax warpgroups (thread == query row == TMEM lane) =====================
     const int wg = warp >> 2;
     const int rowi = (warp & 3) * 32 + lane;
-    const uint32_t tslot = tmem + ((uint32_t)((warp & 3) * 32) << 16) + FA_SLOT * wg;
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t tout = tlane + FA_COL_O + 16 * wg;
     float m = -INFINITY;                      // reference maximum of this warpgroup's exponentials (log2 units)
     uint32_t r[4][32];
     int nmine = 0;
     for (int j = wg; j < ntiles; j += 2, ++nmine) {
-      const int it = j >> 1;
-      tc::mbar_wait(&sm.bar_s_full[wg], it & 1);
+      const int it = j >> 1, slot = j % FA_SLOTS;
+      const uint32_t tslot = tlane + FA_SLOT * slot;
+      tc::mbar_wait(&sm.bar_s_full[slot], (j / FA_SLOTS) & 1);
       tc::tc_fence_after();
       tc::tmem_ld_x32(tslot + 0, r[0]);
       tc::tmem_ld_x32(tslot + 32, r[1]);
@@ -163,11 +164,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fwd_tc_kernel(
           const float m_new = fmaxf(m, mt);
           const float alpha = tc::ex2f(m - m_new);
           uint32_t ov[16];
-          tc::tmem_ld_x16(tslot + FA_COL_O, ov);
+          tc::tmem_ld_x16(tout, ov);
           tc::tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-          tc::tmem_st_x16(tslot + FA_COL_O, ov);
+          tc::tmem_st_x16(tout, ov);
           m = m_new;
         }
       } else {
@@ -185,11 +186,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fwd_tc_kernel(
             const float p1 = tc::ex2f(__uint_as_float(r[c + h][2 * i + 1]) + mneg);
             pk[h * 16 + i] = tc::pack_bf16x2(p0, p1);
           }
-        tc::tmem_st_x32(tslot + FA_COL_P + c * 16, pk);
+        tc::tmem_st_x32(tslot + c * 16, pk);          // P over S[0,64): the whole S row is already in registers
       }
       tc::tmem_st_wait();
       tc::tc_fence_before();
-      tc::mbar_arrive(&sm.bar_p_ready[wg]);
+      tc::mbar_arrive(&sm.bar_p_ready[slot]);
     }
     // ---- merge the two warpgroups' partial results ----
     uint32_t ov[16];
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fwd_tc_kernel(
     if (nmine > 0) {
       tc::mbar_wait(&sm.bar_o_done[wg], (nmine - 1) & 1);
       tc::tc_fence_after();
-      tc::tmem_ld_x16(tslot + FA_COL_O, ov);
+      tc::tmem_ld_x16(tout, ov);
       tc::tmem_ld_wait();
     }
     if (wg == 1) {

@@ -29,35 +29,58 @@ typedef __nv_bfloat16 bf16;
 constexpr int PP_THREADS = 320;
 constexpr int PP_BM = 128;        // stationary rows (TMEM lanes)
 constexpr int PP_BN = 64;         // streamed rows per tile (TMEM columns per slot)
-constexpr int PP_STAGES = 4;
+constexpr int PP_STAGES = 5;      // smem stages of the streamed operand (>= slots + 1)
+constexpr int PP_SLOTS = 3;       // TMEM score slots: the MMA warp runs up to two tiles ahead of the math warpgroups
+constexpr uint32_t PP_SLOT_COLS = 128;   // per slot: S' [0,64) dP' [64,128);  P aliases S'[0,32), dS aliases dP'[0,32)
 
 template <int KATOMS>
 struct __align__(1024) PPSmem {
   bf16 stat[KATOMS][PP_BM * 64];                   // stationary operand, 16 KB per 64-column atom
   bf16 strm[PP_STAGES][KATOMS][PP_BN * 64];        // streamed operand, 8 KB per atom
   uint64_t bar_stat, bar_full[PP_STAGES], bar_empty[PP_STAGES];
-  uint64_t bar_s_full[2], bar_p_ready[2], bar_mma_done[2];
+  uint64_t bar_s_full[PP_SLOTS], bar_p_ready[PP_SLOTS], bar_final;
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ uint64_t desc_k(const void* atom_base, int ks) {          // K-major, k-step ks inside the atom
-  return tc::desc_advance(tc::smem_desc_sw128_kmajor(smem_u32(atom_base)), (ks & 3) * 32);
-}
-// MN-major view of a streamed tile: B[n, kk] = tile[row kk][col n0 + n]; rows are 128 B apart, 8-row groups
-// 1024 B apart (SBO), 64-column chunks one atom (PP_BN*128 B) apart (LBO).
-__device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 __host__ __device__ constexpr uint32_t idesc_bmn(int M, int N) { return tc::idesc_bf16_f32(M, N) | (1u << 16); }
 
+// Shared skeleton of the two kernels.
+//   warp 8: TMA producer;  warp 9: MMA issuer;  warps 0-7: two math warpgroups, WG w takes tiles j = w (mod 2).
+//   Tile j uses TMEM slot j % nslots.  The MMA warp issues the score MMAs of tile j as soon as the slot's previous
+//   tile (j - nslots) has had its gradient MMAs ISSUED (tcgen05.mma of one thread execute in order, so the slot's
+//   P/dS -- which alias the score columns -- are consumed before they are overwritten); the gradient MMAs of tile
+//   j - (nslots-1) follow.  A warpgroup therefore finds its next scores ready when it finishes a tile.
+template <int KATOMS>
+__device__ __forceinline__ void pp_init(PPSmem<KATOMS>& sm, int warp, int lane, const CUtensorMap* m0, const CUtensorMap* m1) {
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&sm.bar_stat, 1);
+    for (int s = 0; s < PP_STAGES; ++s) { tc::mbar_init(&sm.bar_full[s], 1); tc::mbar_init(&sm.bar_empty[s], 1); }
+    for (int s = 0; s < PP_SLOTS; ++s) { tc::mbar_init(&sm.bar_s_full[s], 1); tc::mbar_init(&sm.bar_p_ready[s], 128); }
+    tc::mbar_init(&sm.bar_final, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 8 && lane == 0) { tc::tma_prefetch_desc(m0); tc::tma_prefetch_desc(m1); }
+  if (warp == 9) tc::tmem_alloc<512>(&sm.tmem_base);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+}
+
+template <int KATOMS>
+__device__ __forceinline__ void pp_producer(PPSmem<KATOMS>& sm, const CUtensorMap* m_stat, const CUtensorMap* m_strm, int r0,
+                                            int bn, int ntiles) {
+  tc::mbar_arrive_expect_tx(&sm.bar_stat, KATOMS * PP_BM * 64 * 2);
+  for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.stat[a], m_stat, &sm.bar_stat, a * 64, r0, bn);
+  for (int j = 0; j < ntiles; ++j) {
+    const int s = j % PP_STAGES, ph = (j / PP_STAGES) & 1;
+    tc::mbar_wait(&sm.bar_empty[s], ph ^ 1);
+    tc::mbar_arrive_expect_tx(&sm.bar_full[s], KATOMS * PP_BN * 64 * 2);
+    for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.strm[s][a], m_strm, &sm.bar_full[s], a * 64, j * PP_BN, bn);
+  }
+}
+
 // ---- key-stationary: dK, dV ------------------------------------------------------------------------
-// TMEM columns: slot s at 192*s: S'^T [0,64) dP'^T [64,128) P^T [128,160) dS^T [160,192);  dV at 384, dK at 400.
+// TMEM columns: slot s at 128*s: S'^T [0,64) dP'^T [64,128); P^T over [0,32), dS^T over [64,96).  dV at 384, dK at 400.
 template <int KATOMS>
 __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dkv_tc_kernel(
     const __grid_constant__ CUtensorMap tm_k_stat, const __grid_constant__ CUtensorMap tm_q_strm,
@@ -70,38 +93,14 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dkv_tc_kernel(
   const int ntiles = (L + PP_BN - 1) / PP_BN;
   const int nks = C1 >> 4;
   constexpr uint32_t COL_DV = 384, COL_DK = 400;
+  constexpr int NS = PP_SLOTS;
 
-  if (threadIdx.x == 0) {
-    tc::mbar_init(&sm.bar_stat, 1);
-    for (int s = 0; s < PP_STAGES; ++s) { tc::mbar_init(&sm.bar_full[s], 1); tc::mbar_init(&sm.bar_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(&sm.bar_s_full[s], 1);
-      tc::mbar_init(&sm.bar_p_ready[s], 128);
-      tc::mbar_init(&sm.bar_mma_done[s], 1);
-    }
-    tc::fence_barrier_init();
-  }
-  if (warp == 8 && lane == 0) { tc::tma_prefetch_desc(&tm_k_stat); tc::tma_prefetch_desc(&tm_q_strm); }
-  if (warp == 9) tc::tmem_alloc<512>(&sm.tmem_base);
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
+  pp_init(sm, warp, lane, &tm_k_stat, &tm_q_strm);
   const uint32_t tmem = sm.tmem_base;
 
   if (warp == 8) {
-    if (lane == 0) {
-      tc::mbar_arrive_expect_tx(&sm.bar_stat, KATOMS * PP_BM * 64 * 2);
-      for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.stat[a], &tm_k_stat, &sm.bar_stat, a * 64, k0, bn);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j % PP_STAGES, ph = (j / PP_STAGES) & 1;
-        tc::mbar_wait(&sm.bar_empty[s], ph ^ 1);
-        tc::mbar_arrive_expect_tx(&sm.bar_full[s], KATOMS * PP_BN * 64 * 2);
-        for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.strm[s][a], &tm_q_strm, &sm.bar_full[s], a * 64, j * PP_BN, bn);
-      }
-    }
+    if (lane == 0) pp_producer(sm, &tm_k_stat, &tm_q_strm, k0, bn, ntiles);
   } else if (warp == 9) {
-    // MMA issue: the whole warp runs the (uniform) loop and waits; one elected lane issues.  Descriptors are
-    // 32-bit adds on precomputed low words -- the issuing thread is the critical resource of this kernel.
     constexpr uint32_t idesc_s = tc::idesc_bf16_f32(PP_BM, PP_BN);
     constexpr uint32_t idesc_dv = idesc_bmn(PP_BM, 16);
     constexpr uint32_t idesc_dk = idesc_bmn(PP_BM, 32);
@@ -111,11 +110,10 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dkv_tc_kernel(
     const uint32_t v_lo = tc::desc_lo_mn(smem_u32(sm.strm[0][C1 >> 6]) + (C1 & 63) * 2, PP_BN * 128);
     const uint32_t q_lo = tc::desc_lo_mn(smem_u32(sm.strm[0][0]), PP_BN * 128);
     tc::mbar_wait(&sm.bar_stat, 0);
-    // software pipeline: scores of tile j are issued before the gradient MMAs of tile j-1
-    for (int j = 0; j <= ntiles; ++j) {
+    for (int j = 0; j < ntiles + NS - 1; ++j) {
       if (j < ntiles) {
-        const int st = j % PP_STAGES, slot = j & 1;
-        const uint32_t tslot = tmem + 192 * slot;
+        const int st = j % PP_STAGES, slot = j % NS;
+        const uint32_t tslot = tmem + PP_SLOT_COLS * slot;
         tc::mbar_wait(&sm.bar_full[st], (j / PP_STAGES) & 1);
         tc::tc_fence_after();
         if (tc::elect_one()) {
@@ -129,20 +127,21 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dkv_tc_kernel(
         }
         __syncwarp();
       }
-      if (j > 0) {
-        const int jj = j - 1, st = jj % PP_STAGES, slot = jj & 1;
-        const uint32_t tslot = tmem + 192 * slot;
-        tc::mbar_wait(&sm.bar_p_ready[slot], (jj >> 1) & 1);
+      const int jj = j - (NS - 1);
+      if (jj >= 0) {
+        const int st = jj % PP_STAGES, slot = jj % NS;
+        const uint32_t tslot = tmem + PP_SLOT_COLS * slot;
+        tc::mbar_wait(&sm.bar_p_ready[slot], (jj / NS) & 1);
         tc::tc_fence_after();
         if (tc::elect_one()) {
           const uint32_t vb = v_lo + st * STAGE, qb = q_lo + st * STAGE;
 #pragma unroll
           for (int ks = 0; ks < PP_BN / 16; ++ks) {
-            tc::mma_ts(tmem + COL_DV, tslot + 128 + ks * 8, tc::desc64(vb + ks * 128), idesc_dv, (jj > 0 || ks > 0) ? 1u : 0u);
-            tc::mma_ts(tmem + COL_DK, tslot + 160 + ks * 8, tc::desc64(qb + ks * 128), idesc_dk, (jj > 0 || ks > 0) ? 1u : 0u);
+            tc::mma_ts(tmem + COL_DV, tslot + ks * 8, tc::desc64(vb + ks * 128), idesc_dv, (jj > 0 || ks > 0) ? 1u : 0u);
+            tc::mma_ts(tmem + COL_DK, tslot + 64 + ks * 8, tc::desc64(qb + ks * 128), idesc_dk, (jj > 0 || ks > 0) ? 1u : 0u);
           }
           tc::mma_commit(&sm.bar_empty[st]);
-          tc::mma_commit(&sm.bar_mma_done[slot]);
+          if (jj == ntiles - 1) tc::mma_commit(&sm.bar_final);
         }
         __syncwarp();
       }
@@ -151,13 +150,12 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dkv_tc_kernel(
     // ===================== math warpgroups: thread == key row == TMEM lane =====================
     const int wg = warp >> 2;
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t tslot = tlane + 192 * wg;
     uint32_t rs[32], rd[32], pp[16], pd[16];
     for (int j = wg; j < ntiles; j += 2) {
-      const int it = j >> 1;
-      tc::mbar_wait(&sm.bar_s_full[wg], it & 1);
+      const int slot = j % NS;
+      const uint32_t tslot = tlane + PP_SLOT_COLS * slot;
+      tc::mbar_wait(&sm.bar_s_full[slot], (j / NS) & 1);
       tc::tc_fence_after();
-      if (it > 0) tc::mbar_wait(&sm.bar_mma_done[wg], (it - 1) & 1);   // previous P^T/dS^T of this slot consumed
 #pragma unroll
       for (int c = 0; c < PP_BN / 32; ++c) {
         tc::tmem_ld_x32(tslot + c * 32, rs);
@@ -169,18 +167,15 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dkv_tc_kernel(
           pp[i] = tc::pack_bf16x2(p0, p1);
           pd[i] = tc::pack_bf16x2(p0 * __uint_as_float(rd[2 * i]), p1 * __uint_as_float(rd[2 * i + 1]));
         }
-        tc::tmem_st_x16(tslot + 128 + c * 16, pp);
-        tc::tmem_st_x16(tslot + 160 + c * 16, pd);
+        tc::tmem_st_x16(tslot + c * 16, pp);          // P^T over S'^T[0,32): those columns are already in registers
+        tc::tmem_st_x16(tslot + 64 + c * 16, pd);     // dS^T over dP'^T[0,32)
       }
       tc::tmem_st_wait();
       tc::tc_fence_before();
-      tc::mbar_arrive(&sm.bar_p_ready[wg]);
+      tc::mbar_arrive(&sm.bar_p_ready[slot]);
     }
-    // epilogue: wait for the last gradient MMAs of both slots, then WG0 writes dK, WG1 writes dV
-    for (int s = 0; s < 2; ++s) {
-      const int n_s = (ntiles - s + 1) / 2;              // tiles handled by slot s
-      if (n_s > 0) tc::mbar_wait(&sm.bar_mma_done[s], (n_s - 1) & 1);
-    }
+    // epilogue: after the last gradient MMAs WG0 writes dK, WG1 writes dV
+    tc::mbar_wait(&sm.bar_final, 0);
     tc::tc_fence_after();
     const int kj = k0 + (warp & 3) * 32 + lane;
     const size_t row = (size_t)bn * L + kj;
@@ -237,7 +232,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dkv_tc_kernel(
 }
 
 // ---- query-stationary: dQa (content gradient + gradients of the relative rows Aq, Bq) ---------------
-// TMEM columns: slot s at 160*s: S' [0,64) dP' [64,128) dS [128,160);  dQa at 320 (NQ <= 160 columns).
+// TMEM columns: slot s at 128*s: S' [0,64) dP' [64,128); dS over [64,96).  dQa (NQ <= 160 columns) behind the slots:
+// three slots when NQ <= 128 (dQa at 384), two otherwise (dQa at 256).
 template <int KATOMS>
 __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dq_tc_kernel(
     const __grid_constant__ CUtensorMap tm_q_stat, const __grid_constant__ CUtensorMap tm_k_strm,
@@ -248,36 +244,14 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dq_tc_kernel(
   const int bn = blockIdx.y, q0 = blockIdx.x * PP_BM;
   const int ntiles = (L + PP_BN - 1) / PP_BN;
   const int nks = C1 >> 4;
-  constexpr uint32_t COL_DQ = 320;
+  const int NS = NQ <= 128 ? 3 : 2;
+  const uint32_t COL_DQ = PP_SLOT_COLS * NS;
 
-  if (threadIdx.x == 0) {
-    tc::mbar_init(&sm.bar_stat, 1);
-    for (int s = 0; s < PP_STAGES; ++s) { tc::mbar_init(&sm.bar_full[s], 1); tc::mbar_init(&sm.bar_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(&sm.bar_s_full[s], 1);
-      tc::mbar_init(&sm.bar_p_ready[s], 128);
-      tc::mbar_init(&sm.bar_mma_done[s], 1);
-    }
-    tc::fence_barrier_init();
-  }
-  if (warp == 8 && lane == 0) { tc::tma_prefetch_desc(&tm_q_stat); tc::tma_prefetch_desc(&tm_k_strm); }
-  if (warp == 9) tc::tmem_alloc<512>(&sm.tmem_base);
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
+  pp_init(sm, warp, lane, &tm_q_stat, &tm_k_strm);
   const uint32_t tmem = sm.tmem_base;
 
   if (warp == 8) {
-    if (lane == 0) {
-      tc::mbar_arrive_expect_tx(&sm.bar_stat, KATOMS * PP_BM * 64 * 2);
-      for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.stat[a], &tm_q_stat, &sm.bar_stat, a * 64, q0, bn);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j % PP_STAGES, ph = (j / PP_STAGES) & 1;
-        tc::mbar_wait(&sm.bar_empty[s], ph ^ 1);
-        tc::mbar_arrive_expect_tx(&sm.bar_full[s], KATOMS * PP_BN * 64 * 2);
-        for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.strm[s][a], &tm_k_strm, &sm.bar_full[s], a * 64, j * PP_BN, bn);
-      }
-    }
+    if (lane == 0) pp_producer(sm, &tm_q_stat, &tm_k_strm, q0, bn, ntiles);
   } else if (warp == 9) {
     constexpr uint32_t idesc_s = tc::idesc_bf16_f32(PP_BM, PP_BN);
     const uint32_t idesc_dq = idesc_bmn(PP_BM, NQ);
@@ -286,10 +260,10 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dq_tc_kernel(
     const uint32_t strm_lo = tc::desc_lo_k(smem_u32(sm.strm[0][0]));
     const uint32_t k_lo = tc::desc_lo_mn(smem_u32(sm.strm[0][0]), PP_BN * 128);
     tc::mbar_wait(&sm.bar_stat, 0);
-    for (int j = 0; j <= ntiles; ++j) {
+    for (int j = 0; j < ntiles + NS - 1; ++j) {
       if (j < ntiles) {
-        const int st = j % PP_STAGES, slot = j & 1;
-        const uint32_t tslot = tmem + 160 * slot;
+        const int st = j % PP_STAGES, slot = j % NS;
+        const uint32_t tslot = tmem + PP_SLOT_COLS * slot;
         tc::mbar_wait(&sm.bar_full[st], (j / PP_STAGES) & 1);
         tc::tc_fence_after();
         if (tc::elect_one()) {
@@ -303,18 +277,19 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dq_tc_kernel(
         }
         __syncwarp();
       }
-      if (j > 0) {
-        const int jj = j - 1, st = jj % PP_STAGES, slot = jj & 1;
-        const uint32_t tslot = tmem + 160 * slot;
-        tc::mbar_wait(&sm.bar_p_ready[slot], (jj >> 1) & 1);
+      const int jj = j - (NS - 1);
+      if (jj >= 0) {
+        const int st = jj % PP_STAGES, slot = jj % NS;
+        const uint32_t tslot = tmem + PP_SLOT_COLS * slot;
+        tc::mbar_wait(&sm.bar_p_ready[slot], (jj / NS) & 1);
         tc::tc_fence_after();
         if (tc::elect_one()) {
           const uint32_t kb = k_lo + st * STAGE;
 #pragma unroll
           for (int ks = 0; ks < PP_BN / 16; ++ks)
-            tc::mma_ts(tmem + COL_DQ, tslot + 128 + ks * 8, tc::desc64(kb + ks * 128), idesc_dq, (jj > 0 || ks > 0) ? 1u : 0u);
+            tc::mma_ts(tmem + COL_DQ, tslot + 64 + ks * 8, tc::desc64(kb + ks * 128), idesc_dq, (jj > 0 || ks > 0) ? 1u : 0u);
           tc::mma_commit(&sm.bar_empty[st]);
-          tc::mma_commit(&sm.bar_mma_done[slot]);
+          if (jj == ntiles - 1) tc::mma_commit(&sm.bar_final);
         }
         __syncwarp();
       }
@@ -322,13 +297,12 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dq_tc_kernel(
   } else {
     const int wg = warp >> 2;
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t tslot = tlane + 160 * wg;
     uint32_t rs[32], rd[32], pd[16];
     for (int j = wg; j < ntiles; j += 2) {
-      const int it = j >> 1;
-      tc::mbar_wait(&sm.bar_s_full[wg], it & 1);
+      const int slot = j % NS;
+      const uint32_t tslot = tlane + PP_SLOT_COLS * slot;
+      tc::mbar_wait(&sm.bar_s_full[slot], (j / NS) & 1);
       tc::tc_fence_after();
-      if (it > 0) tc::mbar_wait(&sm.bar_mma_done[wg], (it - 1) & 1);
 #pragma unroll
       for (int c = 0; c < PP_BN / 32; ++c) {
         tc::tmem_ld_x32(tslot + c * 32, rs);
@@ -339,16 +313,13 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dq_tc_kernel(
           const float p0 = tc::ex2f(__uint_as_float(rs[2 * i])), p1 = tc::ex2f(__uint_as_float(rs[2 * i + 1]));
           pd[i] = tc::pack_bf16x2(p0 * __uint_as_float(rd[2 * i]), p1 * __uint_as_float(rd[2 * i + 1]));
         }
-        tc::tmem_st_x16(tslot + 128 + c * 16, pd);
+        tc::tmem_st_x16(tslot + 64 + c * 16, pd);     // dS over dP'[0,32): already in registers
       }
       tc::tmem_st_wait();
       tc::tc_fence_before();
-      tc::mbar_arrive(&sm.bar_p_ready[wg]);
+      tc::mbar_arrive(&sm.bar_p_ready[slot]);
     }
-    for (int s = 0; s < 2; ++s) {
-      const int n_s = (ntiles - s + 1) / 2;
-      if (n_s > 0) tc::mbar_wait(&sm.bar_mma_done[s], (n_s - 1) & 1);
-    }
+    tc::mbar_wait(&sm.bar_final, 0);
     tc::tc_fence_after();
     // dQa rows -> global (B,nh,L,KD) fp32; the two warpgroups split the columns in 32-wide chunks
     const int qi = q0 + (warp & 3) * 32 + lane;
@@ -357,9 +328,17 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dq_tc_kernel(
       tc::tmem_ld_x32(tlane + COL_DQ + c0, rs);
       tc::tmem_ld_wait();
       if (qi < L) {
+        if ((KD & 3) == 0) {                         // 16-byte stores (row stride and column offset are multiples of 4 floats)
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if (c0 + e < KD) dqa[row * KD + c0 + e] = __uint_as_float(rs[e]);
+          for (int e = 0; e < 32; e += 4)
+            if (c0 + e < KD)
+              *reinterpret_cast<float4*>(dqa + row * KD + c0 + e) =
+                  make_float4(__uint_as_float(rs[e]), __uint_as_float(rs[e + 1]), __uint_as_float(rs[e + 2]), __uint_as_float(rs[e + 3]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (c0 + e < KD) dqa[row * KD + c0 + e] = __uint_as_float(rs[e]);
+        }
       }
     }
   }

@@ -16,6 +16,7 @@
 //   dT^T      [2N-1 x dkh]    += dR^T[2N-1 x rows] . Q[rows x dkh]          (accumulated in registers, fixed order)
 #include <algorithm>
 #include <cuda_bf16.h>
+#include "tc_common.cuh"
 #include "bf16_path.cuh"
 
 namespace aaconv {
@@ -47,7 +48,6 @@ namespace {
 
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr int TR = 64;             // rows per tile (4 row groups of 16)
-constexpr int PQ = 36;             // q tile pitch (floats): == 4 (mod 32) -> conflict-free A-fragment loads (row = g)
 
 __device__ __forceinline__ uint32_t f2tf32(float x) {
   uint32_t r;
@@ -65,6 +65,13 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+// 1-D bulk copy global -> shared (TMA unit, no tensor map): dst/src 16 B aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes),
+                 "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
@@ -97,14 +104,20 @@ __global__ void __launch_bounds__(256) aug_build_fwd_kernel(const BuildP p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint32_t* tabw = reinterpret_cast<uint32_t*>(smem_raw);                 // [DK8][PBW] tf32
   uint32_t* tabh = tabw + (p.relative ? p.DK8 * p.PBW : 0);               // [DK8][PBH]
-  float* qs = reinterpret_cast<float*>(tabh + (p.relative ? p.DK8 * p.PBH : 0));   // [TR][PQ]  q (zero padded)
-  float* ks = qs + TR * PQ;                                               // [TR][dkh]
-  float* vs = ks + TR * p.dkh;                                            // [TR][dvh]
+  // q, k, v tiles are contiguous copies of the global rows (one bulk copy each).  The MMA K padding (columns
+  // dkh..DK8 of a q row) therefore reads the head of the next row / of ks: finite values (the float region is zeroed
+  // once) that meet zero table rows.
+  float* qs = reinterpret_cast<float*>(tabh + (p.relative ? p.DK8 * p.PBH : 0));   // [TR][dkh]
+  float* ks = qs + TR * p.dkh;                                            // [TR][dkh]
+  float* vs = ks + TR * p.dkh;                                            // [TR][dvh] (+ pad)
   const int PT = p.KP + 8;
-  bf16* tq = reinterpret_cast<bf16*>(vs + ((TR * p.dvh + 3) & ~3));       // [TR][PT]
+  const int PQ = p.dkh;
+  bf16* tq = reinterpret_cast<bf16*>(vs + ((TR * p.dvh + 3) & ~3) + 4);   // [TR][PT]
   bf16* tk = tq + TR * PT;
   int* rx = reinterpret_cast<int*>(tk + TR * PT);                         // [TR] x and y of each tile row
   int* ry = rx + TR;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(ry + TR);
+  if (threadIdx.x == 0) { tc::mbar_init(bar, 1); tc::fence_barrier_init(); }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int CP = p.KP >> 1, rows_per_pass = 256 / CP, cp = threadIdx.x % CP, rsub = threadIdx.x / CP;
@@ -118,7 +131,22 @@ __global__ void __launch_bounds__(256) aug_build_fwd_kernel(const BuildP p) {
       tabh[i] = (e < p.dkh && r < p.RH) ? f2tf32(p.krh[e * p.RH + r]) : 0u;
     }
   }
-  for (int i = threadIdx.x; i < TR * PQ; i += blockDim.x) qs[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * TR * p.dkh + ((TR * p.dvh + 3) & ~3) + 4; i += blockDim.x) qs[i] = 0.f;
+  uint32_t phase = 0;
+  // kind of this thread's two columns: Ka value = kcst + [x == kohx] + [y == kohy] + kld[r * kst];  Qa: 0 zero, 1 q, 2 skip (rel)
+  const int c0 = 2 * cp;
+  float kcst[2];
+  int kohx[2], kohy[2], kst[2], kofs[2], qmode[2];        // kofs: offset from qs (ks and vs follow it in shared memory)
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = c0 + h;
+    kcst[h] = 0.f; kohx[h] = -1; kohy[h] = -1; kst[h] = 0; kofs[h] = 0; qmode[h] = 0;
+    if (c < p.dkh) { kofs[h] = (int)(ks - qs) + c; kst[h] = p.dkh; qmode[h] = 1; }
+    else if (c < p.KD) { qmode[h] = 2; if (c < p.dkh + p.W) kohx[h] = c - p.dkh; else kohy[h] = c - p.dkh - p.W; }
+    else if (c < p.KD + 2) kcst[h] = 1.f;
+    else if (c >= p.C1 && c < p.C1 + p.dvh) { kofs[h] = (int)(vs - qs) + (c - p.C1); kst[h] = p.dvh; }
+    else if (c >= p.C1 + p.dvh && c < p.C1 + p.dvh + 2) kcst[h] = 1.f;
+  }
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const int bn = tile / p.tiles_per_bn, l0 = (tile - bn * p.tiles_per_bn) * TR;
     const int nrows = min(TR, p.L - l0);
@@ -129,20 +157,28 @@ __global__ void __launch_bounds__(256) aug_build_fwd_kernel(const BuildP p) {
       rx[threadIdx.x] = l - y * p.W;
       ry[threadIdx.x] = y;
     }
-    // asynchronous tile loads (LDGSTS): no register staging, no load->store ordering stalls.  Pad columns of qs were
-    // zeroed once; rows past the end of the image (last tile only) are zeroed here.
-    for (int r = warp; r < TR; r += 8) {
-      if (r < nrows) {
+    // tile loads: three 1-D bulk copies (TMA unit) when the blocks are 16 B aligned, else per-element LDGSTS
+    const bool bulk = (((row0 * p.dkh) | (size_t)(nrows * p.dkh) | (row0 * p.dvh) | (size_t)(nrows * p.dvh)) & 3) == 0;
+    if (bulk) {
+      if (threadIdx.x == 0) {
+        const uint32_t bq = nrows * p.dkh * 4, bv = nrows * p.dvh * 4;
+        tc::mbar_arrive_expect_tx(bar, 2 * bq + bv);
+        bulk_g2s(qs, p.q + row0 * p.dkh, bq, bar);
+        bulk_g2s(ks, p.k + row0 * p.dkh, bq, bar);
+        bulk_g2s(vs, p.v + row0 * p.dvh, bv, bar);
+      }
+      tc::mbar_wait(bar, phase);
+      phase ^= 1;
+    } else {
+      for (int r = warp; r < nrows; r += 8) {
         if (lane < p.dkh) {
           cp_async4(qs + r * PQ + lane, p.q + (row0 + r) * p.dkh + lane);
           cp_async4(ks + r * p.dkh + lane, p.k + (row0 + r) * p.dkh + lane);
         }
         if (lane < p.dvh) cp_async4(vs + r * p.dvh + lane, p.v + (row0 + r) * p.dvh + lane);
-      } else if (lane < p.dkh) {
-        qs[r * PQ + lane] = 0.f;
       }
+      cp_async_wait_all();
     }
-    cp_async_wait_all();
     __syncthreads();
 
     // ---- relative columns of Qa: warps 0-3 the W axis, warps 4-7 the H axis, 16 rows each ----
@@ -178,39 +214,25 @@ __global__ void __launch_bounds__(256) aug_build_fwd_kernel(const BuildP p) {
         if ((unsigned)(xb + 1) < (unsigned)N) tq[rb * PT + colbase + xb + 1] = __float2bfloat16(c[3]);
       }
     }
-    // ---- everything else: q columns and zero tail of Qa, all of Ka.  A thread owns one column pair (its kind is
-    //      loop invariant) and walks down the rows; bf16x2 stores ----
+    // ---- everything else: q columns and zero tail of Qa, all of Ka.  A thread owns one column pair whose kind was
+    //      decoded once (branch-free inner loop) and walks down the rows; bf16x2 stores.  Rows past the end of the
+    //      image are never copied out, so they need no masking. ----
     if (rsub < rows_per_pass) {
-      const int c0 = 2 * cp;
       for (int r = rsub; r < TR; r += rows_per_pass) {
         const int x = rx[r], y = ry[r];
-        const bool rv = r < nrows;
         float kv[2], qv[2];
-        bool qw[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int c = c0 + h;
-          kv[h] = 0.f; qv[h] = 0.f; qw[h] = true;
-          if (c < p.dkh) {
-            qv[h] = qs[r * PQ + c] * LOG2E;
-            kv[h] = rv ? ks[r * p.dkh + c] : 0.f;
-          } else if (c < p.KD) {
-            qw[h] = false;                                 // relative column: written by the MMA phase
-            kv[h] = (c < p.dkh + p.W) ? (c - p.dkh == x ? 1.f : 0.f) : (c - p.dkh - p.W == y ? 1.f : 0.f);
-          } else if (c < p.KD + 2) {
-            kv[h] = 1.f;
-          } else if (c >= p.C1 && c < p.C1 + p.dvh) {
-            kv[h] = rv ? vs[r * p.dvh + (c - p.C1)] : 0.f;
-          } else if (c >= p.C1 + p.dvh && c < p.C1 + p.dvh + 2) {
-            kv[h] = 1.f;
-          }
+          kv[h] = kcst[h] + (x == kohx[h] ? 1.f : 0.f) + (y == kohy[h] ? 1.f : 0.f);
+          if (kst[h]) kv[h] += qs[kofs[h] + r * kst[h]];
+          qv[h] = qmode[h] == 1 ? qs[r * PQ + c0 + h] * LOG2E : 0.f;
         }
         *reinterpret_cast<__nv_bfloat162*>(tk + r * PT + c0) = __floats2bfloat162_rn(kv[0], kv[1]);
-        if (qw[0] && qw[1]) {
+        if (qmode[0] != 2 && qmode[1] != 2) {
           *reinterpret_cast<__nv_bfloat162*>(tq + r * PT + c0) = __floats2bfloat162_rn(qv[0], qv[1]);
         } else {
-          if (qw[0]) tq[r * PT + c0] = __float2bfloat16(qv[0]);
-          if (qw[1]) tq[r * PT + c0 + 1] = __float2bfloat16(qv[1]);
+          if (qmode[0] != 2) tq[r * PT + c0] = __float2bfloat16(qv[0]);
+          if (qmode[1] != 2) tq[r * PT + c0 + 1] = __float2bfloat16(qv[1]);
         }
       }
     }
@@ -257,9 +279,9 @@ size_t aug_build_smem(const Dims& d) {
   const int DK8 = cdiv(d.dkh, 8) * 8;
   size_t s = 0;
   if (d.relative) s += sizeof(uint32_t) * DK8 * (size_t)(table_pitch(d.RW) + table_pitch(d.RH));
-  s += sizeof(float) * (TR * PQ + TR * d.dkh + ((TR * d.dvh + 3) & ~3));
+  s += sizeof(float) * (2 * TR * d.dkh + ((TR * d.dvh + 3) & ~3) + 4);
   s += sizeof(bf16) * 2 * TR * (size_t)(a.KP + 8);
-  s += sizeof(int) * 2 * TR;
+  s += sizeof(int) * 2 * TR + 16;
   return s;
 }
 
@@ -308,11 +330,10 @@ struct RelBwdP {
   float* partial;       // [grid][2][RP * DK8] key_rel gradient partials (transposed: [r][e])
   int L, H, W, nh, dkh, KD, KPq, relative;
   int DK8, RW, RH, PBW, PBH, PTW, PTH, PA, RP;
-  int tiles_per_bn, ntiles;
+  int tiles_per_bn, ntiles, tile_floats;
   float qscale;
 };
 
-constexpr int PQ2 = 40;   // q tile pitch == 8 (mod 32): conflict-free B-fragment loads with k = row = t
 
 inline int pitch_mod32(int n, int want) {
   int p = n;
@@ -322,12 +343,18 @@ inline int pitch_mod32(int n, int want) {
 
 // MT = 16-row tiles of the relative axis (2N-1 <= 16*MT), NTE = 8-column tiles of dkh (dkh <= 8*NTE)
 template <int MT, int NTE>
-__global__ void __launch_bounds__(256) rel_bwd_kernel(const RelBwdP p) {
+__global__ void __launch_bounds__(256, (MT <= 5 ? 2 : 1)) rel_bwd_kernel(const RelBwdP p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint32_t* tabw = reinterpret_cast<uint32_t*>(smem_raw);        // [DK8][PTW]  pitch == 4 (mod 32): B frags with n = e = g, k = r = t
   uint32_t* tabh = tabw + p.DK8 * p.PTW;                         // [DK8][PTH]
-  float* da = reinterpret_cast<float*>(tabh + p.DK8 * p.PTH);    // [TR][PA]    dQa rows of the tile
-  float* qs = da + TR * p.PA;                                    // [TR][PQ2]   q (zero padded)
+  // q and dQa tiles are contiguous copies of the global rows (one bulk copy each).  K/N padding of the q fragments
+  // (columns dkh..8*NTE) reads the next row / the head of da: it only feeds output columns that are discarded.
+  float* qs = reinterpret_cast<float*>(tabh + p.DK8 * p.PTH);    // [TR][dkh]   q
+  float* da = qs + ((TR * p.dkh + 3) & ~3);                      // [TR][PA]    dQa rows of the tile (PA == KD)
+  const int PQ2 = p.dkh;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(da + p.tile_floats);
+  if (threadIdx.x == 0) { tc::mbar_init(bar, 1); tc::fence_barrier_init(); }
+  uint32_t phase = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 
   for (int i = threadIdx.x; i < p.DK8 * p.PTW; i += blockDim.x) {
@@ -338,7 +365,7 @@ __global__ void __launch_bounds__(256) rel_bwd_kernel(const RelBwdP p) {
     const int e = i / p.PTH, r = i - e * p.PTH;
     tabh[i] = (e < p.dkh && r < p.RH) ? f2tf32(p.krh[e * p.RH + r]) : 0u;
   }
-  for (int i = threadIdx.x; i < TR * PQ2; i += blockDim.x) qs[i] = 0.f;   // pad columns stay zero
+  for (int i = threadIdx.x; i < ((TR * p.dkh + 3) & ~3) + TR * p.PA; i += blockDim.x) qs[i] = 0.f;
   float acc[MT][NTE][4];                                         // G role: dT^T[r][e] of this warp's axis / row half
 #pragma unroll
   for (int a = 0; a < MT; ++a)
@@ -352,16 +379,27 @@ __global__ void __launch_bounds__(256) rel_bwd_kernel(const RelBwdP p) {
     const int nrows = min(TR, p.L - l0);
     const size_t row0 = (size_t)bn * p.L + l0;
     __syncthreads();
-    for (int r = warp; r < TR; r += 8) {               // one warp per row, asynchronous (LDGSTS)
-      if (r < nrows) {
+    if (nrows < TR) {                                  // last tile of an image: rows past the end must contribute zero
+      for (int i = threadIdx.x + nrows * p.dkh; i < TR * p.dkh; i += blockDim.x) qs[i] = 0.f;
+      for (int i = threadIdx.x + nrows * p.PA; i < TR * p.PA; i += blockDim.x) da[i] = 0.f;
+    }
+    const bool bulk = p.PA == p.KD && (((row0 * p.dkh) | (size_t)(nrows * p.dkh) | (row0 * p.KD) | (size_t)(nrows * p.KD)) & 3) == 0;
+    if (bulk) {
+      if (threadIdx.x == 0) {
+        const uint32_t bq = nrows * p.dkh * 4, bd = nrows * p.KD * 4;
+        tc::mbar_arrive_expect_tx(bar, bq + bd);
+        bulk_g2s(qs, p.q + row0 * p.dkh, bq, bar);
+        bulk_g2s(da, p.dqa + row0 * p.KD, bd, bar);
+      }
+      tc::mbar_wait(bar, phase);
+      phase ^= 1;
+    } else {
+      for (int r = warp; r < nrows; r += 8) {
         for (int c = lane; c < p.KD; c += 32) cp_async4(da + r * p.PA + c, p.dqa + (row0 + r) * p.KD + c);
         if (lane < p.dkh) cp_async4(qs + r * PQ2 + lane, p.q + (row0 + r) * p.dkh + lane);
-      } else {
-        for (int c = lane; c < p.KD; c += 32) da[r * p.PA + c] = 0.f;
-        if (lane < p.dkh) qs[r * PQ2 + lane] = 0.f;
       }
+      cp_async_wait_all();
     }
-    cp_async_wait_all();
     __syncthreads();
 
     if (warp < 4) {
@@ -548,14 +586,15 @@ int rel_bwd(const Dims& d, const float* dqa, const float* q, const float* krw, c
   p.DK8 = cdiv(d.dkh, 8) * 8; p.RW = d.RW; p.RH = d.RH;
   p.PBW = p.PBH = 0;
   p.PTW = pitch_mod32(cdiv(d.RW, 8) * 8, 4); p.PTH = pitch_mod32(cdiv(d.RH, 8) * 8, 4);
-  p.PA = pitch_mod32(a.KD, 3);
+  p.PA = a.KD;                                                       // contiguous rows: one bulk copy per tile
   p.RP = cdiv(std::max(d.RW, d.RH), 16) * 16;
   p.tiles_per_bn = cdiv(d.L, TR); p.ntiles = p.tiles_per_bn * d.BN;
   p.qscale = d.qscale;
   const int mt = p.RP / 16, nte = p.DK8 / 8;
-  size_t tile_floats = (size_t)TR * p.PA + (size_t)TR * PQ2;
-  tile_floats = std::max(tile_floats, (size_t)4 * p.RP * p.DK8);       // the reduction buffer aliases the tile
-  const size_t smem = sizeof(uint32_t) * p.DK8 * (size_t)(p.PTW + p.PTH) + sizeof(float) * tile_floats;
+  size_t tile_floats = (size_t)TR * p.PA;
+  tile_floats = (std::max(tile_floats, (size_t)4 * p.RP * p.DK8) + 3) & ~size_t(3);       // the reduction buffer aliases the dQa tile
+  p.tile_floats = (int)tile_floats;
+  const size_t smem = sizeof(uint32_t) * p.DK8 * (size_t)(p.PTW + p.PTH) + sizeof(float) * (((TR * d.dkh + 3) & ~3) + tile_floats) + 16;
   if (smem > 200 * 1024) return fail(AACONV_E_UNSUPPORTED, "rel_bwd: %zu B of shared memory needed", smem);
   const int grid = std::min(p.ntiles, REL_BWD_GRID);
   if (nte <= 3) AACONV_TRY(dispatch_rel_bwd<3>(mt, p, grid, smem, st));

@@ -461,8 +461,9 @@ int tc_fprop(const Dims& d, const TcGemmBufs& t, const float* x, const float* co
   // accumulator chunks, up to PG_MAX_CHUNKS per launch
   struct C { int n0, kind; };
   std::vector<C> all;
-  for (int n0 = 0; n0 < d.Cc; n0 += 128) all.push_back({n0, 0});
+  // short-K projection chunks first: their (scattered) epilogues hide under the long conv mainloop
   for (int n0 = 0; n0 < d.Nqkv; n0 += 128) all.push_back({n0, 1});
+  for (int n0 = 0; n0 < d.Cc; n0 += 128) all.push_back({n0, 0});
   for (size_t i = 0; i < all.size(); i += PG_MAX_CHUNKS) {
     p.nchunks = (int)std::min<size_t>(PG_MAX_CHUNKS, all.size() - i);
     for (int c = 0; c < p.nchunks; ++c) {
@@ -491,27 +492,59 @@ int tc_dgrad(const Dims& d, const TcGemmBufs& t, const float* conv_w, const floa
   pack_wd_kernel<<<148 * 4, 256, 0, st>>>(conv_w, qkv_w, static_cast<bf16*>(t.wd), static_cast<bf16*>(t.wq), d.Cc, d.Cin, T,
                                            t.CinP, t.KPc, d.Nqkv, t.KPq);
   AACONV_LAUNCH_OK("pack_wd");
-  for (int rh = 0; rh < s; ++rh)
+  // taps of the conv (and the 1x1 projection) that reach input-pixel class (rh, rw)
+  auto class_segs = [&](int rh, int rw, PGSeg* out) {
+    int ns = 0;
+    if (d.Cc)
+      for (int kh = 0; kh < d.ks; ++kh)
+        for (int kw = 0; kw < d.ks; ++kw) {      // input pixel h = s*hc + rh receives dy[(h + pad - kh)/s] when divisible
+          const int nh_ = rh + d.pad - kh, nw_ = rw + d.pad - kw;
+          if (((nh_ % s) + s) % s || ((nw_ % s) + s) % s) continue;
+          out[ns++] = {0, floordiv(nw_, s), floordiv(nh_, s), t.KPc / 64, 0, (kh * d.ks + kw) * t.CinP};
+        }
+    if (rh == 0 && rw == 0) out[ns++] = {1, 0, 0, t.KPq / 64, 1, 0};   // 1x1 stride-s projection touches class (0,0)
+    return ns;
+  };
+  for (int rh = 0; rh < s; ++rh) {
+    const int Hc = d.Hin > rh ? (d.Hin - rh + s - 1) / s : 0;
+    if (Hc == 0) continue;
+    PGParams p;
+    memset(&p, 0, sizeof p);
+    PGSeg seg0[PG_MAX_SEGS], seg1[PG_MAX_SEGS];
+    const int ns0 = class_segs(rh, 0, seg0), ns1 = s == 2 ? class_segs(rh, 1, seg1) : 0;
+    if (s == 2 && d.Win >= 2 && ns0 > 0 && ns1 > 0 && ns0 + ns1 <= PG_MAX_SEGS) {
+      // both column classes in one CTA: accumulator chunks (2i, 2i+1) = (rw 0, rw 1) of the same 128 channels
+      const int Wc = (d.Win + 1) / 2;
+      p.Wt = Wc; p.Ht = Hc; p.r = rows_per_tile(Wc, Hc); p.tiles_h = cdiv(Hc, p.r);
+      AACONV_TRY(make_nhwc_map(&p.amaps[0], t.dyh, d.B, d.H, d.W, t.KPc, 1, 0, 0, p.r, p.Wt));
+      AACONV_TRY(make_nhwc_map(&p.amaps[1], t.dqkvh, d.B, d.H, d.W, t.KPq, 1, 0, 0, p.r, p.Wt));
+      AACONV_TRY(make_2d_map(&p.bmaps[0], t.wd, t.KPc, (size_t)T * t.CinP));
+      AACONV_TRY(make_2d_map(&p.bmaps[1], t.wq, t.KPq, (size_t)t.CinP));
+      for (int i = 0; i < ns0; ++i) p.segs[i] = seg0[i];
+      for (int i = 0; i < ns1; ++i) p.segs[ns0 + i] = seg1[i];
+      p.mode = 1; p.out0 = dx; p.Cin = d.Cin; p.Hin = d.Hin; p.Win = d.Win; p.stride = s; p.rh = rh; p.rw = 0; p.pair = 1;
+      for (int n0 = 0; n0 < d.Cin; n0 += 128 * (PG_MAX_CHUNKS / 2)) {
+        const int nn = std::min(PG_MAX_CHUNKS / 2, cdiv(d.Cin - n0, 128));
+        p.nchunks = 2 * nn;
+        for (int c = 0; c < nn; ++c) {
+          p.chunks[2 * c] = {n0 + c * 128, 0, ns0, 0};
+          p.chunks[2 * c + 1] = {n0 + c * 128, ns0, ns0 + ns1, 0};
+        }
+        AACONV_TRY(launch_pg(p, d.B, st, "conv_qkv_dgrad_tc"));
+      }
+      continue;
+    }
     for (int rw = 0; rw < s; ++rw) {
-      const int Hc = d.Hin > rh ? (d.Hin - rh + s - 1) / s : 0, Wc = d.Win > rw ? (d.Win - rw + s - 1) / s : 0;
-      if (Hc == 0 || Wc == 0) continue;
-      PGParams p;
+      const int Wc = d.Win > rw ? (d.Win - rw + s - 1) / s : 0;
+      if (Wc == 0) continue;
       memset(&p, 0, sizeof p);
       p.Wt = Wc; p.Ht = Hc; p.r = rows_per_tile(Wc, Hc); p.tiles_h = cdiv(Hc, p.r);
       AACONV_TRY(make_nhwc_map(&p.amaps[0], t.dyh, d.B, d.H, d.W, t.KPc, 1, 0, 0, p.r, p.Wt));
       AACONV_TRY(make_nhwc_map(&p.amaps[1], t.dqkvh, d.B, d.H, d.W, t.KPq, 1, 0, 0, p.r, p.Wt));
       AACONV_TRY(make_2d_map(&p.bmaps[0], t.wd, t.KPc, (size_t)T * t.CinP));
       AACONV_TRY(make_2d_map(&p.bmaps[1], t.wq, t.KPq, (size_t)t.CinP));
-      int ns = 0;
-      if (d.Cc)
-        for (int kh = 0; kh < d.ks; ++kh)
-          for (int kw = 0; kw < d.ks; ++kw) {    // input pixel h = s*hc + rh receives dy[(h + pad - kh)/s] when divisible
-            const int nh_ = rh + d.pad - kh, nw_ = rw + d.pad - kw;
-            if (((nh_ % s) + s) % s || ((nw_ % s) + s) % s) continue;
-            p.segs[ns++] = {0, floordiv(nw_, s), floordiv(nh_, s), t.KPc / 64, 0, (kh * d.ks + kw) * t.CinP};
-          }
-      if (rh == 0 && rw == 0) p.segs[ns++] = {1, 0, 0, t.KPq / 64, 1, 0};   // 1x1 stride-s projection touches class (0,0)
-      p.mode = 1; p.out0 = dx; p.Cin = d.Cin; p.Hin = d.Hin; p.Win = d.Win; p.stride = s; p.rh = rh; p.rw = rw;
+      const int ns = class_segs(rh, rw, p.segs);
+      p.mode = 1; p.out0 = dx; p.Cin = d.Cin; p.Hin = d.Hin; p.Win = d.Win; p.stride = s; p.rh = rh; p.rw = rw; p.pair = 0;
       if (ns == 0) {   // no tap reaches this class (e.g. 1x1 conv with stride 2): gradient is zero there
         AACONV_TRY(tc_zero_class(d, dx, rh, rw, st));
         continue;
@@ -522,6 +555,7 @@ int tc_dgrad(const Dims& d, const TcGemmBufs& t, const float* conv_w, const floa
         AACONV_TRY(launch_pg(p, d.B, st, "conv_qkv_dgrad_tc"));
       }
     }
+  }
   return 0;
 }
 

@@ -31,3 +31,22 @@ def load_case(name, tag):
 def rel_err(a, b):
     a, b = a.double(), b.double()
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def autocast_reference(s, p, x, dy):
+    """The reference op sequence (oracle port of attn_aug_conv.py:65-97) executed by PyTorch itself in bf16
+    (torch.autocast) on the GPU: the calibration for what bf16 arithmetic can deliver on these inputs.
+    -> dict with 'y', 'x' (grad) and the parameter-gradient names."""
+    prm = {k: v.float().cuda().requires_grad_(True) for k, v in p.items()}
+    xc = x.float().cuda().requires_grad_(True)
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        y = O.aaconv_forward_sequential(xc, prm, s)
+    y.float().backward(dy.float().cuda())
+    out = {'y': y.float().detach(), 'x': xc.grad}
+    out.update({k: v.grad for k, v in prm.items()})
+    return out
