@@ -24,8 +24,9 @@ constexpr int FA_BM = 128;       // queries per CTA (TMEM lanes)
 constexpr int FA_BN = 128;       // keys per tile
 constexpr int FA_STAGES = 4;     // K smem stages (>= slots + 1)
 constexpr int FA_SLOTS = 3;      // TMEM score slots: the MMA warp runs up to two tiles ahead of the softmax warpgroups
-constexpr int FA_THREADS = 320;  // warps 0-3 softmax WG0, 4-7 softmax WG1, warp 8 TMA, warp 9 MMA (+TMEM alloc)
-constexpr uint32_t FA_SLOT = 128, FA_COL_O = 384;   // slot s: S at 128*s (P, bf16, aliases its first 64 columns); O of warpgroup w at 384 + 16*w
+constexpr int FA_THREADS = 352;  // warps 0-3 softmax WG0, 4-7 softmax WG1, warp 8 TMA, warp 9 score MMAs (+TMEM alloc), warp 10 P.V MMAs
+constexpr uint32_t FA_SLOT = 128;   // TMEM: Qa (bf16) [0, 32*KATOMS); slot s: S at 32*KATOMS + 128*s (P, bf16, aliases its first 64 columns);
+                                    // O of warpgroup w behind the slots at + 16*w
 constexpr float FA_RESCALE_THRESHOLD = 8.f;                          // log2 units
 
 template <int KATOMS>
@@ -33,7 +34,7 @@ struct __align__(1024) FwdSmem {
   bf16 q[KATOMS][FA_BM * 64];                 // K-major, 128 B rows, 128B swizzle (one atom = 64 k-elements)
   bf16 k[FA_STAGES][KATOMS][FA_BN * 64];
   float xch[FA_BM][18];                       // WG1 -> WG0 hand-over of (m, O[0..16))
-  uint64_t bar_q, bar_full[FA_STAGES], bar_empty[FA_STAGES], bar_s_full[FA_SLOTS], bar_p_ready[FA_SLOTS], bar_o_done[2];
+  uint64_t bar_q, bar_a_ready, bar_full[FA_STAGES], bar_empty[FA_STAGES], bar_s_full[FA_SLOTS], bar_p_ready[FA_SLOTS], bar_slot_free[FA_SLOTS], bar_o_done[2];
   uint32_t tmem_base;
 };
 
@@ -49,8 +50,13 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fwd_tc_kernel(
 
   if (threadIdx.x == 0) {
     tc::mbar_init(&sm.bar_q, 1);
+    tc::mbar_init(&sm.bar_a_ready, 128);
     for (int s = 0; s < FA_STAGES; ++s) { tc::mbar_init(&sm.bar_full[s], 1); tc::mbar_init(&sm.bar_empty[s], 1); }
-    for (int s = 0; s < FA_SLOTS; ++s) { tc::mbar_init(&sm.bar_s_full[s], 1); tc::mbar_init(&sm.bar_p_ready[s], 128); }
+    for (int s = 0; s < FA_SLOTS; ++s) {
+      tc::mbar_init(&sm.bar_s_full[s], 1);
+      tc::mbar_init(&sm.bar_p_ready[s], 128);
+      tc::mbar_init(&sm.bar_slot_free[s], 1);
+    }
     for (int s = 0; s < 2; ++s) tc::mbar_init(&sm.bar_o_done[s], 1);
     tc::fence_barrier_init();
   }
@@ -60,6 +66,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fwd_tc_kernel(
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
+  constexpr uint32_t COL_SLOT0 = KATOMS * 32, FA_COL_O = COL_SLOT0 + FA_SLOT * FA_SLOTS;
 
   if (warp == 8) {
     // ===================== TMA producer =====================
@@ -77,54 +84,72 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fwd_tc_kernel(
     // ===================== MMA issuer (whole warp runs the uniform loop, one elected lane issues) =====================
     constexpr uint32_t idesc_s = tc::idesc_bf16_f32(FA_BM, FA_BN);
     constexpr uint32_t idesc_o = tc::idesc_bf16_f32(FA_BM, 16) | (1u << 16);      // B (the V block) is MN-major
-    constexpr uint32_t Q_ATOM = (FA_BM * 128) >> 4, K_ATOM = (FA_BN * 128) >> 4, K_STAGE = KATOMS * K_ATOM;
-    const uint32_t q_lo = tc::desc_lo_k(smem_u32(sm.q[0]));
+    constexpr uint32_t K_ATOM = (FA_BN * 128) >> 4, K_STAGE = KATOMS * K_ATOM;
     const uint32_t k_lo = tc::desc_lo_k(smem_u32(sm.k[0][0]));
     const uint32_t v_lo = tc::desc_lo_mn(smem_u32(sm.k[0][C1 >> 6]) + (C1 & 63) * 2, FA_BN * 128);
     const int nks = C1 >> 4;
-    tc::mbar_wait(&sm.bar_q, 0);
-    for (int j = 0; j < ntiles + FA_SLOTS - 1; ++j) {
-      if (j < ntiles) {
-        const int st = j % FA_STAGES, slot = j % FA_SLOTS;
-        tc::mbar_wait(&sm.bar_full[st], (j / FA_STAGES) & 1);
-        tc::tc_fence_after();
-        if (tc::elect_one()) {
-          const uint32_t b0 = k_lo + st * K_STAGE;
-          for (int ks = 0; ks < nks; ++ks)
-            tc::mma_ss(tmem + FA_SLOT * slot, tc::desc64(q_lo + (ks >> 2) * Q_ATOM + (ks & 3) * 2),
-                       tc::desc64(b0 + (ks >> 2) * K_ATOM + (ks & 3) * 2), idesc_s, ks > 0);
-          tc::mma_commit(&sm.bar_s_full[slot]);
-        }
-        __syncwarp();
+    tc::mbar_wait(&sm.bar_a_ready, 0);        // Qa copied to TMEM by warpgroup 0: score MMAs run in TS mode (tools/mma_bench.cu)
+    tc::tc_fence_after();
+    for (int j = 0; j < ntiles; ++j) {
+      const int st = j % FA_STAGES, slot = j % FA_SLOTS;
+      tc::mbar_wait(&sm.bar_full[st], (j / FA_STAGES) & 1);
+      if (j >= FA_SLOTS) tc::mbar_wait(&sm.bar_slot_free[slot], ((j / FA_SLOTS) - 1) & 1);   // P.V of the slot's previous tile done
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+        tc::issue_ts_ksteps_n<0, K_ATOM>(nks, tmem + COL_SLOT0 + FA_SLOT * slot, 0u, tmem, k_lo + st * K_STAGE, idesc_s);
+        tc::mma_commit(&sm.bar_s_full[slot]);
       }
-      const int jj = j - (FA_SLOTS - 1);
-      if (jj >= 0) {
-        const int st = jj % FA_STAGES, slot = jj % FA_SLOTS, wgo = jj & 1;
-        tc::mbar_wait(&sm.bar_p_ready[slot], (jj / FA_SLOTS) & 1);
-        tc::tc_fence_after();
-        if (tc::elect_one()) {
-          const uint32_t vb = v_lo + st * K_STAGE, tp = tmem + FA_SLOT * slot, to = tmem + FA_COL_O + 16 * wgo;
-#pragma unroll
-          for (int ks = 0; ks < FA_BN / 16; ++ks)    // 16 keys = 16 rows of 128 B = 2048 B = 128 descriptor units
-            tc::mma_ts(to, tp + ks * 8, tc::desc64(vb + ks * 128), idesc_o, (jj > 1 || ks > 0) ? 1u : 0u);
-          tc::mma_commit(&sm.bar_empty[st]);
-          tc::mma_commit(&sm.bar_o_done[wgo]);
-        }
-        __syncwarp();
-      }
+      __syncwarp();
     }
-  } else {
+  } else if (warp == 10) {
+    // ===================== P.V issuer: a second issuing warp keeps the tensor pipe fed while the other one waits =====================
+    constexpr uint32_t idesc_o = tc::idesc_bf16_f32(FA_BM, 16) | (1u << 16);      // B (the V block) is MN-major
+    constexpr uint32_t K_ATOM = (FA_BN * 128) >> 4, K_STAGE = KATOMS * K_ATOM;
+    const uint32_t v_lo = tc::desc_lo_mn(smem_u32(sm.k[0][C1 >> 6]) + (C1 & 63) * 2, FA_BN * 128);
+    for (int jj = 0; jj < ntiles; ++jj) {
+      const int st = jj % FA_STAGES, slot = jj % FA_SLOTS, wgo = jj & 1;
+      tc::mbar_wait(&sm.bar_p_ready[slot], (jj / FA_SLOTS) & 1);
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+        const uint32_t vb = v_lo + st * K_STAGE, tp = tmem + COL_SLOT0 + FA_SLOT * slot, to = tmem + FA_COL_O + 16 * wgo;
+#pragma unroll
+        for (int ks = 0; ks < FA_BN / 16; ++ks)    // 16 keys = 16 rows of 128 B = 2048 B = 128 descriptor units
+          tc::mma_ts(to, tp + ks * 8, tc::desc64(vb + ks * 128), idesc_o, (jj > 1 || ks > 0) ? 1u : 0u);
+        tc::mma_commit(&sm.bar_empty[st]);
+        tc::mma_commit(&sm.bar_slot_free[slot]);
+        tc::mma_commit(&sm.bar_o_done[wgo]);
+      }
+      __syncwarp();
+    }
+  } else if (warp < 8) {
     // ===================== softmax warpgroups (thread == query row == TMEM lane) =====================
     const int wg = warp >> 2;
     const int rowi = (warp & 3) * 32 + lane;
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t tout = tlane + FA_COL_O + 16 * wg;
+    if (wg == 0) {                             // stationary Qa tile: shared memory -> TMEM (row -> lane, column c <- elements 2c, 2c+1)
+      tc::mbar_wait(&sm.bar_q, 0);
+#pragma unroll
+      for (int a = 0; a < KATOMS; ++a) {
+        uint32_t w[32];
+        const uint8_t* rowp = reinterpret_cast<const uint8_t*>(sm.q[a]) + rowi * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {          // undo the 128B swizzle: 16-byte chunk c of row r sits at c ^ (r % 8)
+          const uint4 v = *reinterpret_cast<const uint4*>(rowp + ((c ^ (rowi & 7)) << 4));
+          w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+        }
+        tc::tmem_st_x32(tlane + a * 32, w);
+      }
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      tc::mbar_arrive(&sm.bar_a_ready);
+    }
     float m = -INFINITY;                      // reference maximum of this warpgroup's exponentials (log2 units)
     uint32_t r[4][32];
     int nmine = 0;
     for (int j = wg; j < ntiles; j += 2, ++nmine) {
       const int it = j >> 1, slot = j % FA_SLOTS;
-      const uint32_t tslot = tlane + FA_SLOT * slot;
+      const uint32_t tslot = tlane + COL_SLOT0 + FA_SLOT * slot;
       tc::mbar_wait(&sm.bar_s_full[slot], (j / FA_SLOTS) & 1);
       tc::tc_fence_after();
       tc::tmem_ld_x32(tslot + 0, r[0]);

@@ -26,7 +26,7 @@ typedef __nv_bfloat16 bf16;
 // ------------------------------------------------------------------------------------------------
 // ping-pong kernel skeleton: 8 math warps (two warpgroups, one TMEM slot each), 1 TMA warp, 1 MMA warp
 // ------------------------------------------------------------------------------------------------
-constexpr int PP_THREADS = 320;
+constexpr int PP_THREADS = 352;   // warps 0-7 math, 8 TMA, 9 score-MMA issuer (+TMEM alloc), 10 gradient-MMA issuer
 constexpr int PP_BM = 128;        // stationary rows (TMEM lanes)
 constexpr int PP_BN = 64;         // streamed rows per tile (TMEM columns per slot)
 constexpr int PP_STAGES = 5;      // smem stages of the streamed operand (>= slots + 1)
@@ -38,25 +38,30 @@ struct __align__(1024) PPSmem {
   bf16 stat[KATOMS][PP_BM * 64];                   // stationary operand, 16 KB per 64-column atom
   bf16 strm[PP_STAGES][KATOMS][PP_BN * 64];        // streamed operand, 8 KB per atom
   uint64_t bar_stat, bar_full[PP_STAGES], bar_empty[PP_STAGES];
-  uint64_t bar_s_full[PP_SLOTS], bar_p_ready[PP_SLOTS], bar_final;
+  uint64_t bar_s_full[PP_SLOTS], bar_p_ready[PP_SLOTS], bar_slot_free[PP_SLOTS], bar_final, bar_a_ready;
   uint32_t tmem_base;
 };
 
 __host__ __device__ constexpr uint32_t idesc_bmn(int M, int N) { return tc::idesc_bf16_f32(M, N) | (1u << 16); }
 
 // Shared skeleton of the two kernels.
-//   warp 8: TMA producer;  warp 9: MMA issuer;  warps 0-7: two math warpgroups, WG w takes tiles j = w (mod 2).
-//   Tile j uses TMEM slot j % nslots.  The MMA warp issues the score MMAs of tile j as soon as the slot's previous
-//   tile (j - nslots) has had its gradient MMAs ISSUED (tcgen05.mma of one thread execute in order, so the slot's
-//   P/dS -- which alias the score columns -- are consumed before they are overwritten); the gradient MMAs of tile
-//   j - (nslots-1) follow.  A warpgroup therefore finds its next scores ready when it finishes a tile.
+//   warp 8: TMA producer;  warp 9: score-MMA issuer;  warp 10: gradient-MMA issuer;  warps 0-7: two math warpgroups,
+//   WG w takes tiles j = w (mod 2).  Tile j uses TMEM slot j % nslots.  Two issuing warps, because the tensor pipe idles
+//   whenever its single issuer sits in an mbarrier wait (measured with the clock timeline, tools/attn_timeline.py): the
+//   score warp runs ahead by up to nslots tiles (it only waits for the K tile and for the slot's previous gradient MMAs,
+//   bar_slot_free), the gradient warp follows the math warpgroups (bar_p_ready).
 template <int KATOMS>
 __device__ __forceinline__ void pp_init(PPSmem<KATOMS>& sm, int warp, int lane, const CUtensorMap* m0, const CUtensorMap* m1) {
   if (threadIdx.x == 0) {
     tc::mbar_init(&sm.bar_stat, 1);
     for (int s = 0; s < PP_STAGES; ++s) { tc::mbar_init(&sm.bar_full[s], 1); tc::mbar_init(&sm.bar_empty[s], 1); }
-    for (int s = 0; s < PP_SLOTS; ++s) { tc::mbar_init(&sm.bar_s_full[s], 1); tc::mbar_init(&sm.bar_p_ready[s], 128); }
+    for (int s = 0; s < PP_SLOTS; ++s) {
+      tc::mbar_init(&sm.bar_s_full[s], 1);
+      tc::mbar_init(&sm.bar_p_ready[s], 128);
+      tc::mbar_init(&sm.bar_slot_free[s], 1);
+    }
     tc::mbar_init(&sm.bar_final, 1);
+    tc::mbar_init(&sm.bar_a_ready, 128);
     tc::fence_barrier_init();
   }
   if (warp == 8 && lane == 0) { tc::tma_prefetch_desc(m0); tc::tma_prefetch_desc(m1); }
@@ -79,6 +84,28 @@ __device__ __forceinline__ void pp_producer(PPSmem<KATOMS>& sm, const CUtensorMa
   }
 }
 
+// The stationary operand is the A operand of every score MMA.  A from shared memory costs ~45 cycles per MMA on top of
+// N/2 (tools/mma_bench.cu: SS N=64 76 cycles, TS 46), so warpgroup 0 copies the tile once into TMEM (row r -> lane r,
+// column c <- elements 2c, 2c+1, the layout P uses) and all score MMAs run in TS mode.
+template <int KATOMS>
+__device__ __forceinline__ void pp_stationary_to_tmem(PPSmem<KATOMS>& sm, uint32_t tlane_a, int r) {
+  tc::mbar_wait(&sm.bar_stat, 0);
+#pragma unroll
+  for (int a = 0; a < KATOMS; ++a) {
+    uint32_t w[32];
+    const uint8_t* rowp = reinterpret_cast<const uint8_t*>(sm.stat[a]) + r * 128;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {                        // undo the 128B swizzle: 16-byte chunk c of row r sits at c ^ (r % 8)
+      const uint4 v = *reinterpret_cast<const uint4*>(rowp + ((c ^ (r & 7)) << 4));
+      w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+    }
+    tc::tmem_st_x32(tlane_a + a * 32, w);
+  }
+  tc::tmem_st_wait();
+  tc::tc_fence_before();
+  tc::mbar_arrive(&sm.bar_a_ready);
+}
+
 // ---- key-stationary: dK, dV ------------------------------------------------------------------------
 // TMEM columns: slot s at 128*s: S'^T [0,64) dP'^T [64,128); P^T over [0,32), dS^T over [64,96).  dV at 384, dK at 400.
 template <int KATOMS>
@@ -92,8 +119,9 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dkv_tc_kernel(
   const int bn = blockIdx.y, k0 = blockIdx.x * PP_BM;
   const int ntiles = (L + PP_BN - 1) / PP_BN;
   const int nks = C1 >> 4;
-  constexpr uint32_t COL_DV = 384, COL_DK = 400;
-  constexpr int NS = PP_SLOTS;
+  // TMEM columns: Ka (bf16) [0, 32*KATOMS); slots of 128 behind it; dV (16) and dK (32) behind the slots
+  constexpr int NS = (KATOMS * 32 + 3 * 128 + 48 <= 512) ? 3 : 2;
+  constexpr uint32_t COL_SLOT0 = KATOMS * 32, COL_DV = COL_SLOT0 + 128 * NS, COL_DK = COL_DV + 16;
 
   pp_init(sm, warp, lane, &tm_k_stat, &tm_q_strm);
   const uint32_t tmem = sm.tmem_base;
@@ -109,51 +137,53 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dkv_tc_kernel(
     const uint32_t strm_lo = tc::desc_lo_k(smem_u32(sm.strm[0][0]));
     const uint32_t v_lo = tc::desc_lo_mn(smem_u32(sm.strm[0][C1 >> 6]) + (C1 & 63) * 2, PP_BN * 128);
     const uint32_t q_lo = tc::desc_lo_mn(smem_u32(sm.strm[0][0]), PP_BN * 128);
-    tc::mbar_wait(&sm.bar_stat, 0);
-    for (int j = 0; j < ntiles + NS - 1; ++j) {
-      if (j < ntiles) {
-        const int st = j % PP_STAGES, slot = j % NS;
-        const uint32_t tslot = tmem + PP_SLOT_COLS * slot;
-        tc::mbar_wait(&sm.bar_full[st], (j / PP_STAGES) & 1);
-        tc::tc_fence_after();
-        if (tc::elect_one()) {
-          const uint32_t b0 = strm_lo + st * STAGE;
-          for (int ks = 0; ks < nks; ++ks)
-            tc::mma_ss(tslot, tc::desc64(stat_lo + (ks >> 2) * STAT_ATOM + (ks & 3) * 2),
-                       tc::desc64(b0 + (ks >> 2) * STRM_ATOM + (ks & 3) * 2), idesc_s, ks > 0);
-          tc::mma_ss(tslot + 64, tc::desc64(stat_lo + (nks >> 2) * STAT_ATOM + (nks & 3) * 2),
-                     tc::desc64(b0 + (nks >> 2) * STRM_ATOM + (nks & 3) * 2), idesc_s, 0);
-          tc::mma_commit(&sm.bar_s_full[slot]);
-        }
-        __syncwarp();
+    tc::mbar_wait(&sm.bar_a_ready, 0);
+    tc::tc_fence_after();
+    for (int j = 0; j < ntiles; ++j) {
+      const int st = j % PP_STAGES, slot = j % NS;
+      const uint32_t tslot = tmem + COL_SLOT0 + PP_SLOT_COLS * slot;
+      tc::mbar_wait(&sm.bar_full[st], (j / PP_STAGES) & 1);
+      if (j >= NS) tc::mbar_wait(&sm.bar_slot_free[slot], ((j / NS) - 1) & 1);
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+        tc::issue_ts_ksteps_n<1, STRM_ATOM>(nks, tslot, tslot + 64, tmem, strm_lo + st * STAGE, idesc_s);
+        tc::mma_commit(&sm.bar_s_full[slot]);
       }
-      const int jj = j - (NS - 1);
-      if (jj >= 0) {
-        const int st = jj % PP_STAGES, slot = jj % NS;
-        const uint32_t tslot = tmem + PP_SLOT_COLS * slot;
-        tc::mbar_wait(&sm.bar_p_ready[slot], (jj / NS) & 1);
-        tc::tc_fence_after();
-        if (tc::elect_one()) {
-          const uint32_t vb = v_lo + st * STAGE, qb = q_lo + st * STAGE;
-#pragma unroll
-          for (int ks = 0; ks < PP_BN / 16; ++ks) {
-            tc::mma_ts(tmem + COL_DV, tslot + ks * 8, tc::desc64(vb + ks * 128), idesc_dv, (jj > 0 || ks > 0) ? 1u : 0u);
-            tc::mma_ts(tmem + COL_DK, tslot + 64 + ks * 8, tc::desc64(qb + ks * 128), idesc_dk, (jj > 0 || ks > 0) ? 1u : 0u);
-          }
-          tc::mma_commit(&sm.bar_empty[st]);
-          if (jj == ntiles - 1) tc::mma_commit(&sm.bar_final);
-        }
-        __syncwarp();
-      }
+      __syncwarp();
     }
-  } else {
+  } else if (warp == 10) {
+    constexpr uint32_t idesc_dv = idesc_bmn(PP_BM, 16);
+    constexpr uint32_t idesc_dk = idesc_bmn(PP_BM, 32);
+    constexpr uint32_t STRM_ATOM = (PP_BN * 128) >> 4, STAGE = KATOMS * STRM_ATOM;
+    const uint32_t v_lo = tc::desc_lo_mn(smem_u32(sm.strm[0][C1 >> 6]) + (C1 & 63) * 2, PP_BN * 128);
+    const uint32_t q_lo = tc::desc_lo_mn(smem_u32(sm.strm[0][0]), PP_BN * 128);
+    for (int jj = 0; jj < ntiles; ++jj) {
+      const int st = jj % PP_STAGES, slot = jj % NS;
+      const uint32_t tslot = tmem + COL_SLOT0 + PP_SLOT_COLS * slot;
+      tc::mbar_wait(&sm.bar_p_ready[slot], (jj / NS) & 1);
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+        const uint32_t vb = v_lo + st * STAGE, qb = q_lo + st * STAGE;
+#pragma unroll
+        for (int ks = 0; ks < PP_BN / 16; ++ks) {
+          tc::mma_ts(tmem + COL_DV, tslot + ks * 8, tc::desc64(vb + ks * 128), idesc_dv, (jj > 0 || ks > 0) ? 1u : 0u);
+          tc::mma_ts(tmem + COL_DK, tslot + 64 + ks * 8, tc::desc64(qb + ks * 128), idesc_dk, (jj > 0 || ks > 0) ? 1u : 0u);
+        }
+        tc::mma_commit(&sm.bar_empty[st]);
+        tc::mma_commit(&sm.bar_slot_free[slot]);
+        if (jj == ntiles - 1) tc::mma_commit(&sm.bar_final);
+      }
+      __syncwarp();
+    }
+  } else if (warp < 8) {
     // ===================== math warpgroups: thread == key row == TMEM lane =====================
     const int wg = warp >> 2;
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    if (wg == 0) pp_stationary_to_tmem(sm, tlane, (warp & 3) * 32 + lane);
     uint32_t rs[32], rd[32], pp[16], pd[16];
     for (int j = wg; j < ntiles; j += 2) {
       const int slot = j % NS;
-      const uint32_t tslot = tlane + PP_SLOT_COLS * slot;
+      const uint32_t tslot = tlane + COL_SLOT0 + PP_SLOT_COLS * slot;
       tc::mbar_wait(&sm.bar_s_full[slot], (j / NS) & 1);
       tc::tc_fence_after();
 #pragma unroll
@@ -237,18 +267,22 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dkv_tc_kernel(
 template <int KATOMS>
 __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dq_tc_kernel(
     const __grid_constant__ CUtensorMap tm_q_stat, const __grid_constant__ CUtensorMap tm_k_strm,
-    float* __restrict__ dqa, int L, int KD, int NQ, int C1) {
+    float* __restrict__ dqa, int L, int KD, int NQ, int C1, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   PPSmem<KATOMS>& sm = *reinterpret_cast<PPSmem<KATOMS>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bn = blockIdx.y, q0 = blockIdx.x * PP_BM;
   const int ntiles = (L + PP_BN - 1) / PP_BN;
   const int nks = C1 >> 4;
-  const int NS = NQ <= 128 ? 3 : 2;
-  const uint32_t COL_DQ = PP_SLOT_COLS * NS;
+  // TMEM columns: Qa (bf16) [0, 32*KATOMS); slots of 128 behind it; dQa (NQ <= 160) behind the slots
+  const int NS = (KATOMS * 32 + 3 * 128 + NQ <= 512) ? 3 : 2;
+  const uint32_t COL_SLOT0 = KATOMS * 32, COL_DQ = COL_SLOT0 + PP_SLOT_COLS * NS;
 
   pp_init(sm, warp, lane, &tm_q_stat, &tm_k_strm);
   const uint32_t tmem = sm.tmem_base;
+  // optional timeline of CTA (0,0): dbg[event][tile], clock64 stamps (tools/attn_timeline.py)
+  const bool rec = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+#define PP_STAMP(ev, tile) do { if (rec) dbg[(ev) * 64 + (tile)] = clock64(); } while (0)   // 12 events x 64 tiles
 
   if (warp == 8) {
     if (lane == 0) pp_producer(sm, &tm_q_stat, &tm_k_strm, q0, bn, ntiles);
@@ -259,55 +293,63 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dq_tc_kernel(
     const uint32_t stat_lo = tc::desc_lo_k(smem_u32(sm.stat[0]));
     const uint32_t strm_lo = tc::desc_lo_k(smem_u32(sm.strm[0][0]));
     const uint32_t k_lo = tc::desc_lo_mn(smem_u32(sm.strm[0][0]), PP_BN * 128);
-    tc::mbar_wait(&sm.bar_stat, 0);
-    for (int j = 0; j < ntiles + NS - 1; ++j) {
-      if (j < ntiles) {
-        const int st = j % PP_STAGES, slot = j % NS;
-        const uint32_t tslot = tmem + PP_SLOT_COLS * slot;
-        tc::mbar_wait(&sm.bar_full[st], (j / PP_STAGES) & 1);
-        tc::tc_fence_after();
-        if (tc::elect_one()) {
-          const uint32_t b0 = strm_lo + st * STAGE;
-          for (int ks = 0; ks < nks; ++ks)
-            tc::mma_ss(tslot, tc::desc64(stat_lo + (ks >> 2) * STAT_ATOM + (ks & 3) * 2),
-                       tc::desc64(b0 + (ks >> 2) * STRM_ATOM + (ks & 3) * 2), idesc_s, ks > 0);
-          tc::mma_ss(tslot + 64, tc::desc64(stat_lo + (nks >> 2) * STAT_ATOM + (nks & 3) * 2),
-                     tc::desc64(b0 + (nks >> 2) * STRM_ATOM + (nks & 3) * 2), idesc_s, 0);
-          tc::mma_commit(&sm.bar_s_full[slot]);
-        }
-        __syncwarp();
+    tc::mbar_wait(&sm.bar_a_ready, 0);
+    tc::tc_fence_after();
+    for (int j = 0; j < ntiles; ++j) {
+      const int st = j % PP_STAGES, slot = j % NS;
+      const uint32_t tslot = tmem + COL_SLOT0 + PP_SLOT_COLS * slot;
+      PP_STAMP(8, j);
+      tc::mbar_wait(&sm.bar_full[st], (j / PP_STAGES) & 1);
+      if (j >= NS) tc::mbar_wait(&sm.bar_slot_free[slot], ((j / NS) - 1) & 1);
+      tc::tc_fence_after();
+      PP_STAMP(0, j);
+      if (tc::elect_one()) {
+        tc::issue_ts_ksteps_n<1, STRM_ATOM>(nks, tslot, tslot + 64, tmem, strm_lo + st * STAGE, idesc_s);
+        tc::mma_commit(&sm.bar_s_full[slot]);
       }
-      const int jj = j - (NS - 1);
-      if (jj >= 0) {
-        const int st = jj % PP_STAGES, slot = jj % NS;
-        const uint32_t tslot = tmem + PP_SLOT_COLS * slot;
-        tc::mbar_wait(&sm.bar_p_ready[slot], (jj / NS) & 1);
-        tc::tc_fence_after();
-        if (tc::elect_one()) {
-          const uint32_t kb = k_lo + st * STAGE;
-#pragma unroll
-          for (int ks = 0; ks < PP_BN / 16; ++ks)
-            tc::mma_ts(tmem + COL_DQ, tslot + 64 + ks * 8, tc::desc64(kb + ks * 128), idesc_dq, (jj > 0 || ks > 0) ? 1u : 0u);
-          tc::mma_commit(&sm.bar_empty[st]);
-          if (jj == ntiles - 1) tc::mma_commit(&sm.bar_final);
-        }
-        __syncwarp();
-      }
+      __syncwarp();
+      PP_STAMP(1, j);
     }
-  } else {
+  } else if (warp == 10) {
+    const uint32_t idesc_dq = idesc_bmn(PP_BM, NQ);
+    constexpr uint32_t STRM_ATOM = (PP_BN * 128) >> 4, STAGE = KATOMS * STRM_ATOM;
+    const uint32_t k_lo = tc::desc_lo_mn(smem_u32(sm.strm[0][0]), PP_BN * 128);
+    for (int jj = 0; jj < ntiles; ++jj) {
+      const int st = jj % PP_STAGES, slot = jj % NS;
+      const uint32_t tslot = tmem + COL_SLOT0 + PP_SLOT_COLS * slot;
+      tc::mbar_wait(&sm.bar_p_ready[slot], (jj / NS) & 1);
+      tc::tc_fence_after();
+      PP_STAMP(2, jj);
+      if (tc::elect_one()) {
+        const uint32_t kb = k_lo + st * STAGE;
+#pragma unroll
+        for (int ks = 0; ks < PP_BN / 16; ++ks)
+          tc::mma_ts(tmem + COL_DQ, tslot + 64 + ks * 8, tc::desc64(kb + ks * 128), idesc_dq, (jj > 0 || ks > 0) ? 1u : 0u);
+        tc::mma_commit(&sm.bar_empty[st]);
+        tc::mma_commit(&sm.bar_slot_free[slot]);
+        if (jj == ntiles - 1) tc::mma_commit(&sm.bar_final);
+      }
+      __syncwarp();
+      PP_STAMP(9, jj);
+    }
+  } else if (warp < 8) {
     const int wg = warp >> 2;
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    if (wg == 0) pp_stationary_to_tmem(sm, tlane, (warp & 3) * 32 + lane);
     uint32_t rs[32], rd[32], pd[16];
     for (int j = wg; j < ntiles; j += 2) {
       const int slot = j % NS;
-      const uint32_t tslot = tlane + PP_SLOT_COLS * slot;
+      const uint32_t tslot = tlane + COL_SLOT0 + PP_SLOT_COLS * slot;
+      if ((warp & 3) == 0) PP_STAMP(3, j);
       tc::mbar_wait(&sm.bar_s_full[slot], (j / NS) & 1);
       tc::tc_fence_after();
+      if ((warp & 3) == 0) PP_STAMP(4, j);
 #pragma unroll
       for (int c = 0; c < PP_BN / 32; ++c) {
         tc::tmem_ld_x32(tslot + c * 32, rs);
         tc::tmem_ld_x32(tslot + 64 + c * 32, rd);
         tc::tmem_ld_wait();
+        if ((warp & 3) == 0 && c == 0) PP_STAMP(5, j);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float p0 = tc::ex2f(__uint_as_float(rs[2 * i])), p1 = tc::ex2f(__uint_as_float(rs[2 * i + 1]));
@@ -318,8 +360,11 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dq_tc_kernel(
       tc::tmem_st_wait();
       tc::tc_fence_before();
       tc::mbar_arrive(&sm.bar_p_ready[slot]);
+      if ((warp & 3) == 0) PP_STAMP(6, j);
     }
+    if ((warp & 3) == 0) PP_STAMP(7, wg);
     tc::mbar_wait(&sm.bar_final, 0);
+    if ((warp & 3) == 0) PP_STAMP(7, 2 + wg);
     tc::tc_fence_after();
     // dQa rows -> global (B,nh,L,KD) fp32; the two warpgroups split the columns in 32-wide chunks
     const int qi = q0 + (warp & 3) * 32 + lane;
@@ -342,10 +387,16 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_bwd_dq_tc_kernel(
       }
     }
   }
+  if ((warp & 3) == 0 && warp < 8) PP_STAMP(7, 4 + (warp >> 2));
+#undef PP_STAMP
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 9) tc::tmem_dealloc<512>(tmem);
 }
+
+// debug hook (tools/attn_timeline.py): device buffer of 8 x 64 clock stamps written by CTA (0,0) of the dq kernel
+long long* g_attn_dbg = nullptr;
+extern "C" void aaconv_debug_set_timeline(void* p) { g_attn_dbg = static_cast<long long*>(p); }
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -376,7 +427,7 @@ static int launch_bwd(const Dims& d, const AugLayout& a, const void* qa, const v
   {
     auto kern = attn_bwd_dq_tc_kernel<KATOMS>;
     AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, PP_THREADS, smem, st>>>(tq_stat, tk_strm, dqa, d.L, a.KD, a.NQ, a.C1);
+    kern<<<grid, PP_THREADS, smem, st>>>(tq_stat, tk_strm, dqa, d.L, a.KD, a.NQ, a.C1, g_attn_dbg);
     AACONV_LAUNCH_OK("attn_bwd_dq_tc");
   }
   return 0;

@@ -184,6 +184,34 @@ __device__ __forceinline__ uint32_t desc_lo_mn(uint32_t saddr, uint32_t lbo_byte
 }
 __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)DESC_HI_SW128 << 32) | lo; }
 
+// Fully unrolled score-MMA issue (A in TMEM, B K-major in shared memory, one 16-wide k-step per MMA).  The issue rate of the
+// single issuing thread is the critical resource: with compile-time trip counts and offsets the tensor pipe runs at its
+// N/2-cycle floor, with a runtime loop each MMA costs ~80 cycles of issue (tools/mma_bench.cu).  NKS = number of k-steps
+// of the main accumulator; EXTRA = 1 issues one more k-step (index NKS) into a second accumulator.
+template <int NKS, int EXTRA, uint32_t B_ATOM>
+__device__ __forceinline__ void issue_ts_ksteps(uint32_t d_main, uint32_t d_extra, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc) {
+#pragma unroll
+  for (int ks = 0; ks < NKS; ++ks)
+    mma_ts(d_main, a_tmem + ks * 8, desc64(b_lo + (ks >> 2) * B_ATOM + (ks & 3) * 2), idesc, ks > 0 ? 1u : 0u);
+  if (EXTRA) mma_ts(d_extra, a_tmem + NKS * 8, desc64(b_lo + (NKS >> 2) * B_ATOM + (NKS & 3) * 2), idesc, 0u);
+}
+template <int EXTRA, uint32_t B_ATOM>
+__device__ __forceinline__ void issue_ts_ksteps_n(int nks, uint32_t d_main, uint32_t d_extra, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc) {
+  switch (nks) {   // warp-uniform
+    case 1: issue_ts_ksteps<1, EXTRA, B_ATOM>(d_main, d_extra, a_tmem, b_lo, idesc); break;
+    case 2: issue_ts_ksteps<2, EXTRA, B_ATOM>(d_main, d_extra, a_tmem, b_lo, idesc); break;
+    case 3: issue_ts_ksteps<3, EXTRA, B_ATOM>(d_main, d_extra, a_tmem, b_lo, idesc); break;
+    case 4: issue_ts_ksteps<4, EXTRA, B_ATOM>(d_main, d_extra, a_tmem, b_lo, idesc); break;
+    case 5: issue_ts_ksteps<5, EXTRA, B_ATOM>(d_main, d_extra, a_tmem, b_lo, idesc); break;
+    case 6: issue_ts_ksteps<6, EXTRA, B_ATOM>(d_main, d_extra, a_tmem, b_lo, idesc); break;
+    case 7: issue_ts_ksteps<7, EXTRA, B_ATOM>(d_main, d_extra, a_tmem, b_lo, idesc); break;
+    case 8: issue_ts_ksteps<8, EXTRA, B_ATOM>(d_main, d_extra, a_tmem, b_lo, idesc); break;
+    case 9: issue_ts_ksteps<9, EXTRA, B_ATOM>(d_main, d_extra, a_tmem, b_lo, idesc); break;
+    case 10: issue_ts_ksteps<10, EXTRA, B_ATOM>(d_main, d_extra, a_tmem, b_lo, idesc); break;
+    default: issue_ts_ksteps<11, EXTRA, B_ATOM>(d_main, d_extra, a_tmem, b_lo, idesc); break;
+  }
+}
+
 // advance the start address by `bytes` (a multiple of 16; used to step K by 16 bf16 = 32 B inside the atom)
 __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); }
 
