@@ -1,0 +1,805 @@
+// bf16 tcgen05 attention core of AAConv2d for small value widths (dv/nh <= 2, the Transition-1 case): forward, dK/dV and dQa
+// kernels in which only the dense contractions stay on the tensor cores and the rank-dvh value terms run on the CUDA cores:
+//
+//   forward   S' = Qa.Ka^T (tcgen05, TS)           p = 2^(S'-m),  l += p,  o += p v[k]           (no P write-back, no P.V MMA)
+//   backward  S' = Qa.Ka^T - lse2 (tcgen05, TS)    p = 2^S',  dP = dO.v[k] - delta,  dS = p dP    (no dP' MMA, no dP' TMEM read)
+//             dQa += dS.Ka,  dK += dS^T.Qa,  dV += P^T.dO  (tcgen05, TS, MN-major B)
+//
+// Why (measured): the value width is 1..2, so P.V / dO.v are 1-2 FMAs per score next to one MUFU.EX2;
+// doing them in registers halves the TMEM reads, removes two of the four barrier round trips per tile and shrinks a score
+// slot to the S' columns alone, so that four slots fit in TMEM and the issuing warps run far enough ahead of the math
+// warpgroups to keep both busy.  v / dO / delta tiles come as fp32 through 1-D bulk copies on the K/Q tile's barrier.
+// Reference rows a3-a8 (attn_aug_conv.py:75-91) and their adjoint; layouts as in attn_tc_bwd.cu.
+#include "tc_common.cuh"
+#include "bf16_path.cuh"
+
+namespace aaconv {
+
+using tc::smem_u32;
+typedef __nv_bfloat16 bf16;
+
+// ablation switches for tools/attn_ablate.py (0 in production): 1 no MUFU, 2 no global traffic after the first tiles,
+// 4 no gradient MMAs, 8 no math at all
+int g_attn_dbg_mode = 0;
+extern long long* g_attn_dbg;      // attn_tc_bwd.cu: timeline buffer (tools/attn_timeline.py)
+extern "C" void aaconv_debug_set_mode(int m) { g_attn_dbg_mode = m; }
+
+namespace {
+
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// index + phase of a ring of n entries, advanced without integer division (a runtime modulo costs a MUFU.RCP, and the MUFU
+// pipe is what the math warps saturate)
+struct Ring {
+  int i = 0;
+  uint32_t ph = 0;
+  __device__ __forceinline__ void next(int n) { if (++i == n) { i = 0; ph ^= 1; } }
+};
+
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
+// stationary tile (shared memory, 128B-swizzled K-major atoms) -> TMEM: row r -> lane r, column c <- elements 2c, 2c+1
+template <int KATOMS>
+__device__ __forceinline__ void stationary_to_tmem(const bf16 (*stat)[128 * 64], uint32_t tlane_a, int r) {
+#pragma unroll
+  for (int a = 0; a < KATOMS; ++a) {
+    uint32_t w[32];
+    const uint8_t* rowp = reinterpret_cast<const uint8_t*>(stat[a]) + r * 128;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 v = *reinterpret_cast<const uint4*>(rowp + ((c ^ (r & 7)) << 4));
+      w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+    }
+    tc::tmem_st_x32(tlane_a + a * 32, w);
+  }
+  tc::tmem_st_wait();
+  tc::tc_fence_before();
+}
+
+// one key tile of the forward softmax: scores of this thread's query row in r (log2 units), fp32 values in shared memory
+template <int DVH, bool TAIL>
+__device__ __forceinline__ void fwd_cc_tile(uint32_t (&r)[4][32], uint32_t vt, int nvalid, float& m, float& l, float (&acc)[DVH]) {
+  if (TAIL) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c * 32 + i >= nvalid) r[c][i] = 0xff800000u;   // zero-filled keys past L: logit -> -inf
+  }
+  float mt = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) mt = fmaxf(mt, fmaxf(__uint_as_float(r[c][i]), __uint_as_float(r[c][i + 1])));
+  if (mt > m + 8.f) {                          // lazy rescale: exponentials stay below 2^8
+    const float m_new = fmaxf(m, mt);
+    const float alpha = tc::ex2f(m - m_new);   // 0 on the first tile (m = -inf)
+    l *= alpha;
+#pragma unroll
+    for (int e = 0; e < DVH; ++e) acc[e] *= alpha;
+    m = m_new;
+  }
+  const float mneg = -m;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float vv[4 * DVH];
+#pragma unroll
+      for (int u = 0; u < DVH; ++u) {
+        const float4 t4 = lds128(vt + ((c * 32 + i) * DVH + 4 * u) * 4);
+        vv[4 * u] = t4.x; vv[4 * u + 1] = t4.y; vv[4 * u + 2] = t4.z; vv[4 * u + 3] = t4.w;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float p = tc::ex2f(__uint_as_float(r[c][i + u]) + mneg);
+        l += p;
+#pragma unroll
+        for (int e = 0; e < DVH; ++e) {
+          const float val = (TAIL && c * 32 + i + u >= nvalid) ? 0.f : vv[u * DVH + e];
+          acc[e] = fmaf(p, val, acc[e]);
+        }
+      }
+    }
+}
+
+// ================================================================================================
+// forward
+// ================================================================================================
+constexpr int CF_BM = 128, CF_BN = 128, CF_SLOTS = 3, CF_THREADS = 320;
+template <int KATOMS> struct CfStages { static constexpr int value = KATOMS >= 3 ? 3 : 4; };
+
+template <int KATOMS, int DVH>
+struct __align__(1024) CfSmem {
+  static constexpr int ST = CfStages<KATOMS>::value;
+  bf16 q[KATOMS][CF_BM * 64];
+  bf16 k[ST][KATOMS][CF_BN * 64];
+  float vt[ST][CF_BN * DVH];                  // fp32 values of the key tile
+  float xch[CF_BM][4];                        // WG1 -> WG0 hand-over of (m, l, o[0..DVH))
+  uint64_t bar_q, bar_a_ready, bar_full[ST], bar_empty[ST], bar_s_full[CF_SLOTS], bar_slot_free[CF_SLOTS];
+  uint32_t tmem_base;
+};
+
+template <int KATOMS, int NKS, class Smem>
+__device__ __forceinline__ void cf_score_loop(Smem& sm, uint32_t tmem, int ntiles) {
+  constexpr int ST = Smem::ST, NS = CF_SLOTS;
+  constexpr uint32_t COL_SLOT0 = KATOMS * 32;
+  constexpr uint32_t idesc_s = tc::idesc_bf16_f32(CF_BM, CF_BN);
+  constexpr uint32_t K_ATOM = (CF_BN * 128) >> 4, K_STAGE = KATOMS * K_ATOM;
+  const uint32_t k_lo = tc::desc_lo_k(smem_u32(sm.k[0][0]));
+  Ring rst, rsl;
+  for (int j = 0; j < ntiles; ++j, rst.next(ST), rsl.next(NS)) {
+    const int st = rst.i, slot = rsl.i;
+    tc::mbar_wait(&sm.bar_full[st], rst.ph);
+    if (j >= NS) tc::mbar_wait(&sm.bar_slot_free[slot], rsl.ph ^ 1);
+    tc::tc_fence_after();
+    if (tc::elect_one()) {
+      tc::issue_ts_ksteps<NKS, 0, K_ATOM>(tmem + COL_SLOT0 + 128 * slot, 0u, tmem, k_lo + st * K_STAGE, idesc_s);
+      tc::mma_commit(&sm.bar_s_full[slot]);
+      tc::mma_commit(&sm.bar_empty[st]);        // the K tile is free once these MMAs are done (+128 arrivals for vt)
+    }
+    __syncwarp();
+  }
+}
+
+template <int KATOMS, int DVH>
+__global__ void __launch_bounds__(CF_THREADS, 1) attn_fwd_cc_kernel(
+    const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, const float* __restrict__ v,
+    float* __restrict__ o, float* __restrict__ lse, int L, int C1, int dbg) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  typedef CfSmem<KATOMS, DVH> Smem;
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int ST = Smem::ST, NS = CF_SLOTS;
+  constexpr uint32_t COL_SLOT0 = KATOMS * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bn = blockIdx.y, q0 = blockIdx.x * CF_BM;
+  const int ntiles = (L + CF_BN - 1) / CF_BN;
+
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&sm.bar_q, 1);
+    tc::mbar_init(&sm.bar_a_ready, 128);
+    for (int s = 0; s < ST; ++s) { tc::mbar_init(&sm.bar_full[s], 1); tc::mbar_init(&sm.bar_empty[s], 129); }
+    for (int s = 0; s < NS; ++s) { tc::mbar_init(&sm.bar_s_full[s], 1); tc::mbar_init(&sm.bar_slot_free[s], 128); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 8 && lane == 0) { tc::tma_prefetch_desc(&tm_q); tc::tma_prefetch_desc(&tm_k); }
+  if (warp == 9) tc::tmem_alloc<512>(&sm.tmem_base);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      tc::mbar_arrive_expect_tx(&sm.bar_q, KATOMS * CF_BM * 64 * 2);
+      for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.q[a], &tm_q, &sm.bar_q, a * 64, q0, bn);
+      Ring rg;
+      for (int j = 0; j < ntiles; ++j, rg.next(ST)) {
+        const int s = rg.i;
+        const int nvalid = min(CF_BN, L - j * CF_BN);
+        tc::mbar_wait(&sm.bar_empty[s], rg.ph ^ 1);
+        tc::mbar_arrive_expect_tx(&sm.bar_full[s], KATOMS * CF_BN * 64 * 2 + nvalid * DVH * 4);
+        for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.k[s][a], &tm_k, &sm.bar_full[s], a * 64, j * CF_BN, bn);
+        bulk_g2s(sm.vt[s], v + ((size_t)bn * L + (size_t)j * CF_BN) * DVH, nvalid * DVH * 4, &sm.bar_full[s]);
+      }
+    }
+  } else if (warp == 9) {
+    const int nks = C1 >> 4;
+    tc::mbar_wait(&sm.bar_a_ready, 0);
+    tc::tc_fence_after();
+    switch (nks) {      // dispatched once, outside the tile loop
+      case 1: cf_score_loop<KATOMS, 1>(sm, tmem, ntiles); break;
+      case 2: cf_score_loop<KATOMS, 2>(sm, tmem, ntiles); break;
+      case 3: cf_score_loop<KATOMS, 3>(sm, tmem, ntiles); break;
+      case 4: cf_score_loop<KATOMS, 4>(sm, tmem, ntiles); break;
+      case 5: cf_score_loop<KATOMS, 5>(sm, tmem, ntiles); break;
+      case 6: cf_score_loop<KATOMS, 6>(sm, tmem, ntiles); break;
+      case 7: cf_score_loop<KATOMS, 7>(sm, tmem, ntiles); break;
+      case 8: cf_score_loop<KATOMS, 8>(sm, tmem, ntiles); break;
+      case 9: cf_score_loop<KATOMS, 9>(sm, tmem, ntiles); break;
+      case 10: cf_score_loop<KATOMS, 10>(sm, tmem, ntiles); break;
+      default: cf_score_loop<KATOMS, 11>(sm, tmem, ntiles); break;
+    }
+  } else {
+    // ===================== softmax warpgroups (thread == query row == TMEM lane) =====================
+    const int wg = warp >> 2;
+    const int rowi = (warp & 3) * 32 + lane;
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    if (wg == 0) {
+      tc::mbar_wait(&sm.bar_q, 0);
+      stationary_to_tmem<KATOMS>(sm.q, tlane, rowi);
+      tc::mbar_arrive(&sm.bar_a_ready);
+    }
+    float m = -INFINITY, l = 0.f, acc[DVH];
+#pragma unroll
+    for (int e = 0; e < DVH; ++e) acc[e] = 0.f;
+    uint32_t r[4][32];
+    Ring rst, rsl;
+    if (wg) { rst.next(ST); rsl.next(NS); }
+    for (int j = wg; j < ntiles; j += 2, rst.next(ST), rst.next(ST), rsl.next(NS), rsl.next(NS)) {
+      const int slot = rsl.i, st = rst.i;
+      const uint32_t tslot = tlane + COL_SLOT0 + 128 * slot;
+      tc::mbar_wait(&sm.bar_s_full[slot], rsl.ph);
+      tc::tc_fence_after();
+      tc::tmem_ld_x32(tslot + 0, r[0]);
+      tc::tmem_ld_x32(tslot + 32, r[1]);
+      tc::tmem_ld_x32(tslot + 64, r[2]);
+      tc::tmem_ld_x32(tslot + 96, r[3]);
+      tc::tmem_ld_wait();
+      tc::tc_fence_before();
+      tc::mbar_arrive(&sm.bar_slot_free[slot]);   // the scores are in registers: the slot can be refilled
+      const int nvalid = L - j * CF_BN;           // >= CF_BN for every tile but (possibly) the last
+      const uint32_t vt = smem_u32(sm.vt[st]);
+      if (dbg & 8) {                               // ablation: no math
+        l += __uint_as_float(r[0][0]);
+      } else if (dbg & 1) {                        // ablation: no MUFU (same FMA-pipe work)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { const float pq = __uint_as_float(r[c][i]) * 0.001f + m; l += pq; acc[0] = fmaf(pq, l, acc[0]); }
+      } else if (nvalid < CF_BN) fwd_cc_tile<DVH, true>(r, vt, nvalid, m, l, acc);
+      else fwd_cc_tile<DVH, false>(r, vt, nvalid, m, l, acc);
+      tc::mbar_arrive(&sm.bar_empty[st]);          // value tile consumed
+    }
+    // ---- merge the two warpgroups' partial results ----
+    if (wg == 1) {
+      sm.xch[rowi][0] = m;
+      sm.xch[rowi][1] = l;
+#pragma unroll
+      for (int e = 0; e < DVH; ++e) sm.xch[rowi][2 + e] = acc[e];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (wg == 0) {
+      const float m1 = sm.xch[rowi][0];
+      const float mm = fmaxf(m, m1);
+      const float a0 = tc::ex2f(m - mm), a1 = (m1 == -INFINITY) ? 0.f : tc::ex2f(m1 - mm);
+      const float lt = a0 * l + a1 * sm.xch[rowi][1];
+      const int qi = q0 + rowi;
+      if (qi < L) {
+        const float inv = 1.f / lt;
+        const size_t row = (size_t)bn * L + qi;
+#pragma unroll
+        for (int e = 0; e < DVH; ++e) o[row * DVH + e] = (a0 * acc[e] + a1 * sm.xch[rowi][2 + e]) * inv;
+        lse[row] = (mm + log2f(lt)) * 0.6931471805599453f;
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tc::tmem_dealloc<512>(tmem);
+}
+
+// ================================================================================================
+// backward
+// ================================================================================================
+constexpr int CB_BM = 128, CB_BN = 64, CB_STAGES = 6, CB_MAXSLOTS = 4;
+// three math warpgroups (tile j -> warpgroup j % 3): three warps per scheduler keep the MUFU pipe busy while the others sit
+// in TMEM load / store / barrier latencies;  then one TMA warp, the score-MMA issuer (+TMEM alloc) and the gradient-MMA issuer
+constexpr int CB_NWG = 3, CB_W_TMA = 4 * CB_NWG, CB_W_S = CB_W_TMA + 1, CB_W_G = CB_W_TMA + 2, CB_THREADS = 32 * (CB_W_G + 1);
+
+template <int KATOMS, int SIDE_FLOATS>
+struct __align__(1024) CbSmem {
+  bf16 stat[KATOMS][CB_BM * 64];
+  bf16 strm[CB_STAGES][KATOMS][CB_BN * 64];
+  float side[CB_STAGES][SIDE_FLOATS];          // fp32 side tile: v (dq kernel) or dO | delta (dkv kernel)
+  uint64_t bar_stat, bar_a_ready, bar_full[CB_STAGES], bar_empty[CB_STAGES];
+  uint64_t bar_s_full[CB_MAXSLOTS], bar_p_ready[CB_MAXSLOTS], bar_slot_free[CB_MAXSLOTS], bar_final;
+  uint32_t tmem_base;
+};
+
+template <class Smem>
+__device__ __forceinline__ void cb_init(Smem& sm, int warp, int lane, const CUtensorMap* m0, const CUtensorMap* m1) {
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&sm.bar_stat, 1);
+    tc::mbar_init(&sm.bar_a_ready, 128);
+    for (int s = 0; s < CB_STAGES; ++s) { tc::mbar_init(&sm.bar_full[s], 1); tc::mbar_init(&sm.bar_empty[s], 129); }
+    for (int s = 0; s < CB_MAXSLOTS; ++s) {
+      tc::mbar_init(&sm.bar_s_full[s], 1);
+      tc::mbar_init(&sm.bar_p_ready[s], 128);
+      tc::mbar_init(&sm.bar_slot_free[s], 1);
+    }
+    tc::mbar_init(&sm.bar_final, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == CB_W_TMA && lane == 0) { tc::tma_prefetch_desc(m0); tc::tma_prefetch_desc(m1); }
+  if (warp == CB_W_S) tc::tmem_alloc<512>(&sm.tmem_base);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+}
+
+template <int KATOMS, int NKS, class Smem>
+__device__ __forceinline__ void cb_score_loop(Smem& sm, uint32_t tmem, uint32_t col_slot0, int NS, int ntiles, long long* tl) {
+  constexpr uint32_t idesc_s = tc::idesc_bf16_f32(CB_BM, CB_BN);
+  constexpr uint32_t STRM_ATOM = (CB_BN * 128) >> 4, STAGE = KATOMS * STRM_ATOM;
+  const uint32_t strm_lo = tc::desc_lo_k(smem_u32(sm.strm[0][0]));
+  Ring rst, rsl;
+  for (int j = 0; j < ntiles; ++j, rst.next(CB_STAGES), rsl.next(NS)) {
+    const int st = rst.i, slot = rsl.i;
+    if (tl) tl[8 * 64 + j] = clock64();
+    tc::mbar_wait(&sm.bar_full[st], rst.ph);
+    if (tl) tl[0 * 64 + j] = clock64();
+    if (j >= NS) tc::mbar_wait(&sm.bar_slot_free[slot], rsl.ph ^ 1);
+    tc::tc_fence_after();
+    if (tl) tl[9 * 64 + j] = clock64();
+    if (tc::elect_one()) {
+      tc::issue_ts_ksteps<NKS, 0, STRM_ATOM>(tmem + col_slot0 + 64 * slot, 0u, tmem, strm_lo + st * STAGE, idesc_s);
+      tc::mma_commit(&sm.bar_s_full[slot]);
+    }
+    __syncwarp();
+    if (tl) tl[1 * 64 + j] = clock64();
+  }
+}
+// score-MMA issuer shared by both backward kernels: S'(j) -> slot j % NS as soon as the K/Q tile has landed and the
+// slot's previous gradient MMAs are done.  The k-step count is dispatched ONCE, outside the tile loop (an indirect
+// branch per tile costs hundreds of cycles on the issuing warp, which is the critical resource).
+template <int KATOMS, class Smem>
+__device__ __forceinline__ void cb_score_issuer(Smem& sm, uint32_t tmem, uint32_t col_slot0, int NS, int nks, int ntiles,
+                                                long long* tl = nullptr) {
+  tc::mbar_wait(&sm.bar_a_ready, 0);
+  tc::tc_fence_after();
+  switch (nks) {
+    case 1: cb_score_loop<KATOMS, 1>(sm, tmem, col_slot0, NS, ntiles, tl); break;
+    case 2: cb_score_loop<KATOMS, 2>(sm, tmem, col_slot0, NS, ntiles, tl); break;
+    case 3: cb_score_loop<KATOMS, 3>(sm, tmem, col_slot0, NS, ntiles, tl); break;
+    case 4: cb_score_loop<KATOMS, 4>(sm, tmem, col_slot0, NS, ntiles, tl); break;
+    case 5: cb_score_loop<KATOMS, 5>(sm, tmem, col_slot0, NS, ntiles, tl); break;
+    case 6: cb_score_loop<KATOMS, 6>(sm, tmem, col_slot0, NS, ntiles, tl); break;
+    case 7: cb_score_loop<KATOMS, 7>(sm, tmem, col_slot0, NS, ntiles, tl); break;
+    case 8: cb_score_loop<KATOMS, 8>(sm, tmem, col_slot0, NS, ntiles, tl); break;
+    case 9: cb_score_loop<KATOMS, 9>(sm, tmem, col_slot0, NS, ntiles, tl); break;
+    case 10: cb_score_loop<KATOMS, 10>(sm, tmem, col_slot0, NS, ntiles, tl); break;
+    default: cb_score_loop<KATOMS, 11>(sm, tmem, col_slot0, NS, ntiles, tl); break;
+  }
+}
+
+// one key tile of the dQa kernel: dS = 2^S' (dO.v[k] - delta) for this thread's query row, packed to bf16
+template <int DVH, bool TAIL>
+__device__ __forceinline__ void dq_cc_tile(const uint32_t (&rs)[2][32], uint32_t (&pd)[32], uint32_t vt, int nvalid,
+                                           const float (&go)[DVH], float ndelta) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float vv[4 * DVH];
+#pragma unroll
+      for (int u = 0; u < DVH; ++u) {
+        const float4 t4 = lds128(vt + ((c * 32 + i) * DVH + 4 * u) * 4);
+        vv[4 * u] = t4.x; vv[4 * u + 1] = t4.y; vv[4 * u + 2] = t4.z; vv[4 * u + 3] = t4.w;
+      }
+      float ds[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float dp = ndelta;
+#pragma unroll
+        for (int e = 0; e < DVH; ++e) dp = fmaf(go[e], vv[u * DVH + e], dp);
+        ds[u] = tc::ex2f(__uint_as_float(rs[c][i + u])) * dp;
+        if (TAIL && c * 32 + i + u >= nvalid) ds[u] = 0.f;     // zero-filled keys past L
+      }
+      pd[c * 16 + (i >> 1)] = tc::pack_bf16x2(ds[0], ds[1]);
+      pd[c * 16 + (i >> 1) + 1] = tc::pack_bf16x2(ds[2], ds[3]);
+    }
+}
+
+// one query tile of the dK/dV kernel: P^T = 2^S'^T and dS^T = P^T (dO[q].v - delta[q]) for this thread's key row
+template <int DVH, bool TAIL>
+__device__ __forceinline__ void dkv_cc_tile(const uint32_t (&rs)[2][32], uint32_t (&pp)[32], uint32_t (&pd)[32], uint32_t dot,
+                                            uint32_t dlt, int nvalid, const float (&vk)[DVH]) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float gg[4 * DVH];
+#pragma unroll
+      for (int u = 0; u < DVH; ++u) {
+        const float4 t4 = lds128(dot + ((c * 32 + i) * DVH + 4 * u) * 4);
+        gg[4 * u] = t4.x; gg[4 * u + 1] = t4.y; gg[4 * u + 2] = t4.z; gg[4 * u + 3] = t4.w;
+      }
+      const float4 dl = lds128(dlt + (c * 32 + i) * 4);
+      const float dls[4] = {dl.x, dl.y, dl.z, dl.w};
+      float p[4], ds[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float dp = -dls[u];
+#pragma unroll
+        for (int e = 0; e < DVH; ++e) dp = fmaf(gg[u * DVH + e], vk[e], dp);
+        if (TAIL && c * 32 + i + u >= nvalid) dp = 0.f;        // zero-filled queries past L
+        p[u] = tc::ex2f(__uint_as_float(rs[c][i + u]));
+        ds[u] = p[u] * dp;
+      }
+      pp[c * 16 + (i >> 1)] = tc::pack_bf16x2(p[0], p[1]);
+      pp[c * 16 + (i >> 1) + 1] = tc::pack_bf16x2(p[2], p[3]);
+      pd[c * 16 + (i >> 1)] = tc::pack_bf16x2(ds[0], ds[1]);
+      pd[c * 16 + (i >> 1) + 1] = tc::pack_bf16x2(ds[2], ds[3]);
+    }
+}
+
+// ---- query-stationary: dQa ------------------------------------------------------------------------
+// TMEM: Qa [0, 32K); slot s: S' at 32K + 64 s (dS, bf16, over its first 32 columns); dQa behind the slots.
+template <int KATOMS, int DVH>
+__global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dq_cc_kernel(
+    const __grid_constant__ CUtensorMap tm_q_stat, const __grid_constant__ CUtensorMap tm_k_strm,
+    const float* __restrict__ v, const float* __restrict__ d_o, const float* __restrict__ delta, float* __restrict__ dqa, int L,
+    int KD, int NQ, int C1, int dbg, long long* __restrict__ tl) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  typedef CbSmem<KATOMS, CB_BN * DVH> Smem;
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bn = blockIdx.y, q0 = blockIdx.x * CB_BM;
+  const int ntiles = (L + CB_BN - 1) / CB_BN;
+  const int NS = min(CB_MAXSLOTS, (512 - KATOMS * 32 - NQ) / 64);
+  const uint32_t COL_SLOT0 = KATOMS * 32, COL_DQ = COL_SLOT0 + 64 * NS;
+
+  const bool rec = tl != nullptr && blockIdx.x == 3 && blockIdx.y == 40 && lane == 0;   // a CTA of a middle wave
+#define CC_STAMP(ev, tile) do { if (rec) tl[(ev) * 64 + (tile)] = clock64(); } while (0)
+  if (warp == 0) CC_STAMP(10, 0);
+  cb_init(sm, warp, lane, &tm_q_stat, &tm_k_strm);
+  const uint32_t tmem = sm.tmem_base;
+  if (warp == 0) CC_STAMP(10, 1);
+
+  if (warp == CB_W_TMA) {
+    if (lane == 0) {
+      tc::mbar_arrive_expect_tx(&sm.bar_stat, KATOMS * CB_BM * 64 * 2);
+      for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.stat[a], &tm_q_stat, &sm.bar_stat, a * 64, q0, bn);
+      Ring rg;
+      for (int j = 0; j < ntiles; ++j, rg.next(CB_STAGES)) {
+        const int s = rg.i;
+        const int nvalid = min(CB_BN, L - j * CB_BN);
+        tc::mbar_wait(&sm.bar_empty[s], rg.ph ^ 1);
+        if ((dbg & 2) && j >= CB_STAGES) { tc::mbar_arrive(&sm.bar_full[s]); continue; }     // ablation: no global traffic
+        tc::mbar_arrive_expect_tx(&sm.bar_full[s], KATOMS * CB_BN * 64 * 2 + nvalid * DVH * 4);
+        for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.strm[s][a], &tm_k_strm, &sm.bar_full[s], a * 64, j * CB_BN, bn);
+        bulk_g2s(sm.side[s], v + ((size_t)bn * L + (size_t)j * CB_BN) * DVH, nvalid * DVH * 4, &sm.bar_full[s]);
+      }
+    }
+  } else if (warp == CB_W_S) {
+    cb_score_issuer<KATOMS>(sm, tmem, COL_SLOT0, NS, C1 >> 4, ntiles, rec ? tl : nullptr);
+  } else if (warp == CB_W_G) {
+    const uint32_t idesc_dq = tc::idesc_bf16_f32(CB_BM, NQ) | (1u << 16);
+    constexpr uint32_t STRM_ATOM = (CB_BN * 128) >> 4, STAGE = KATOMS * STRM_ATOM;
+    const uint32_t k_lo = tc::desc_lo_mn(smem_u32(sm.strm[0][0]), CB_BN * 128);
+    Ring rst, rsl;
+    for (int jj = 0; jj < ntiles; ++jj, rst.next(CB_STAGES), rsl.next(NS)) {
+      const int st = rst.i, slot = rsl.i;
+      const uint32_t tslot = tmem + COL_SLOT0 + 64 * slot;
+      tc::mbar_wait(&sm.bar_p_ready[slot], rsl.ph);
+      tc::tc_fence_after();
+      CC_STAMP(2, jj);
+      if (tc::elect_one()) {
+        const uint32_t kb = k_lo + st * STAGE;
+#pragma unroll
+        for (int ks = 0; ks < CB_BN / 16; ++ks)
+          if (!(dbg & 4) || jj == 0) tc::mma_ts(tmem + COL_DQ, tslot + ks * 8, tc::desc64(kb + ks * 128), idesc_dq, (jj > 0 || ks > 0) ? 1u : 0u);
+        tc::mma_commit(&sm.bar_empty[st]);
+        tc::mma_commit(&sm.bar_slot_free[slot]);
+        if (jj == ntiles - 1) tc::mma_commit(&sm.bar_final);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int wg = warp >> 2;
+    const int rowi = (warp & 3) * 32 + lane;
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    if (wg == 0) {
+      tc::mbar_wait(&sm.bar_stat, 0);
+      if (warp == 0) CC_STAMP(10, 2);
+      stationary_to_tmem<KATOMS>(sm.stat, tlane, rowi);
+      tc::mbar_arrive(&sm.bar_a_ready);
+      if (warp == 0) CC_STAMP(10, 3);
+    }
+    const int qi = q0 + rowi;
+    const size_t row = (size_t)bn * L + qi;
+    float go[DVH], ndelta = 0.f;
+#pragma unroll
+    for (int e = 0; e < DVH; ++e) go[e] = qi < L ? d_o[row * DVH + e] : 0.f;
+    if (qi < L) ndelta = -delta[row];
+    uint32_t rs[2][32], pd[32];
+    Ring rst, rsl;
+    for (int i = 0; i < wg; ++i) { rst.next(CB_STAGES); rsl.next(NS); }
+    for (int j = wg; j < ntiles; j += CB_NWG) {
+      const int slot = rsl.i, st = rst.i;
+      const uint32_t tslot = tlane + COL_SLOT0 + 64 * slot;
+      const int nvalid = L - j * CB_BN;
+      const bool tail = nvalid < CB_BN;
+      if ((warp & 3) == 0) CC_STAMP(3, j);
+      tc::mbar_wait(&sm.bar_s_full[slot], rsl.ph);
+      tc::tc_fence_after();
+      if ((warp & 3) == 0) CC_STAMP(4, j);
+      tc::tmem_ld_x32(tslot, rs[0]);
+      tc::tmem_ld_x32(tslot + 32, rs[1]);
+      tc::tmem_ld_wait();
+      const uint32_t vt = smem_u32(sm.side[st]);
+      if (dbg & 8) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) pd[i] = rs[0][i];
+      } else if (dbg & 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) pd[i] = tc::pack_bf16x2(__uint_as_float(rs[0][i]) * ndelta, __uint_as_float(rs[1][i]) * go[0]);
+      } else if (tail) dq_cc_tile<DVH, true>(rs, pd, vt, nvalid, go, ndelta);
+      else dq_cc_tile<DVH, false>(rs, pd, vt, nvalid, go, ndelta);
+      tc::tmem_st_x32(tslot, pd);                    // dS (bf16) over S'[0,32): all of S' is in registers
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      tc::mbar_arrive(&sm.bar_p_ready[slot]);
+      tc::mbar_arrive(&sm.bar_empty[st]);            // value tile consumed
+      if ((warp & 3) == 0) CC_STAMP(6, j);
+#pragma unroll
+      for (int i = 0; i < CB_NWG; ++i) { rst.next(CB_STAGES); rsl.next(NS); }
+    }
+    if (warp == 0) CC_STAMP(10, 4);
+    tc::mbar_wait(&sm.bar_final, 0);
+    tc::tc_fence_after();
+    if (warp == 0) CC_STAMP(10, 5);
+    for (int c0 = wg * 32; c0 < NQ; c0 += 32 * CB_NWG) {
+      tc::tmem_ld_x32(tlane + COL_DQ + c0, rs[0]);
+      tc::tmem_ld_wait();
+      if (qi < L) {
+        if ((KD & 3) == 0) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            if (c0 + e < KD)
+              *reinterpret_cast<float4*>(dqa + row * KD + c0 + e) =
+                  make_float4(__uint_as_float(rs[0][e]), __uint_as_float(rs[0][e + 1]), __uint_as_float(rs[0][e + 2]), __uint_as_float(rs[0][e + 3]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (c0 + e < KD) dqa[row * KD + c0 + e] = __uint_as_float(rs[0][e]);
+        }
+      }
+    }
+  }
+  if (warp == 0) CC_STAMP(10, 6);
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) CC_STAMP(10, 7);
+#undef CC_STAMP
+  if (warp == CB_W_S) tc::tmem_dealloc<512>(tmem);
+}
+
+// ---- key-stationary: dK, dV ------------------------------------------------------------------------
+// TMEM: Ka [0, 32K); slot s: S'^T at 32K + 64 s (P^T over columns [0,32), dS^T over [32,64)); dV (16), dK (32) behind the slots.
+template <int KATOMS, int DVH>
+__global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
+    const __grid_constant__ CUtensorMap tm_k_stat, const __grid_constant__ CUtensorMap tm_q_strm,
+    const float* __restrict__ v, const float* __restrict__ d_o, const float* __restrict__ delta, float* __restrict__ dk,
+    float* __restrict__ dv, bf16* __restrict__ dqkvh, int KPq, int nh, int L, int dkh, int C1) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  typedef CbSmem<KATOMS, CB_BN * (DVH + 1)> Smem;
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bn = blockIdx.y, k0 = blockIdx.x * CB_BM;
+  const int ntiles = (L + CB_BN - 1) / CB_BN;
+  const int NS = min(CB_MAXSLOTS, (512 - KATOMS * 32 - 48) / 64);
+  const uint32_t COL_SLOT0 = KATOMS * 32, COL_DV = COL_SLOT0 + 64 * NS, COL_DK = COL_DV + 16;
+
+  cb_init(sm, warp, lane, &tm_k_stat, &tm_q_strm);
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == CB_W_TMA) {
+    if (lane == 0) {
+      tc::mbar_arrive_expect_tx(&sm.bar_stat, KATOMS * CB_BM * 64 * 2);
+      for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.stat[a], &tm_k_stat, &sm.bar_stat, a * 64, k0, bn);
+      Ring rg;
+      for (int j = 0; j < ntiles; ++j, rg.next(CB_STAGES)) {
+        const int s = rg.i;
+        const int nvalid = min(CB_BN, L - j * CB_BN);
+        const size_t r0 = (size_t)bn * L + (size_t)j * CB_BN;
+        tc::mbar_wait(&sm.bar_empty[s], rg.ph ^ 1);
+        tc::mbar_arrive_expect_tx(&sm.bar_full[s], KATOMS * CB_BN * 64 * 2 + nvalid * (DVH + 1) * 4);
+        for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.strm[s][a], &tm_q_strm, &sm.bar_full[s], a * 64, j * CB_BN, bn);
+        bulk_g2s(sm.side[s], d_o + r0 * DVH, nvalid * DVH * 4, &sm.bar_full[s]);
+        bulk_g2s(sm.side[s] + CB_BN * DVH, delta + r0, nvalid * 4, &sm.bar_full[s]);
+      }
+    }
+  } else if (warp == CB_W_S) {
+    cb_score_issuer<KATOMS>(sm, tmem, COL_SLOT0, NS, C1 >> 4, ntiles);
+  } else if (warp == CB_W_G) {
+    constexpr uint32_t idesc_dv = tc::idesc_bf16_f32(CB_BM, 16) | (1u << 16);
+    constexpr uint32_t idesc_dk = tc::idesc_bf16_f32(CB_BM, 32) | (1u << 16);
+    constexpr uint32_t STRM_ATOM = (CB_BN * 128) >> 4, STAGE = KATOMS * STRM_ATOM;
+    const uint32_t v_lo = tc::desc_lo_mn(smem_u32(sm.strm[0][C1 >> 6]) + (C1 & 63) * 2, CB_BN * 128);
+    const uint32_t q_lo = tc::desc_lo_mn(smem_u32(sm.strm[0][0]), CB_BN * 128);
+    Ring rst, rsl;
+    for (int jj = 0; jj < ntiles; ++jj, rst.next(CB_STAGES), rsl.next(NS)) {
+      const int st = rst.i, slot = rsl.i;
+      const uint32_t tslot = tmem + COL_SLOT0 + 64 * slot;
+      tc::mbar_wait(&sm.bar_p_ready[slot], rsl.ph);
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+        const uint32_t vb = v_lo + st * STAGE, qb = q_lo + st * STAGE;
+#pragma unroll
+        for (int ks = 0; ks < CB_BN / 16; ++ks) {
+          tc::mma_ts(tmem + COL_DV, tslot + ks * 8, tc::desc64(vb + ks * 128), idesc_dv, (jj > 0 || ks > 0) ? 1u : 0u);
+          tc::mma_ts(tmem + COL_DK, tslot + 32 + ks * 8, tc::desc64(qb + ks * 128), idesc_dk, (jj > 0 || ks > 0) ? 1u : 0u);
+        }
+        tc::mma_commit(&sm.bar_empty[st]);
+        tc::mma_commit(&sm.bar_slot_free[slot]);
+        if (jj == ntiles - 1) tc::mma_commit(&sm.bar_final);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int wg = warp >> 2;
+    const int rowi = (warp & 3) * 32 + lane;
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    if (wg == 0) {
+      tc::mbar_wait(&sm.bar_stat, 0);
+      stationary_to_tmem<KATOMS>(sm.stat, tlane, rowi);
+      tc::mbar_arrive(&sm.bar_a_ready);
+    }
+    const int kj = k0 + rowi;
+    const size_t row = (size_t)bn * L + kj;
+    float vk[DVH];
+#pragma unroll
+    for (int e = 0; e < DVH; ++e) vk[e] = kj < L ? v[row * DVH + e] : 0.f;
+    uint32_t rs[2][32], pp[32], pd[32];
+    Ring rst, rsl;
+    for (int i = 0; i < wg; ++i) { rst.next(CB_STAGES); rsl.next(NS); }
+    for (int j = wg; j < ntiles; j += CB_NWG) {
+      const int slot = rsl.i, st = rst.i;
+      const uint32_t tslot = tlane + COL_SLOT0 + 64 * slot;
+      const int nvalid = L - j * CB_BN;
+      const bool tail = nvalid < CB_BN;
+      tc::mbar_wait(&sm.bar_s_full[slot], rsl.ph);
+      tc::tc_fence_after();
+      tc::tmem_ld_x32(tslot, rs[0]);
+      tc::tmem_ld_x32(tslot + 32, rs[1]);
+      tc::tmem_ld_wait();
+      const uint32_t dot = smem_u32(sm.side[st]), dlt = dot + CB_BN * DVH * 4;
+      if (tail) dkv_cc_tile<DVH, true>(rs, pp, pd, dot, dlt, nvalid, vk);
+      else dkv_cc_tile<DVH, false>(rs, pp, pd, dot, dlt, nvalid, vk);
+      tc::tmem_st_x32(tslot, pp);                    // P^T over S'^T[0,32), dS^T over [32,64): all of S'^T is in registers
+      tc::tmem_st_x32(tslot + 32, pd);
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      tc::mbar_arrive(&sm.bar_p_ready[slot]);
+      tc::mbar_arrive(&sm.bar_empty[st]);
+#pragma unroll
+      for (int i = 0; i < CB_NWG; ++i) { rst.next(CB_STAGES); rsl.next(NS); }
+    }
+    tc::mbar_wait(&sm.bar_final, 0);
+    tc::tc_fence_after();
+    const float LN2 = 0.6931471805599453f;               // Qa carries log2(e)*q
+    const int b = bn / nh, n = bn - b * nh;
+    bf16* prow = dqkvh ? dqkvh + ((size_t)b * L + kj) * KPq : nullptr;
+    if (wg == 0) {
+      tc::tmem_ld_x32(tlane + COL_DK, rs[0]);
+      tc::tmem_ld_wait();
+      if (kj < L) {
+        if (prow) {
+          bf16* dst = prow + nh * dkh + n * dkh;
+          if (((dkh | KPq) & 3) == 0) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+              if (e < dkh) {
+                uint2 w;
+                w.x = tc::pack_bf16x2(__uint_as_float(rs[0][e]) * LN2, __uint_as_float(rs[0][e + 1]) * LN2);
+                w.y = tc::pack_bf16x2(__uint_as_float(rs[0][e + 2]) * LN2, __uint_as_float(rs[0][e + 3]) * LN2);
+                *reinterpret_cast<uint2*>(dst + e) = w;
+              }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (e < dkh) dst[e] = __float2bfloat16(__uint_as_float(rs[0][e]) * LN2);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (e < dkh) dk[row * dkh + e] = __uint_as_float(rs[0][e]) * LN2;
+        }
+      }
+    } else if (wg == 1) {
+      uint32_t rv[16];
+      tc::tmem_ld_x16(tlane + COL_DV, rv);
+      tc::tmem_ld_wait();
+      if (kj < L) {
+        if (prow) {
+          bf16* dst = prow + 2 * nh * dkh + n * DVH;
+#pragma unroll
+          for (int e = 0; e < DVH; ++e) dst[e] = __float2bfloat16(__uint_as_float(rv[e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < DVH; ++e) dv[row * DVH + e] = __uint_as_float(rv[e]);
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == CB_W_S) tc::tmem_dealloc<512>(tmem);
+}
+
+int make_aug_map(const Dims& d, const void* t, int KP, uint32_t box_rows, CUtensorMap* out) {
+  const uint64_t dims[3] = {(uint64_t)KP, (uint64_t)d.L, (uint64_t)d.BN};
+  const uint64_t strides[2] = {(uint64_t)KP * 2, (uint64_t)d.L * KP * 2};
+  const uint32_t box[3] = {64, box_rows, 1};
+  return make_tmap_bf16(out, t, 3, dims, strides, box, nullptr);
+}
+
+template <int KATOMS, int DVH>
+int launch_fwd_cc(const Dims& d, const AugLayout& a, const void* qa, const void* ka, const float* v, float* o, float* lse,
+                  cudaStream_t st) {
+  CUtensorMap tq, tk;
+  AACONV_TRY(make_aug_map(d, qa, a.KP, CF_BM, &tq));
+  AACONV_TRY(make_aug_map(d, ka, a.KP, CF_BN, &tk));
+  const size_t smem = sizeof(CfSmem<KATOMS, DVH>) + 1024;
+  auto kern = attn_fwd_cc_kernel<KATOMS, DVH>;
+  AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<dim3(cdiv(d.L, CF_BM), d.BN), CF_THREADS, smem, st>>>(tq, tk, v, o, lse, d.L, a.C1, g_attn_dbg_mode);
+  AACONV_LAUNCH_OK("attn_fwd_cc");
+  return 0;
+}
+
+template <int KATOMS, int DVH>
+int launch_bwd_cc(const Dims& d, const AugLayout& a, const void* qa, const void* ka, const float* v, const float* d_o,
+                  const float* delta, float* dqa, float* dk, float* dv, void* dqkvh, int KPq, cudaStream_t st) {
+  CUtensorMap tq_stat, tk_strm, tk_stat, tq_strm;
+  AACONV_TRY(make_aug_map(d, qa, a.KP, CB_BM, &tq_stat));
+  AACONV_TRY(make_aug_map(d, ka, a.KP, CB_BN, &tk_strm));
+  AACONV_TRY(make_aug_map(d, ka, a.KP, CB_BM, &tk_stat));
+  AACONV_TRY(make_aug_map(d, qa, a.KP, CB_BN, &tq_strm));
+  dim3 grid(cdiv(d.L, CB_BM), d.BN);
+  {
+    const size_t smem = sizeof(CbSmem<KATOMS, CB_BN * (DVH + 1)>) + 1024;
+    auto kern = attn_bwd_dkv_cc_kernel<KATOMS, DVH>;
+    AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, CB_THREADS, smem, st>>>(tk_stat, tq_strm, v, d_o, delta, dk, dv, static_cast<bf16*>(dqkvh), KPq, d.nh, d.L, d.dkh, a.C1);
+    AACONV_LAUNCH_OK("attn_bwd_dkv_cc");
+  }
+  {
+    const size_t smem = sizeof(CbSmem<KATOMS, CB_BN * DVH>) + 1024;
+    auto kern = attn_bwd_dq_cc_kernel<KATOMS, DVH>;
+    AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, CB_THREADS, smem, st>>>(tq_stat, tk_strm, v, d_o, delta, dqa, d.L, a.KD, a.NQ, a.C1, g_attn_dbg_mode, g_attn_dbg);
+    AACONV_LAUNCH_OK("attn_bwd_dq_cc");
+  }
+  return 0;
+}
+
+}  // namespace
+
+// value width 1..2 and 16-byte-aligned fp32 side tiles (L % 4 == 0)
+int cc_attn_supported(const Dims& d) {
+  if (aug_supported(d)) return AACONV_E_UNSUPPORTED;
+  if (d.dvh < 1 || d.dvh > 2 || (d.L & 3)) return AACONV_E_UNSUPPORTED;
+  return 0;
+}
+
+int cc_attn_fwd(const Dims& d, const void* qa, const void* ka, const float* v, float* o, float* lse, cudaStream_t st) {
+  AACONV_TRY(cc_attn_supported(d));
+  const AugLayout a = aug_layout(d);
+  const int K = a.KP / 64;
+  if (d.dvh == 1) {
+    if (K == 1) return launch_fwd_cc<1, 1>(d, a, qa, ka, v, o, lse, st);
+    if (K == 2) return launch_fwd_cc<2, 1>(d, a, qa, ka, v, o, lse, st);
+    return launch_fwd_cc<3, 1>(d, a, qa, ka, v, o, lse, st);
+  }
+  if (K == 1) return launch_fwd_cc<1, 2>(d, a, qa, ka, v, o, lse, st);
+  if (K == 2) return launch_fwd_cc<2, 2>(d, a, qa, ka, v, o, lse, st);
+  return launch_fwd_cc<3, 2>(d, a, qa, ka, v, o, lse, st);
+}
+
+int cc_attn_bwd(const Dims& d, const void* qa, const void* ka, const float* v, const float* d_o, const float* delta, float* dqa,
+                float* dk, float* dv, void* dqkvh, int KPq, cudaStream_t st) {
+  AACONV_TRY(cc_attn_supported(d));
+  const AugLayout a = aug_layout(d);
+  const int K = a.KP / 64;
+  if (d.dvh == 1) {
+    if (K == 1) return launch_bwd_cc<1, 1>(d, a, qa, ka, v, d_o, delta, dqa, dk, dv, dqkvh, KPq, st);
+    if (K == 2) return launch_bwd_cc<2, 1>(d, a, qa, ka, v, d_o, delta, dqa, dk, dv, dqkvh, KPq, st);
+    return launch_bwd_cc<3, 1>(d, a, qa, ka, v, d_o, delta, dqa, dk, dv, dqkvh, KPq, st);
+  }
+  if (K == 1) return launch_bwd_cc<1, 2>(d, a, qa, ka, v, d_o, delta, dqa, dk, dv, dqkvh, KPq, st);
+  if (K == 2) return launch_bwd_cc<2, 2>(d, a, qa, ka, v, d_o, delta, dqa, dk, dv, dqkvh, KPq, st);
+  return launch_bwd_cc<3, 2>(d, a, qa, ka, v, d_o, delta, dqa, dk, dv, dqkvh, KPq, st);
+}
+
+}  // namespace aaconv

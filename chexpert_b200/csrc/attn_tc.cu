@@ -22,7 +22,7 @@ typedef __nv_bfloat16 bf16;
 
 constexpr int FA_BM = 128;       // queries per CTA (TMEM lanes)
 constexpr int FA_BN = 128;       // keys per tile
-constexpr int FA_STAGES = 4;     // K smem stages (>= slots + 1)
+template <int KATOMS> struct FaStages { static constexpr int value = KATOMS >= 3 ? 3 : 4; };   // K smem stages (>= slots; 48 KB each at KATOMS = 3)
 constexpr int FA_SLOTS = 3;      // TMEM score slots: the MMA warp runs up to two tiles ahead of the softmax warpgroups
 constexpr int FA_THREADS = 352;  // warps 0-3 softmax WG0, 4-7 softmax WG1, warp 8 TMA, warp 9 score MMAs (+TMEM alloc), warp 10 P.V MMAs
 constexpr uint32_t FA_SLOT = 128;   // TMEM: Qa (bf16) [0, 32*KATOMS); slot s: S at 32*KATOMS + 128*s (P, bf16, aliases its first 64 columns);
@@ -31,6 +31,7 @@ constexpr float FA_RESCALE_THRESHOLD = 8.f;                          // log2 uni
 
 template <int KATOMS>
 struct __align__(1024) FwdSmem {
+  static constexpr int FA_STAGES = FaStages<KATOMS>::value;
   bf16 q[KATOMS][FA_BM * 64];                 // K-major, 128 B rows, 128B swizzle (one atom = 64 k-elements)
   bf16 k[FA_STAGES][KATOMS][FA_BN * 64];
   float xch[FA_BM][18];                       // WG1 -> WG0 hand-over of (m, O[0..16))
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fwd_tc_kernel(
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bn = blockIdx.y, q0 = blockIdx.x * FA_BM;
   const int ntiles = (L + FA_BN - 1) / FA_BN;
+  constexpr int FA_STAGES = FaStages<KATOMS>::value;
 
   if (threadIdx.x == 0) {
     tc::mbar_init(&sm.bar_q, 1);

@@ -253,8 +253,8 @@ __global__ void __launch_bounds__(256) aug_build_fwd_kernel(const BuildP p) {
 // backward patch of Qa
 // ------------------------------------------------------------------------------------------------
 __global__ void aug_patch_bwd_kernel(const float* __restrict__ lse, const float* __restrict__ d_o,
-                                     const float* __restrict__ o, bf16* __restrict__ qa, size_t rows, int dvh, int KD,
-                                     int C1, int KP) {
+                                     const float* __restrict__ o, bf16* __restrict__ qa, float* __restrict__ delta_out,
+                                     size_t rows, int dvh, int KD, int C1, int KP) {
   const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
   bf16* dst = qa + row * KP;
@@ -271,6 +271,7 @@ __global__ void aug_patch_bwd_kernel(const float* __restrict__ lse, const float*
   split_bf16(-delta, hi, lo);
   dst[C1 + dvh] = hi;
   dst[C1 + dvh + 1] = lo;
+  delta_out[row] = delta;
 }
 }  // namespace
 
@@ -306,11 +307,11 @@ int aug_build_fwd(const Dims& d, const float* q, const float* k, const float* v,
   return 0;
 }
 
-int aug_patch_bwd(const Dims& d, const float* lse, const float* d_o, const float* o, void* qa, cudaStream_t st) {
+int aug_patch_bwd(const Dims& d, const float* lse, const float* d_o, const float* o, void* qa, float* delta, cudaStream_t st) {
   const AugLayout a = aug_layout(d);
   const size_t rows = (size_t)d.BN * d.L;
   const unsigned grid = (unsigned)((rows + 255) / 256);
-  aug_patch_bwd_kernel<<<grid, 256, 0, st>>>(lse, d_o, o, static_cast<bf16*>(qa), rows, d.dvh, a.KD, a.C1, a.KP);
+  aug_patch_bwd_kernel<<<grid, 256, 0, st>>>(lse, d_o, o, static_cast<bf16*>(qa), delta, rows, d.dvh, a.KD, a.C1, a.KP);
   AACONV_LAUNCH_OK("aug_patch_bwd");
   return 0;
 }

@@ -9,7 +9,7 @@ namespace aaconv {
 
 namespace {
 struct Scratch {
-  float *d_o, *dq, *dk, *dv, *partial, *relpart, *dqa, *rw, *rh, *o_tmp, *lse_tmp;
+  float *d_o, *delta, *dq, *dk, *dv, *partial, *relpart, *dqa, *rw, *rh, *o_tmp, *lse_tmp;
   TcGemmBufs gemm;
   bool gemm_ok;
   size_t bytes;
@@ -18,6 +18,7 @@ struct Scratch {
     const size_t rows = (size_t)d.BN * d.L;
     const AugLayout a = aug_layout(d);
     d_o = c.take<float>(rows * d.dvh);
+    delta = c.take<float>(rows);
     dq = c.take<float>(rows * d.dkh);
     dk = c.take<float>(rows * d.dkh);
     dv = c.take<float>(rows * d.dvh);
@@ -83,7 +84,8 @@ int bf16_forward(const Dims& d, const float* x, const aaconv_params* p, float* y
     AACONV_TRY(f32_qkv_fwd(d, x, p->qkv_w, q, k, v, st));
   }
   AACONV_TRY(aug_build_fwd(d, q, k, v, p->key_rel_w, p->key_rel_h, sa.qa, sa.ka, st));
-  AACONV_TRY(tc_attn_fwd(d, sa.qa, sa.ka, o, lse, st));
+  if (cc_attn_supported(d) == 0) AACONV_TRY(cc_attn_fwd(d, sa.qa, sa.ka, v, o, lse, st));
+  else AACONV_TRY(tc_attn_fwd(d, sa.qa, sa.ka, o, lse, st));
   if (weights) {   // visualise path only: exact fp32 map (own fp32 statistics), independent of the bf16 kernel
     AACONV_TRY(f32_rel_fwd(d, q, p->key_rel_w, p->key_rel_h, w.rw, w.rh, st));
     AACONV_TRY(f32_attn_fwd(d, q, k, v, w.rw, w.rh, w.o_tmp, w.lse_tmp, st));
@@ -107,12 +109,15 @@ int bf16_backward(const Dims& d, const float* x, const aaconv_params* p, const f
   SavedAug sa(d, saved);
   // the backward-only columns of Qa (-lse, dO, -delta) are filled in place; idempotent, so a retained graph may
   // run backward again
-  AACONV_TRY(aug_patch_bwd(d, lse, w.d_o, o, sa.qa, st));
+  AACONV_TRY(aug_patch_bwd(d, lse, w.d_o, o, sa.qa, w.delta, st));
   // fast path: the attention-backward kernels write dq*scale, dk, dv as bf16 straight into the packed (B*L, KPq)
   // operand of the projection dgrad/wgrad GEMMs; its padding columns must be finite (they meet zero weights)
   const bool direct = w.gemm_ok && rel_bwd_supported(d) == 0 && tc_wgrad_supported(d) == 0;
   if (direct) AACONV_CUDA_OK(cudaMemsetAsync(w.gemm.dqkvh, 0, sizeof(uint16_t) * (size_t)d.B * d.L * w.gemm.KPq, st));
-  AACONV_TRY(tc_attn_bwd(d, sa.qa, sa.ka, w.dqa, w.dk, w.dv, direct ? w.gemm.dqkvh : nullptr, w.gemm.KPq, st));
+  if (cc_attn_supported(d) == 0)
+    AACONV_TRY(cc_attn_bwd(d, sa.qa, sa.ka, v, w.d_o, w.delta, w.dqa, w.dk, w.dv, direct ? w.gemm.dqkvh : nullptr, w.gemm.KPq, st));
+  else
+    AACONV_TRY(tc_attn_bwd(d, sa.qa, sa.ka, w.dqa, w.dk, w.dv, direct ? w.gemm.dqkvh : nullptr, w.gemm.KPq, st));
   if (direct) {
     AACONV_TRY(rel_bwd(d, w.dqa, q, p->key_rel_w, p->key_rel_h, nullptr, w.gemm.dqkvh, w.gemm.KPq, g->key_rel_w, g->key_rel_h,
                        w.relpart, st));

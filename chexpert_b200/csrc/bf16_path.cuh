@@ -18,7 +18,7 @@ int aug_supported(const Dims& d);
 // aug_ops.cu
 int aug_build_fwd(const Dims& d, const float* q, const float* k, const float* v, const float* krw, const float* krh,
                   void* qa, void* ka, cudaStream_t st);
-int aug_patch_bwd(const Dims& d, const float* lse, const float* d_o, const float* o, void* qa, cudaStream_t st);
+int aug_patch_bwd(const Dims& d, const float* lse, const float* d_o, const float* o, void* qa, float* delta, cudaStream_t st);
 int rel_bwd_supported(const Dims& d);
 size_t rel_bwd_partial_floats(const Dims& d);
 int rel_bwd(const Dims& d, const float* dqa, const float* q, const float* krw, const float* krh, float* dq, void* dqkvh,
@@ -27,6 +27,12 @@ int rel_bwd(const Dims& d, const float* dqa, const float* q, const float* krw, c
 int tc_attn_bwd(const Dims& d, const void* qa, const void* ka, float* dqa, float* dk, float* dv, void* dqkvh, int KPq,
                 cudaStream_t st);
 int aug_bwd_dq(const Dims& d, const float* dqa, const float* krw, const float* krh, float* dq, cudaStream_t st);
+
+// attn_cc.cu: value width <= 2 -- value terms on the CUDA cores, score/gradient contractions on tcgen05
+int cc_attn_supported(const Dims& d);
+int cc_attn_fwd(const Dims& d, const void* qa, const void* ka, const float* v, float* o, float* lse, cudaStream_t st);
+int cc_attn_bwd(const Dims& d, const void* qa, const void* ka, const float* v, const float* d_o, const float* delta, float* dqa,
+                float* dk, float* dv, void* dqkvh, int KPq, cudaStream_t st);
 
 // attn_tc.cu (forward)
 int tc_attn_supported(const Dims& d);

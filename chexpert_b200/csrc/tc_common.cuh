@@ -62,6 +62,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > AACONV_MBAR_SPIN_LIMIT) mbar_timeout(smem_u32(bar), parity);
   }
 }
+// Same, for waiters that are not on the critical path (math warpgroups, TMA producer): back off between polls so that
+// many spinning warps do not crowd the barrier unit the MMA-issuing warps depend on.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(40);
+    if (++spins > (AACONV_MBAR_SPIN_LIMIT >> 4)) mbar_timeout(smem_u32(bar), parity);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // TMA

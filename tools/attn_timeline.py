@@ -21,6 +21,8 @@ x = torch.relu(torch.randn(16, cin, hin, hin, device='cuda')).requires_grad_(Tru
 dy = torch.randn(16, cout, H, H, device='cuda')
 buf = torch.zeros(12 * 64, dtype=torch.int64, device='cuda')
 lib = _lib.load()
+if len(sys.argv) > 1:
+    lib.aaconv_debug_set_mode(int(sys.argv[1]))
 for it in range(3):
     m.zero_grad(set_to_none=True)
     x.grad = None
@@ -32,9 +34,9 @@ torch.cuda.synchronize()
 lib.aaconv_debug_set_timeline(None)
 t = buf.cpu().reshape(12, 64)
 t0 = int(t[t > 0].min())
-names = ['mma:top', 'mma:K landed', 'mma:S issued', 'mma:p_ready', 'mma:G issued', 'wg:wait S', 'wg:S ready', 'wg:ld done', 'wg:arrive']
-order = [8, 0, 1, 2, 9, 3, 4, 5, 6]
+names = ['S:top', 'S:K landed', 'S:slot free', 'S:issued', 'G:p_ready', 'wg:wait S', 'wg:S ready', 'wg:arrive']
+order = [8, 0, 9, 1, 2, 3, 4, 6]
 print('tile ' + ' '.join(f'{n:>13s}' for n in names))
 for j in range(26):
     print(f'{j:4d} ' + ' '.join(f'{(int(t[e, j]) - t0) if t[e, j] > 0 else -1:13d}' for e in order))
-print('epilogue [wg0 loop end, wg1 loop end, wg0 final, wg1 final, wg0 stored, wg1 stored]:', [int(v) - t0 for v in t[7, :6]])
+print('CTA [entry, init done, stat landed, A in TMEM, loop end, final seen, stores done, after sync]:', [int(v) - t0 for v in t[10, :8]])
