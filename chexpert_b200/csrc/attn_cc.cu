@@ -64,21 +64,26 @@ __device__ __forceinline__ void stationary_to_tmem(const bf16 (*stat)[128 * 64],
   tc::tc_fence_before();
 }
 
-// one key tile of the forward softmax: scores of this thread's query row in r (log2 units), fp32 values in shared memory
+// 64 keys of the forward softmax: scores of this thread's query row in r (log2 units), fp32 values in shared memory.
+// Online softmax with lazy rescale: the reference maximum m only moves when the tile maximum exceeds it by 2^8.
 template <int DVH, bool TAIL>
-__device__ __forceinline__ void fwd_cc_tile(uint32_t (&r)[4][32], uint32_t vt, int nvalid, float& m, float& l, float (&acc)[DVH]) {
+__device__ __forceinline__ void fwd_cc_half(uint32_t (&r)[2][32], uint32_t vt, int nvalid, float& m, float& l, float (&acc)[DVH]) {
   if (TAIL) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < 2; ++c)
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         if (c * 32 + i >= nvalid) r[c][i] = 0xff800000u;   // zero-filled keys past L: logit -> -inf
   }
-  float mt = -INFINITY;
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
 #pragma unroll
-  for (int c = 0; c < 4; ++c)
+  for (int c = 0; c < 2; ++c)
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) mt = fmaxf(mt, fmaxf(__uint_as_float(r[c][i]), __uint_as_float(r[c][i + 1])));
+    for (int i = 0; i < 32; i += 8) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) mx[u] = fmaxf(mx[u], fmaxf(__uint_as_float(r[c][i + 2 * u]), __uint_as_float(r[c][i + 2 * u + 1])));
+    }
+  const float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
   if (mt > m + 8.f) {                          // lazy rescale: exponentials stay below 2^8
     const float m_new = fmaxf(m, mt);
     const float alpha = tc::ex2f(m - m_new);   // 0 on the first tile (m = -inf)
@@ -88,8 +93,9 @@ __device__ __forceinline__ void fwd_cc_tile(uint32_t (&r)[4][32], uint32_t vt, i
     m = m_new;
   }
   const float mneg = -m;
+  float l2 = 0.f;
 #pragma unroll
-  for (int c = 0; c < 4; ++c)
+  for (int c = 0; c < 2; ++c)
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       float vv[4 * DVH];
@@ -101,7 +107,7 @@ __device__ __forceinline__ void fwd_cc_tile(uint32_t (&r)[4][32], uint32_t vt, i
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const float p = tc::ex2f(__uint_as_float(r[c][i + u]) + mneg);
-        l += p;
+        if (u & 1) l2 += p; else l += p;
 #pragma unroll
         for (int e = 0; e < DVH; ++e) {
           const float val = (TAIL && c * 32 + i + u >= nvalid) ? 0.f : vv[u * DVH + e];
@@ -109,12 +115,15 @@ __device__ __forceinline__ void fwd_cc_tile(uint32_t (&r)[4][32], uint32_t vt, i
         }
       }
     }
+  l += l2;
 }
 
 // ================================================================================================
 // forward
 // ================================================================================================
-constexpr int CF_BM = 128, CF_BN = 128, CF_SLOTS = 3, CF_THREADS = 320;
+constexpr int CF_BM = 128, CF_BN = 128, CF_SLOTS = 3;
+// three softmax warpgroups (tile j -> warpgroup j % 3), one TMA warp, one score-MMA issuer (+TMEM alloc)
+constexpr int CF_NWG = 3, CF_W_TMA = 4 * CF_NWG, CF_W_S = CF_W_TMA + 1, CF_THREADS = 32 * (CF_W_S + 1);
 template <int KATOMS> struct CfStages { static constexpr int value = KATOMS >= 3 ? 3 : 4; };
 
 template <int KATOMS, int DVH>
@@ -123,7 +132,7 @@ struct __align__(1024) CfSmem {
   bf16 q[KATOMS][CF_BM * 64];
   bf16 k[ST][KATOMS][CF_BN * 64];
   float vt[ST][CF_BN * DVH];                  // fp32 values of the key tile
-  float xch[CF_BM][4];                        // WG1 -> WG0 hand-over of (m, l, o[0..DVH))
+  float xch[CF_NWG - 1][CF_BM][4];            // WG1.. -> WG0 hand-over of (m, l, o[0..DVH))
   uint64_t bar_q, bar_a_ready, bar_full[ST], bar_empty[ST], bar_s_full[CF_SLOTS], bar_slot_free[CF_SLOTS];
   uint32_t tmem_base;
 };
@@ -170,14 +179,14 @@ __global__ void __launch_bounds__(CF_THREADS, 1) attn_fwd_cc_kernel(
     for (int s = 0; s < NS; ++s) { tc::mbar_init(&sm.bar_s_full[s], 1); tc::mbar_init(&sm.bar_slot_free[s], 128); }
     tc::fence_barrier_init();
   }
-  if (warp == 8 && lane == 0) { tc::tma_prefetch_desc(&tm_q); tc::tma_prefetch_desc(&tm_k); }
-  if (warp == 9) tc::tmem_alloc<512>(&sm.tmem_base);
+  if (warp == CF_W_TMA && lane == 0) { tc::tma_prefetch_desc(&tm_q); tc::tma_prefetch_desc(&tm_k); }
+  if (warp == CF_W_S) tc::tmem_alloc<512>(&sm.tmem_base);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
-  if (warp == 8) {
+  if (warp == CF_W_TMA) {
     if (lane == 0) {
       tc::mbar_arrive_expect_tx(&sm.bar_q, KATOMS * CF_BM * 64 * 2);
       for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.q[a], &tm_q, &sm.bar_q, a * 64, q0, bn);
@@ -191,7 +200,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) attn_fwd_cc_kernel(
         bulk_g2s(sm.vt[s], v + ((size_t)bn * L + (size_t)j * CF_BN) * DVH, nvalid * DVH * 4, &sm.bar_full[s]);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == CF_W_S) {
     const int nks = C1 >> 4;
     tc::mbar_wait(&sm.bar_a_ready, 0);
     tc::tc_fence_after();
@@ -221,60 +230,72 @@ __global__ void __launch_bounds__(CF_THREADS, 1) attn_fwd_cc_kernel(
     float m = -INFINITY, l = 0.f, acc[DVH];
 #pragma unroll
     for (int e = 0; e < DVH; ++e) acc[e] = 0.f;
-    uint32_t r[4][32];
+    uint32_t r[2][32];
     Ring rst, rsl;
-    if (wg) { rst.next(ST); rsl.next(NS); }
-    for (int j = wg; j < ntiles; j += 2, rst.next(ST), rst.next(ST), rsl.next(NS), rsl.next(NS)) {
+    for (int i = 0; i < wg; ++i) { rst.next(ST); rsl.next(NS); }
+    for (int j = wg; j < ntiles; j += CF_NWG) {
       const int slot = rsl.i, st = rst.i;
       const uint32_t tslot = tlane + COL_SLOT0 + 128 * slot;
+      const int nvalid = L - j * CF_BN;           // >= CF_BN for every tile but (possibly) the last
+      const uint32_t vt = smem_u32(sm.vt[st]);
       tc::mbar_wait(&sm.bar_s_full[slot], rsl.ph);
       tc::tc_fence_after();
       tc::tmem_ld_x32(tslot + 0, r[0]);
       tc::tmem_ld_x32(tslot + 32, r[1]);
-      tc::tmem_ld_x32(tslot + 64, r[2]);
-      tc::tmem_ld_x32(tslot + 96, r[3]);
+      tc::tmem_ld_wait();
+      if (dbg & 8) l += __uint_as_float(r[0][0]);
+      else if (nvalid < 64) fwd_cc_half<DVH, true>(r, vt, nvalid, m, l, acc);
+      else fwd_cc_half<DVH, false>(r, vt, nvalid, m, l, acc);
+      tc::tmem_ld_x32(tslot + 64, r[0]);
+      tc::tmem_ld_x32(tslot + 96, r[1]);
       tc::tmem_ld_wait();
       tc::tc_fence_before();
-      tc::mbar_arrive(&sm.bar_slot_free[slot]);   // the scores are in registers: the slot can be refilled
-      const int nvalid = L - j * CF_BN;           // >= CF_BN for every tile but (possibly) the last
-      const uint32_t vt = smem_u32(sm.vt[st]);
-      if (dbg & 8) {                               // ablation: no math
-        l += __uint_as_float(r[0][0]);
-      } else if (dbg & 1) {                        // ablation: no MUFU (same FMA-pipe work)
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) { const float pq = __uint_as_float(r[c][i]) * 0.001f + m; l += pq; acc[0] = fmaf(pq, l, acc[0]); }
-      } else if (nvalid < CF_BN) fwd_cc_tile<DVH, true>(r, vt, nvalid, m, l, acc);
-      else fwd_cc_tile<DVH, false>(r, vt, nvalid, m, l, acc);
+      tc::mbar_arrive(&sm.bar_slot_free[slot]);   // all scores of the tile have been read: the slot can be refilled
+      if (dbg & 8) l += __uint_as_float(r[0][0]);
+      else if (nvalid < CF_BN) { if (nvalid > 64) fwd_cc_half<DVH, true>(r, vt + 64 * DVH * 4, nvalid - 64, m, l, acc); }
+      else fwd_cc_half<DVH, false>(r, vt + 64 * DVH * 4, nvalid - 64, m, l, acc);
       tc::mbar_arrive(&sm.bar_empty[st]);          // value tile consumed
-    }
-    // ---- merge the two warpgroups' partial results ----
-    if (wg == 1) {
-      sm.xch[rowi][0] = m;
-      sm.xch[rowi][1] = l;
 #pragma unroll
-      for (int e = 0; e < DVH; ++e) sm.xch[rowi][2 + e] = acc[e];
+      for (int i = 0; i < CF_NWG; ++i) { rst.next(ST); rsl.next(NS); }
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // ---- merge the warpgroups' partial results ----
+    if (wg > 0) {
+      float* x = sm.xch[wg - 1][rowi];
+      x[0] = m;
+      x[1] = l;
+#pragma unroll
+      for (int e = 0; e < DVH; ++e) x[2 + e] = acc[e];
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(128 * CF_NWG) : "memory");
     if (wg == 0) {
-      const float m1 = sm.xch[rowi][0];
-      const float mm = fmaxf(m, m1);
-      const float a0 = tc::ex2f(m - mm), a1 = (m1 == -INFINITY) ? 0.f : tc::ex2f(m1 - mm);
-      const float lt = a0 * l + a1 * sm.xch[rowi][1];
+      float mm = m;
+#pragma unroll
+      for (int g = 0; g < CF_NWG - 1; ++g) mm = fmaxf(mm, sm.xch[g][rowi][0]);
+      const float a0 = tc::ex2f(m - mm);
+      float lt = a0 * l, ot[DVH];
+#pragma unroll
+      for (int e = 0; e < DVH; ++e) ot[e] = a0 * acc[e];
+#pragma unroll
+      for (int g = 0; g < CF_NWG - 1; ++g) {
+        const float mg = sm.xch[g][rowi][0];
+        const float ag = (mg == -INFINITY) ? 0.f : tc::ex2f(mg - mm);
+        lt = fmaf(ag, sm.xch[g][rowi][1], lt);
+#pragma unroll
+        for (int e = 0; e < DVH; ++e) ot[e] = fmaf(ag, sm.xch[g][rowi][2 + e], ot[e]);
+      }
       const int qi = q0 + rowi;
       if (qi < L) {
         const float inv = 1.f / lt;
         const size_t row = (size_t)bn * L + qi;
 #pragma unroll
-        for (int e = 0; e < DVH; ++e) o[row * DVH + e] = (a0 * acc[e] + a1 * sm.xch[rowi][2 + e]) * inv;
+        for (int e = 0; e < DVH; ++e) o[row * DVH + e] = ot[e] * inv;
         lse[row] = (mm + log2f(lt)) * 0.6931471805599453f;
       }
     }
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 9) tc::tmem_dealloc<512>(tmem);
+  if (warp == CF_W_S) tc::tmem_dealloc<512>(tmem);
 }
 
 // ================================================================================================
@@ -389,10 +410,10 @@ __device__ __forceinline__ void dq_cc_tile(const uint32_t (&rs)[2][32], uint32_t
     }
 }
 
-// one query tile of the dK/dV kernel: P^T = 2^S'^T and dS^T = P^T (dO[q].v - delta[q]) for this thread's key row
+// one query tile of the dK/dV kernel for this thread's key row: p = 2^S'^T, dV += p dO[q] (registers), dS^T = p (dO[q].v - delta[q])
 template <int DVH, bool TAIL>
-__device__ __forceinline__ void dkv_cc_tile(const uint32_t (&rs)[2][32], uint32_t (&pp)[32], uint32_t (&pd)[32], uint32_t dot,
-                                            uint32_t dlt, int nvalid, const float (&vk)[DVH]) {
+__device__ __forceinline__ void dkv_cc_tile(const uint32_t (&rs)[2][32], uint32_t (&pd)[32], uint32_t dot, uint32_t dlt, int nvalid,
+                                            const float (&vk)[DVH], float (&dvacc)[DVH]) {
 #pragma unroll
   for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -405,18 +426,19 @@ __device__ __forceinline__ void dkv_cc_tile(const uint32_t (&rs)[2][32], uint32_
       }
       const float4 dl = lds128(dlt + (c * 32 + i) * 4);
       const float dls[4] = {dl.x, dl.y, dl.z, dl.w};
-      float p[4], ds[4];
+      float ds[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float dp = -dls[u];
 #pragma unroll
         for (int e = 0; e < DVH; ++e) dp = fmaf(gg[u * DVH + e], vk[e], dp);
-        if (TAIL && c * 32 + i + u >= nvalid) dp = 0.f;        // zero-filled queries past L
-        p[u] = tc::ex2f(__uint_as_float(rs[c][i + u]));
-        ds[u] = p[u] * dp;
+        float p = tc::ex2f(__uint_as_float(rs[c][i + u]));
+        const bool dead = TAIL && c * 32 + i + u >= nvalid;    // zero-filled queries past L: the side tile holds stale data there
+        if (dead) { p = 0.f; dp = 0.f; }
+#pragma unroll
+        for (int e = 0; e < DVH; ++e) dvacc[e] = fmaf(p, dead ? 0.f : gg[u * DVH + e], dvacc[e]);
+        ds[u] = p * dp;
       }
-      pp[c * 16 + (i >> 1)] = tc::pack_bf16x2(p[0], p[1]);
-      pp[c * 16 + (i >> 1) + 1] = tc::pack_bf16x2(p[2], p[3]);
       pd[c * 16 + (i >> 1)] = tc::pack_bf16x2(ds[0], ds[1]);
       pd[c * 16 + (i >> 1) + 1] = tc::pack_bf16x2(ds[2], ds[3]);
     }
@@ -577,8 +599,9 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bn = blockIdx.y, k0 = blockIdx.x * CB_BM;
   const int ntiles = (L + CB_BN - 1) / CB_BN;
-  const int NS = min(CB_MAXSLOTS, (512 - KATOMS * 32 - 48) / 64);
-  const uint32_t COL_SLOT0 = KATOMS * 32, COL_DV = COL_SLOT0 + 64 * NS, COL_DK = COL_DV + 16;
+  const int NS = min(CB_MAXSLOTS, (512 - KATOMS * 32 - 32) / 64);
+  const uint32_t COL_SLOT0 = KATOMS * 32, COL_DK = COL_SLOT0 + 64 * NS;
+  __shared__ float dv_xch[CB_NWG - 1][CB_BM][DVH];     // dV partials of warpgroups 1.. (dV = P^T dO is accumulated in registers)
 
   cb_init(sm, warp, lane, &tm_k_stat, &tm_q_strm);
   const uint32_t tmem = sm.tmem_base;
@@ -602,10 +625,8 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
   } else if (warp == CB_W_S) {
     cb_score_issuer<KATOMS>(sm, tmem, COL_SLOT0, NS, C1 >> 4, ntiles);
   } else if (warp == CB_W_G) {
-    constexpr uint32_t idesc_dv = tc::idesc_bf16_f32(CB_BM, 16) | (1u << 16);
     constexpr uint32_t idesc_dk = tc::idesc_bf16_f32(CB_BM, 32) | (1u << 16);
     constexpr uint32_t STRM_ATOM = (CB_BN * 128) >> 4, STAGE = KATOMS * STRM_ATOM;
-    const uint32_t v_lo = tc::desc_lo_mn(smem_u32(sm.strm[0][C1 >> 6]) + (C1 & 63) * 2, CB_BN * 128);
     const uint32_t q_lo = tc::desc_lo_mn(smem_u32(sm.strm[0][0]), CB_BN * 128);
     Ring rst, rsl;
     for (int jj = 0; jj < ntiles; ++jj, rst.next(CB_STAGES), rsl.next(NS)) {
@@ -614,12 +635,10 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
       tc::mbar_wait(&sm.bar_p_ready[slot], rsl.ph);
       tc::tc_fence_after();
       if (tc::elect_one()) {
-        const uint32_t vb = v_lo + st * STAGE, qb = q_lo + st * STAGE;
+        const uint32_t qb = q_lo + st * STAGE;
 #pragma unroll
-        for (int ks = 0; ks < CB_BN / 16; ++ks) {
-          tc::mma_ts(tmem + COL_DV, tslot + ks * 8, tc::desc64(vb + ks * 128), idesc_dv, (jj > 0 || ks > 0) ? 1u : 0u);
-          tc::mma_ts(tmem + COL_DK, tslot + 32 + ks * 8, tc::desc64(qb + ks * 128), idesc_dk, (jj > 0 || ks > 0) ? 1u : 0u);
-        }
+        for (int ks = 0; ks < CB_BN / 16; ++ks)
+          tc::mma_ts(tmem + COL_DK, tslot + ks * 8, tc::desc64(qb + ks * 128), idesc_dk, (jj > 0 || ks > 0) ? 1u : 0u);
         tc::mma_commit(&sm.bar_empty[st]);
         tc::mma_commit(&sm.bar_slot_free[slot]);
         if (jj == ntiles - 1) tc::mma_commit(&sm.bar_final);
@@ -640,7 +659,10 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
     float vk[DVH];
 #pragma unroll
     for (int e = 0; e < DVH; ++e) vk[e] = kj < L ? v[row * DVH + e] : 0.f;
-    uint32_t rs[2][32], pp[32], pd[32];
+    float dvacc[DVH];
+#pragma unroll
+    for (int e = 0; e < DVH; ++e) dvacc[e] = 0.f;
+    uint32_t rs[2][32], pd[32];
     Ring rst, rsl;
     for (int i = 0; i < wg; ++i) { rst.next(CB_STAGES); rsl.next(NS); }
     for (int j = wg; j < ntiles; j += CB_NWG) {
@@ -654,10 +676,9 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
       tc::tmem_ld_x32(tslot + 32, rs[1]);
       tc::tmem_ld_wait();
       const uint32_t dot = smem_u32(sm.side[st]), dlt = dot + CB_BN * DVH * 4;
-      if (tail) dkv_cc_tile<DVH, true>(rs, pp, pd, dot, dlt, nvalid, vk);
-      else dkv_cc_tile<DVH, false>(rs, pp, pd, dot, dlt, nvalid, vk);
-      tc::tmem_st_x32(tslot, pp);                    // P^T over S'^T[0,32), dS^T over [32,64): all of S'^T is in registers
-      tc::tmem_st_x32(tslot + 32, pd);
+      if (tail) dkv_cc_tile<DVH, true>(rs, pd, dot, dlt, nvalid, vk, dvacc);
+      else dkv_cc_tile<DVH, false>(rs, pd, dot, dlt, nvalid, vk, dvacc);
+      tc::tmem_st_x32(tslot, pd);                    // dS^T (bf16) over S'^T[0,32): all of S'^T is in registers
       tc::tmem_st_wait();
       tc::tc_fence_before();
       tc::mbar_arrive(&sm.bar_p_ready[slot]);
@@ -665,6 +686,11 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
 #pragma unroll
       for (int i = 0; i < CB_NWG; ++i) { rst.next(CB_STAGES); rsl.next(NS); }
     }
+    if (wg > 0) {
+#pragma unroll
+      for (int e = 0; e < DVH; ++e) dv_xch[wg - 1][rowi][e] = dvacc[e];
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(128 * CB_NWG) : "memory");
     tc::mbar_wait(&sm.bar_final, 0);
     tc::tc_fence_after();
     const float LN2 = 0.6931471805599453f;               // Qa carries log2(e)*q
@@ -696,19 +722,15 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
             if (e < dkh) dk[row * dkh + e] = __uint_as_float(rs[0][e]) * LN2;
         }
       }
-    } else if (wg == 1) {
-      uint32_t rv[16];
-      tc::tmem_ld_x16(tlane + COL_DV, rv);
-      tc::tmem_ld_wait();
-      if (kj < L) {
-        if (prow) {
-          bf16* dst = prow + 2 * nh * dkh + n * DVH;
+    }
+    if (wg == 0 && kj < L) {                             // dV: own partial + the other warpgroups' (fixed order)
 #pragma unroll
-          for (int e = 0; e < DVH; ++e) dst[e] = __float2bfloat16(__uint_as_float(rv[e]));
-        } else {
+      for (int e = 0; e < DVH; ++e) {
+        float t = dvacc[e];
 #pragma unroll
-          for (int e = 0; e < DVH; ++e) dv[row * DVH + e] = __uint_as_float(rv[e]);
-        }
+        for (int g = 0; g < CB_NWG - 1; ++g) t += dv_xch[g][rowi][e];
+        if (prow) prow[2 * nh * dkh + n * DVH + e] = __float2bfloat16(t);
+        else dv[row * DVH + e] = t;
       }
     }
   }
