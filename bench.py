@@ -41,6 +41,13 @@ def flops_fwd(B, cin, hin, cout, dk, dv, nh=8, ks=3):
     return dense + attn
 
 
+# dram bytes per launch of the dominant kernels at T1/B=16, copied from the ncu --set full captures under profiles/
+NCU_DRAM_BYTES_PER_LAUNCH = {   # profiles/r01_b_tcgen05_cc_path.md
+    'attn_fwd_cc': 112.1e6, 'attn_bwd_dkv_cc': 114.9e6, 'attn_bwd_dq_cc': 154.7e6, 'aug_build_fwd': 82.1e6, 'rel_bwd': 104.9e6,
+    'conv_qkv_fprop_tc': 59.1e6, 'conv_qkv_dgrad_tc': 25.8e6, 'conv_qkv_wgrad_tc': 84.9e6, 'pack_nhwc_bf16': 130.0e6,
+}
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -270,7 +277,10 @@ def main():
             L = H * H
             nh, dkh, dvh = 8, dk // 8, dv // 8
             attn_f = 2 * B * nh * L * (L * dkh + dkh * (4 * H - 2) + L * dvh)
-            work = {'attn_fwd': attn_f, 'attn_bwd': 2 * attn_f, 'attn_bwd_dq': attn_f, 'attn_bwd_dkv': attn_f,
+            dense = 2 * B * L * (9 * cin * (cout - dv) + cin * (2 * dk + dv))
+            # algorithmic flops per launch; recompute is not counted
+            work = {'attn_fwd': attn_f, 'attn_bwd_dq': attn_f, 'attn_bwd_dkv': attn_f,
+                    'conv_qkv_fprop': dense, 'conv_qkv_dgrad': dense, 'conv_qkv_wgrad': dense,
                     'conv_fwd': 2 * B * L * 9 * cin * (cout - dv), 'conv_bwd_data': 2 * B * L * 9 * cin * (cout - dv),
                     'conv_bwd_weight': 2 * B * L * 9 * cin * (cout - dv),
                     'qkv_fwd': 2 * B * L * cin * (2 * dk + dv), 'qkv_bwd_data': 2 * B * L * cin * (2 * dk + dv),
@@ -278,9 +288,21 @@ def main():
             key = next((k for k in sorted(work, key=len, reverse=True) if top[0].startswith(k)), None)
             dur = top[1]['ms_total_per_step'] * 1e-3
             ach = work[key] / dur / 1e12 if key else None
+            nl = max(top[1]['launches_per_step'], 1.0)
+            # every score is exponentiated once per attention kernel: the MUFU.EX2 floor (15.9 ex2/clk/SM measured,
+            # tools/mufu_bench.cu) is the binding roofline of the attention kernels, reported beside the tensor one
+            exps = B * nh * L * L if top[0].startswith('attn_') else 0
+            clk = (sampler.summary()['sm_mhz'] or 1965) * 1e6
             roof = {'kernel': top[0], 'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                    'frac': (ach / peak_tf) if ach else None, 'traffic': None, 'peak_source': how,
-                    'ms_per_step': top[1]['ms_total_per_step'], 'launches_per_step': top[1]['launches_per_step'],
+                    'frac': (ach / peak_tf) if ach else None,
+                    'traffic': NCU_DRAM_BYTES_PER_LAUNCH.get(top[0]) if args.shape == 'T1' and B == 16 else None,
+                    'traffic_source': 'ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, profiles/ (T1, B=16)',
+                    'peak_source': how, 'ms_per_step': top[1]['ms_total_per_step'],
+                    'launches_per_step': top[1]['launches_per_step'],
+                    'us_per_launch': top[1]['ms_total_per_step'] * 1e3 / nl,
+                    'mufu_exp_per_launch': exps,
+                    'mufu_floor_us': exps / (148 * 15.9 * clk) * 1e6 if exps else None,
+                    'mufu_frac': (exps / (148 * 15.9 * clk)) / (top[1]['ms_total_per_step'] * 1e-3 / nl) if exps else None,
                     'module_frac_of_bf16_peak': tf / world / peak_tf}
         h2d = x_host.numel() * 4 + dy_host.numel() * 4
         d2h = y_host.numel() * 4 + sum(t.numel() * 4 for t in g_host)

@@ -3,7 +3,7 @@
     python tools/sass_summary.py profiles/<name>.md
 
 UTC*MMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTMALDG = TMA load, UTCBAR = tcgen05.commit, SYNCS = mbarrier,
-MUFU.EX2 = ex2.approx, HMMA = legacy mma.sync (must stay 0 on the tensor-core kernels).
+MUFU.EX2 = ex2.approx, HMMA = legacy mma.sync (only the rank-dkh relative-position kernels use it, TF32).
 """
 import collections
 import os
@@ -41,7 +41,7 @@ def main():
                 counts[kern][p] += 1
     out = ['# SASS mnemonic counts per kernel (cuobjdump -sass libaaconv_b200.so, sm_100a)', '',
            'UTC*MMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTMALDG = TMA tensor load, UTCBAR = tcgen05.commit, '
-           'SYNCS = mbarrier ops, MUFU.EX2 = ex2.approx; HMMA (legacy mma.sync) is 0 everywhere.', '',
+           'SYNCS = mbarrier ops, MUFU.EX2 = ex2.approx; HMMA (legacy mma.sync, TF32) only in the rank-dkh relative-position kernels.', '',
            '| kernel | instrs | ' + ' | '.join(PAT) + ' |', '|---|---|' + '---|' * len(PAT)]
     for k, c in counts.items():
         out.append(f'| {k[:60]} | {c["total"]} | ' + ' | '.join(str(c[p]) if c[p] else '' for p in PAT) + ' |')
