@@ -26,7 +26,7 @@ def main():
         m = re.search(r'Function : (\S+)', line)
         if m:
             kern = subprocess.run(['c++filt', m.group(1)], capture_output=True, text=True).stdout.strip()
-            kern = kern.replace('aaconv::', '').replace('void ', '').split('(')[0]
+            kern = kern.replace('(anonymous namespace)::', '').replace('aaconv::', '').replace('void ', '').split('(')[0]
             counts[kern] = collections.Counter(total=0)
             continue
         if kern is None:
@@ -43,7 +43,8 @@ def main():
            'UTC*MMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTMALDG = TMA tensor load, UTCBAR = tcgen05.commit, '
            'SYNCS = mbarrier ops, MUFU.EX2 = ex2.approx; HMMA (legacy mma.sync, TF32) only in the rank-dkh relative-position kernels.', '',
            '| kernel | instrs | ' + ' | '.join(PAT) + ' |', '|---|---|' + '---|' * len(PAT)]
-    for k, c in counts.items():
+    order = sorted(counts.items(), key=lambda kc: -(kc[1]['UTCHMMA'] * 1000 + kc[1]['HMMA'] * 10 + kc[1]['UTMALDG']))
+    for k, c in order:
         out.append(f'| {k[:60]} | {c["total"]} | ' + ' | '.join(str(c[p]) if c[p] else '' for p in PAT) + ' |')
     open(dst, 'w').write('\n'.join(out) + '\n')
     print('wrote', dst, len(counts), 'kernels')
