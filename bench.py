@@ -123,7 +123,9 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': 'aaconv_fwd_bwd_tflops', 'value': tf, 'unit': 'TFLOP/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': sec * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'AAConv2d {args.shape} fwd+bwd', 'shape': args.shape, 'batch_per_step': B},
+            'config': {'workload': f'AAConv2d {args.shape} fwd+bwd (configs[1])', 'shape': args.shape, 'batch_per_gpu': args.batch,
+                       'cin': cin, 'hin': hin, 'cout': cout, 'dk': dk, 'dv': dv, 'nh': 8, 'precision': 'fp32 (reference arithmetic)',
+                       'sample_batch_per_step': B},
             'cpu_baseline': {'value': tf, 'unit': 'TFLOP/s', 'cores': threads, 'kind': 'port',
                              'sample': f'oracle.SequentialAAConv2d (reference op order, torch CPU fp32) {args.shape} B={B} '
                                        f'fwd+bwd x{args.steps}'},

@@ -31,7 +31,7 @@ struct PGParams {
   PGSeg segs[PG_MAX_SEGS];
   PGChunk chunks[PG_MAX_CHUNKS];
   int nchunks;
-  int r, Wt, Ht, tiles_h;          // tile = r rows x Wt pixels of the (Ht x Wt) pixel grid this launch covers
+  int r, Wt, Ht, tiles_h, ncta;    // tile = r rows x Wt pixels of the (Ht x Wt) pixel grid this job covers; ncta = B * tiles_h
   // epilogue
   int mode;                        // 0 fprop, 1 dgrad
   float* out0; float* q; float* k; float* v;
@@ -46,7 +46,14 @@ struct __align__(1024) PGSmem {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_tc_kernel(const __grid_constant__ PGParams p) {
+// Several independent jobs (accumulator-chunk groups, residue classes) share one launch: blockIdx.y selects the job, so
+// their CTAs fill one another's tail waves (long jobs first: blocks are dispatched in index order).
+constexpr int PG_MAX_JOBS = 4;
+struct PGJobs { PGParams job[PG_MAX_JOBS]; };
+
+__global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_tc_kernel(const __grid_constant__ PGJobs jobs) {
+  const PGParams& p = jobs.job[blockIdx.y];
+  if ((int)blockIdx.x >= p.ncta) return;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   PGSmem& sm = *reinterpret_cast<PGSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -401,13 +408,26 @@ TcGemmBufs tc_gemm_bufs(const Dims& d, void* base) {
   return t;
 }
 
-static int launch_pg(const PGParams& p, int B, cudaStream_t st, const char* name) {
-  const size_t smem = sizeof(PGSmem) + 1024;
-  AACONV_CUDA_OK(cudaFuncSetAttribute(pixel_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pixel_gemm_tc_kernel<<<B * p.tiles_h, PG_THREADS, smem, st>>>(p);
-  AACONV_LAUNCH_OK(name);
-  return 0;
-}
+// launches the queued jobs, PG_MAX_JOBS per launch
+struct PGQueue {
+  std::vector<PGParams> jobs;
+  void add(PGParams p, int B) { p.ncta = B * p.tiles_h; jobs.push_back(p); }
+  int flush(cudaStream_t st, const char* name) {
+    const size_t smem = sizeof(PGSmem) + 1024;
+    AACONV_CUDA_OK(cudaFuncSetAttribute(pixel_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (size_t i = 0; i < jobs.size(); i += PG_MAX_JOBS) {
+      PGJobs j;
+      memset(&j, 0, sizeof j);
+      const int n = (int)std::min<size_t>(PG_MAX_JOBS, jobs.size() - i);
+      int ncta = 0;
+      for (int k = 0; k < n; ++k) { j.job[k] = jobs[i + k]; ncta = std::max(ncta, j.job[k].ncta); }
+      pixel_gemm_tc_kernel<<<dim3(ncta, n), PG_THREADS, smem, st>>>(j);
+      AACONV_LAUNCH_OK(name);
+    }
+    jobs.clear();
+    return 0;
+  }
+};
 
 // channels-last 4D map over the pixels of one residue class (ph, pw) of an (B, Hs, Ws, C) tensor
 static int make_nhwc_map(CUtensorMap* out, const void* base, int B, int Hs, int Ws, int C, int s, int ph, int pw, int r,
@@ -459,20 +479,29 @@ int tc_fprop(const Dims& d, const TcGemmBufs& t, const float* x, const float* co
   p.Cout = d.Cout; p.Cc = d.Cc; p.H = d.H; p.W = d.W; p.L = d.L; p.nh = d.nh; p.dk = d.dk; p.dkh = d.dkh; p.dvh = d.dvh;
   p.Nqkv = d.Nqkv; p.qscale = d.qscale;
   // accumulator chunks, up to PG_MAX_CHUNKS per launch
-  struct C { int n0, kind; };
-  std::vector<C> all;
-  // short-K projection chunks first: their (scattered) epilogues hide under the long conv mainloop
-  for (int n0 = 0; n0 < d.Nqkv; n0 += 128) all.push_back({n0, 1});
-  for (int n0 = 0; n0 < d.Cc; n0 += 128) all.push_back({n0, 0});
-  for (size_t i = 0; i < all.size(); i += PG_MAX_CHUNKS) {
-    p.nchunks = (int)std::min<size_t>(PG_MAX_CHUNKS, all.size() - i);
-    for (int c = 0; c < p.nchunks; ++c) {
-      const C& a = all[i + c];
-      p.chunks[c] = a.kind == 0 ? PGChunk{a.n0, 0, T, 0} : PGChunk{a.n0, seg_qkv, seg_qkv + 1, 1};
+  // One job when everything fits the four TMEM accumulator chunks (the projection is the centre tap: its A tiles are L2-hot
+  // and its scattered epilogues hide under the conv mainloop).  Otherwise groups of conv chunks (long K = 9 taps) first,
+  // then groups of projection chunks (short K) whose CTAs fill the tail of the long ones -- all in one launch.
+  PGQueue qu;
+  const int nc_conv = cdiv(d.Cc, 128), nc_qkv = cdiv(d.Nqkv, 128);
+  if (nc_conv + nc_qkv <= PG_MAX_CHUNKS) {
+    p.nchunks = 0;
+    for (int c = 0; c < nc_qkv; ++c) p.chunks[p.nchunks++] = PGChunk{c * 128, seg_qkv, seg_qkv + 1, 1};
+    for (int c = 0; c < nc_conv; ++c) p.chunks[p.nchunks++] = PGChunk{c * 128, 0, T, 0};
+    qu.add(p, d.B);
+  } else {
+    for (int g0 = 0; g0 < d.Cc; g0 += 128 * PG_MAX_CHUNKS) {
+      p.nchunks = std::min(PG_MAX_CHUNKS, cdiv(d.Cc - g0, 128));
+      for (int c = 0; c < p.nchunks; ++c) p.chunks[c] = PGChunk{g0 + c * 128, 0, T, 0};
+      qu.add(p, d.B);
     }
-    AACONV_TRY(launch_pg(p, d.B, st, "conv_qkv_fprop_tc"));
+    for (int g0 = 0; g0 < d.Nqkv; g0 += 128 * PG_MAX_CHUNKS) {
+      p.nchunks = std::min(PG_MAX_CHUNKS, cdiv(d.Nqkv - g0, 128));
+      for (int c = 0; c < p.nchunks; ++c) p.chunks[c] = PGChunk{g0 + c * 128, seg_qkv, seg_qkv + 1, 1};
+      qu.add(p, d.B);
+    }
   }
-  return 0;
+  return qu.flush(st, "conv_qkv_fprop_tc");
 }
 
 // packed backward operands shared by dgrad and wgrad: dyh (B,L,KPc) and dqkvh (B,L,KPq) = concat(dq*scale, dk, dv)
@@ -505,7 +534,8 @@ int tc_dgrad(const Dims& d, const TcGemmBufs& t, const float* conv_w, const floa
     if (rh == 0 && rw == 0) out[ns++] = {1, 0, 0, t.KPq / 64, 1, 0};   // 1x1 stride-s projection touches class (0,0)
     return ns;
   };
-  for (int rh = 0; rh < s; ++rh) {
+  PGQueue qu;
+  for (int rh = s - 1; rh >= 0; --rh) {           // odd rows first: they get more taps (longer jobs)
     const int Hc = d.Hin > rh ? (d.Hin - rh + s - 1) / s : 0;
     if (Hc == 0) continue;
     PGParams p;
@@ -530,7 +560,7 @@ int tc_dgrad(const Dims& d, const TcGemmBufs& t, const float* conv_w, const floa
           p.chunks[2 * c] = {n0 + c * 128, 0, ns0, 0};
           p.chunks[2 * c + 1] = {n0 + c * 128, ns0, ns0 + ns1, 0};
         }
-        AACONV_TRY(launch_pg(p, d.B, st, "conv_qkv_dgrad_tc"));
+        qu.add(p, d.B);
       }
       continue;
     }
@@ -552,11 +582,11 @@ int tc_dgrad(const Dims& d, const TcGemmBufs& t, const float* conv_w, const floa
       for (int n0 = 0; n0 < d.Cin; n0 += 128 * PG_MAX_CHUNKS) {
         p.nchunks = std::min(PG_MAX_CHUNKS, cdiv(d.Cin - n0, 128));
         for (int c = 0; c < p.nchunks; ++c) p.chunks[c] = {n0 + c * 128, 0, ns, 0};
-        AACONV_TRY(launch_pg(p, d.B, st, "conv_qkv_dgrad_tc"));
+        qu.add(p, d.B);
       }
     }
   }
-  return 0;
+  return qu.flush(st, "conv_qkv_dgrad_tc");
 }
 
 __global__ void zero_class_kernel(float* __restrict__ dx, size_t planes, int Hin, int Win, int s, int rh, int rw) {
