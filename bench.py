@@ -134,6 +134,80 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_model(args):
+    """configs[2]: whole-model data-parallel training step of aadensenet121 (chexpert.py:152-165) on synthetic radiographs."""
+    import torch.distributed as dist
+    from chexpert_b200 import _lib
+    from chexpert_b200.train import TrainStep, synthetic_batch
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    W, K, B = max(args.warmup, 3), args.steps, args.batch
+    ts = TrainStep(dev, size=args.size, precision=args.precision)
+    xh, th = synthetic_batch(B, size=args.size, seed=1000 + rank)
+    xh, th = xh.pin_memory(), th.pin_memory()
+    x, t = xh.to(dev), th.to(dev)
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    def e2e_step():
+        xd = xh.to(dev, non_blocking=True)
+        td = th.to(dev, non_blocking=True)
+        loss_host.copy_(ts(xd, td), non_blocking=True)
+
+    for _ in range(W):
+        ts(x, t)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = _lib.launch_count()
+    ms = timed(lambda: ts(x, t), K)
+    launches = _lib.launch_count() - l0
+    barrier()
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    ms_e2e = timed(e2e_step, max(3, K // 2))
+    barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    if world > 1:
+        tt = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = tt.tolist()
+    if rank == 0:
+        line = {'metric': 'aadensenet121_train_images_per_s', 'value': B * world / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world,
+                'steps': K, 'warmup': W, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
+                'config': {'workload': 'aadensenet121 training step (configs[2])', 'batch_per_gpu': B, 'image': args.size,
+                           'precision': args.precision, 'optimizer': 'SGD nesterov momentum 0.9', 'parallelism': f'dp{world}',
+                           'l2': 'activations of one step (>> 126 MB) stream through L2; no explicit flush',
+                           'dense_blocks': 'torchvision _DenseBlock under torch.autocast(bf16), as the reference wires them'},
+                'e2e': {'value': B * world / (ms_e2e * 1e-3), 'unit': 'images/s', 'ms_per_step': ms_e2e,
+                        'h2d_bytes_per_step': xh.numel() * 4 + th.numel() * 4, 'd2h_bytes_per_step': 4},
+                'gpu_launches': launches, 'clocks': sampler.summary(), 'roofline': None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -146,9 +220,15 @@ def main():
     ap.add_argument('--ref-batch', type=int, default=4, help='per-step batch of the CPU reference arm (bounded sample)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-flush', action='store_true')
+    ap.add_argument('--workload', default='layer', choices=['layer', 'model'],
+                    help="layer: AAConv2d fwd+bwd microbench (configs[1], the headline); model: aadensenet121 training step "
+                         "(configs[2]: batch 16/GPU, 320x320, SGD-nesterov, gradient all-reduce), images/s")
+    ap.add_argument('--size', type=int, default=320)
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.workload == 'model':
+        return run_model(args)
 
     import torch.distributed as dist
     import chexpert_b200 as cb
