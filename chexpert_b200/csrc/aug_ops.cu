@@ -120,7 +120,6 @@ __global__ void __launch_bounds__(256) aug_build_fwd_kernel(const BuildP p) {
   if (threadIdx.x == 0) { tc::mbar_init(bar, 1); tc::fence_barrier_init(); }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int CP = p.KP >> 1, rows_per_pass = 256 / CP, cp = threadIdx.x % CP, rsub = threadIdx.x / CP;
   if (p.relative) {
     for (int i = threadIdx.x; i < p.DK8 * p.PBW; i += blockDim.x) {
       const int e = i / p.PBW, r = i - e * p.PBW;
@@ -133,19 +132,15 @@ __global__ void __launch_bounds__(256) aug_build_fwd_kernel(const BuildP p) {
   }
   for (int i = threadIdx.x; i < 2 * TR * p.dkh + ((TR * p.dvh + 3) & ~3) + 4; i += blockDim.x) qs[i] = 0.f;
   uint32_t phase = 0;
-  // kind of this thread's two columns: Ka value = kcst + [x == kohx] + [y == kohy] + kld[r * kst];  Qa: 0 zero, 1 q, 2 skip (rel)
-  const int c0 = 2 * cp;
-  float kcst[2];
-  int kohx[2], kohy[2], kst[2], kofs[2], qmode[2];        // kofs: offset from qs (ks and vs follow it in shared memory)
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int c = c0 + h;
-    kcst[h] = 0.f; kohx[h] = -1; kohy[h] = -1; kst[h] = 0; kofs[h] = 0; qmode[h] = 0;
-    if (c < p.dkh) { kofs[h] = (int)(ks - qs) + c; kst[h] = p.dkh; qmode[h] = 1; }
-    else if (c < p.KD) { qmode[h] = 2; if (c < p.dkh + p.W) kohx[h] = c - p.dkh; else kohy[h] = c - p.dkh - p.W; }
-    else if (c < p.KD + 2) kcst[h] = 1.f;
-    else if (c >= p.C1 && c < p.C1 + p.dvh) { kofs[h] = (int)(vs - qs) + (c - p.C1); kst[h] = p.dvh; }
-    else if (c >= p.C1 + p.dvh && c < p.C1 + p.dvh + 2) kcst[h] = 1.f;
+  // The tiles keep their constant part across the tiles of this CTA: zeros everywhere, ones in the lse / delta slots of
+  // Ka.  Per tile only the k, v, q columns, the relative columns (MMA phase) and the two one-hot positions per row change.
+  for (int i = threadIdx.x; i < 2 * TR * PT; i += blockDim.x) tq[i] = __float2bfloat16(0.f);   // tq and tk are adjacent
+  if (threadIdx.x < TR) { rx[threadIdx.x] = -1; ry[threadIdx.x] = -1; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < TR * 4; i += blockDim.x) {
+    const int r = i >> 2, w = i & 3;
+    const int c = (w < 2 ? p.KD : p.C1 + p.dvh) + (w & 1);
+    tk[r * PT + c] = __float2bfloat16(1.f);
   }
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const int bn = tile / p.tiles_per_bn, l0 = (tile - bn * p.tiles_per_bn) * TR;
@@ -153,9 +148,13 @@ __global__ void __launch_bounds__(256) aug_build_fwd_kernel(const BuildP p) {
     const size_t row0 = (size_t)bn * p.L + l0;
     __syncthreads();                                   // previous tile fully copied out; tables visible
     if (threadIdx.x < TR) {
-      const int l = l0 + threadIdx.x, y = l / p.W;
-      rx[threadIdx.x] = l - y * p.W;
-      ry[threadIdx.x] = y;
+      const int r = threadIdx.x, l = l0 + r, y = l / p.W, x = l - y * p.W;
+      if (p.relative) {
+        if (rx[r] >= 0) { tk[r * PT + p.dkh + rx[r]] = __float2bfloat16(0.f); tk[r * PT + p.dkh + p.W + ry[r]] = __float2bfloat16(0.f); }
+        if (y < p.H) { tk[r * PT + p.dkh + x] = __float2bfloat16(1.f); tk[r * PT + p.dkh + p.W + y] = __float2bfloat16(1.f); }
+      }
+      rx[r] = y < p.H ? x : -1;
+      ry[r] = y;
     }
     // tile loads: three 1-D bulk copies (TMA unit) when the blocks are 16 B aligned, else per-element LDGSTS
     const bool bulk = (((row0 * p.dkh) | (size_t)(nrows * p.dkh) | (row0 * p.dvh) | (size_t)(nrows * p.dvh)) & 3) == 0;
@@ -214,27 +213,15 @@ __global__ void __launch_bounds__(256) aug_build_fwd_kernel(const BuildP p) {
         if ((unsigned)(xb + 1) < (unsigned)N) tq[rb * PT + colbase + xb + 1] = __float2bfloat16(c[3]);
       }
     }
-    // ---- everything else: q columns and zero tail of Qa, all of Ka.  A thread owns one column pair whose kind was
-    //      decoded once (branch-free inner loop) and walks down the rows; bf16x2 stores.  Rows past the end of the
-    //      image are never copied out, so they need no masking. ----
-    if (rsub < rows_per_pass) {
-      for (int r = rsub; r < TR; r += rows_per_pass) {
-        const int x = rx[r], y = ry[r];
-        float kv[2], qv[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          kv[h] = kcst[h] + (x == kohx[h] ? 1.f : 0.f) + (y == kohy[h] ? 1.f : 0.f);
-          if (kst[h]) kv[h] += qs[kofs[h] + r * kst[h]];
-          qv[h] = qmode[h] == 1 ? qs[r * PQ + c0 + h] * LOG2E : 0.f;
-        }
-        *reinterpret_cast<__nv_bfloat162*>(tk + r * PT + c0) = __floats2bfloat162_rn(kv[0], kv[1]);
-        if (qmode[0] != 2 && qmode[1] != 2) {
-          *reinterpret_cast<__nv_bfloat162*>(tq + r * PT + c0) = __floats2bfloat162_rn(qv[0], qv[1]);
-        } else {
-          if (qmode[0] != 2) tq[r * PT + c0] = __float2bfloat16(qv[0]);
-          if (qmode[1] != 2) tq[r * PT + c0 + 1] = __float2bfloat16(qv[1]);
-        }
-      }
+    // ---- data columns: c*q into Qa, k and v into Ka (everything else in the tiles is constant or written above) ----
+    for (int i = threadIdx.x; i < TR * p.dkh; i += blockDim.x) {
+      const int r = i / p.dkh, e = i - r * p.dkh;
+      tq[r * PT + e] = __float2bfloat16(qs[i] * LOG2E);
+      tk[r * PT + e] = __float2bfloat16(ks[i]);
+    }
+    for (int i = threadIdx.x; i < TR * p.dvh; i += blockDim.x) {
+      const int r = i / p.dvh, e = i - r * p.dvh;
+      tk[r * PT + p.C1 + e] = __float2bfloat16(vs[i]);
     }
     __syncthreads();
     // ---- coalesced copy-out: rows of KP bf16 are contiguous in global memory ----
