@@ -43,6 +43,8 @@ SYMBOLS = {
     'aaconv_bce_forward_backward': (ctypes.c_int, [_P, _P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int,
                                                    _P, _P, _P, _P, _P]),
     'aaconv_launch_count': (ctypes.c_longlong, []),
+    'aaconv_debug_set_timeline': (None, [_P]),
+    'aaconv_debug_set_mode': (None, [ctypes.c_int]),
     'aaconv_profile_begin': (ctypes.c_int, [_P]),
     'aaconv_profile_end': (ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_float), ctypes.c_int]),
 }

@@ -62,7 +62,7 @@ int aaconv_forward(const aaconv_dims* d, int precision, const float* x, const aa
 }
 
 int aaconv_backward(const aaconv_dims* d, int precision, const float* x, const aaconv_params* p, const float* dy,
-                    const void* saved, void* scratch, float* dx, const aaconv_param_grads* g, void* stream) {
+                    void* saved, void* scratch, float* dx, const aaconv_param_grads* g, void* stream) {
   AACONV_TRY(validate(d, precision));
   if (!x || !p || !dy || !saved || !scratch || !g) return fail(AACONV_E_ARG, "NULL buffer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -95,7 +95,7 @@ int bf16_forward(const Dims& d, const float* x, const aaconv_params* p, float* y
   return 0;
 }
 
-int bf16_backward(const Dims& d, const float* x, const aaconv_params* p, const float* dy, const void* saved,
+int bf16_backward(const Dims& d, const float* x, const aaconv_params* p, const float* dy, void* saved,
                   void* scratch, float* dx, const aaconv_param_grads* g, cudaStream_t st) {
   AACONV_TRY(aug_supported(d));
   Scratch w(d, scratch, 0);

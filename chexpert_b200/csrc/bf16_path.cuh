@@ -67,6 +67,6 @@ size_t bf16_scratch_bytes(const Dims& d, int want_weights);
 int64_t bf16_saved_offset(const Dims& d, const char* name);
 int bf16_forward(const Dims& d, const float* x, const aaconv_params* p, float* y, float* weights, void* saved,
                  void* scratch, cudaStream_t st);
-int bf16_backward(const Dims& d, const float* x, const aaconv_params* p, const float* dy, const void* saved,
+int bf16_backward(const Dims& d, const float* x, const aaconv_params* p, const float* dy, void* saved,
                   void* scratch, float* dx, const aaconv_param_grads* g, cudaStream_t st);
 }  // namespace aaconv

@@ -69,7 +69,7 @@ int f32_forward(const Dims& d, const float* x, const aaconv_params* p, float* y,
   return 0;
 }
 
-int f32_backward(const Dims& d, const float* x, const aaconv_params* p, const float* dy, const void* saved,
+int f32_backward(const Dims& d, const float* x, const aaconv_params* p, const float* dy, void* saved,
                  void* scratch, float* dx, const aaconv_param_grads* g, cudaStream_t st) {
   Saved s(d, const_cast<void*>(saved));
   Scratch w(d, scratch);

@@ -39,7 +39,7 @@ size_t f32_scratch_bytes(const Dims& d);
 int64_t f32_saved_offset(const Dims& d, const char* name);
 int f32_forward(const Dims& d, const float* x, const aaconv_params* p, float* y, float* weights, void* saved,
                 void* scratch, cudaStream_t st);
-int f32_backward(const Dims& d, const float* x, const aaconv_params* p, const float* dy, const void* saved,
+int f32_backward(const Dims& d, const float* x, const aaconv_params* p, const float* dy, void* saved,
                  void* scratch, float* dx, const aaconv_param_grads* g, cudaStream_t st);
 
 }  // namespace aaconv

@@ -88,9 +88,11 @@ int aaconv_forward(const aaconv_dims* d, int precision, const float* x, const aa
                    float* y, float* weights, void* saved, void* scratch, void* stream);
 
 /* Backward: the adjoint autograd derives from attn_aug_conv.py:65-97.
- *   dy (B,Cout,H,W); dx (B,Cin,Hin,Win) or NULL; parameter grads are WRITTEN (not accumulated).      */
+ *   dy (B,Cout,H,W); dx (B,Cin,Hin,Win) or NULL; parameter grads are WRITTEN (not accumulated).
+ *   `saved` is the block forward filled; the bf16 path completes its backward-only columns in place (idempotent:
+ *   backward may be called again on the same block, e.g. under retain_graph).                        */
 int aaconv_backward(const aaconv_dims* d, int precision, const float* x, const aaconv_params* p,
-                    const float* dy, const void* saved, void* scratch,
+                    const float* dy, void* saved, void* scratch,
                     float* dx, const aaconv_param_grads* g, void* stream);
 
 /* Loss: replaces nn.BCEWithLogitsLoss(reduction='none')(z,t) [.sum(1).mean(0)]  (chexpert.py:530,160,205).
@@ -110,6 +112,12 @@ int aaconv_bce_forward_backward(const float* z, const float* targets, int ld, co
  *   aaconv_profile_end    stop; fills ms[i] = device time of launch i (gap to the previous mark) and the
  *                         '\n'-joined kernel names; returns the number of entries written (<= max_entries). */
 long long aaconv_launch_count(void);
+/* Debug hooks of the attention kernels (tools/attn_timeline.py, tools/attn_ablate.py); both default to off.
+ *   aaconv_debug_set_timeline  device buffer of 12 x 64 int64: CTA-level clock64 stamps of the dQa kernel (NULL = off)
+ *   aaconv_debug_set_mode      ablation bits: 1 no MUFU, 2 no global traffic after the first tiles, 4 no gradient MMAs,
+ *                              8 no math -- results are WRONG when non-zero; timing experiments only                */
+void aaconv_debug_set_timeline(void* device_buffer);
+void aaconv_debug_set_mode(int mode);
 int aaconv_profile_begin(void* stream);
 int aaconv_profile_end(char* names_buf, size_t names_len, float* ms, int max_entries);
 
