@@ -172,14 +172,16 @@ __global__ void __launch_bounds__(CF_THREADS, 1) attn_fwd_cc_kernel(
   const int bn = blockIdx.y, q0 = blockIdx.x * CF_BM;
   const int ntiles = (L + CF_BN - 1) / CF_BN;
 
-  if (threadIdx.x == 0) {
+  if (warp == CF_W_TMA && lane == 0) {   // barrier set-up + the Q tile load before the CTA-wide sync (see cb_init)
     tc::mbar_init(&sm.bar_q, 1);
     tc::mbar_init(&sm.bar_a_ready, 128);
     for (int s = 0; s < ST; ++s) { tc::mbar_init(&sm.bar_full[s], 1); tc::mbar_init(&sm.bar_empty[s], 129); }
     for (int s = 0; s < NS; ++s) { tc::mbar_init(&sm.bar_s_full[s], 1); tc::mbar_init(&sm.bar_slot_free[s], 128); }
     tc::fence_barrier_init();
+    tc::mbar_arrive_expect_tx(&sm.bar_q, KATOMS * CF_BM * 64 * 2);
+    for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.q[a], &tm_q, &sm.bar_q, a * 64, q0, bn);
+    tc::tma_prefetch_desc(&tm_k);
   }
-  if (warp == CF_W_TMA && lane == 0) { tc::tma_prefetch_desc(&tm_q); tc::tma_prefetch_desc(&tm_k); }
   if (warp == CF_W_S) tc::tmem_alloc<512>(&sm.tmem_base);
   tc::tc_fence_before();
   __syncthreads();
@@ -188,8 +190,6 @@ __global__ void __launch_bounds__(CF_THREADS, 1) attn_fwd_cc_kernel(
 
   if (warp == CF_W_TMA) {
     if (lane == 0) {
-      tc::mbar_arrive_expect_tx(&sm.bar_q, KATOMS * CF_BM * 64 * 2);
-      for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.q[a], &tm_q, &sm.bar_q, a * 64, q0, bn);
       Ring rg;
       for (int j = 0; j < ntiles; ++j, rg.next(ST)) {
         const int s = rg.i;
@@ -316,9 +316,12 @@ struct __align__(1024) CbSmem {
   uint32_t tmem_base;
 };
 
-template <class Smem>
-__device__ __forceinline__ void cb_init(Smem& sm, int warp, int lane, const CUtensorMap* m0, const CUtensorMap* m1) {
-  if (threadIdx.x == 0) {
+// CTA set-up.  The TMA lane initialises the barriers itself and issues the stationary-tile load right away, so that its
+// ~1.4 k cycles of latency run under the TMEM allocation and the CTA-wide sync instead of after them.
+template <int KATOMS, class Smem>
+__device__ __forceinline__ void cb_init(Smem& sm, int warp, int lane, const CUtensorMap* m_stat, const CUtensorMap* m_strm, int row0,
+                                        int bn) {
+  if (warp == CB_W_TMA && lane == 0) {
     tc::mbar_init(&sm.bar_stat, 1);
     tc::mbar_init(&sm.bar_a_ready, 128);
     for (int s = 0; s < CB_STAGES; ++s) { tc::mbar_init(&sm.bar_full[s], 1); tc::mbar_init(&sm.bar_empty[s], 129); }
@@ -329,8 +332,10 @@ __device__ __forceinline__ void cb_init(Smem& sm, int warp, int lane, const CUte
     }
     tc::mbar_init(&sm.bar_final, 1);
     tc::fence_barrier_init();
+    tc::mbar_arrive_expect_tx(&sm.bar_stat, KATOMS * CB_BM * 64 * 2);
+    for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.stat[a], m_stat, &sm.bar_stat, a * 64, row0, bn);
+    tc::tma_prefetch_desc(m_strm);
   }
-  if (warp == CB_W_TMA && lane == 0) { tc::tma_prefetch_desc(m0); tc::tma_prefetch_desc(m1); }
   if (warp == CB_W_S) tc::tmem_alloc<512>(&sm.tmem_base);
   tc::tc_fence_before();
   __syncthreads();
@@ -463,14 +468,12 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dq_cc_kernel(
   const bool rec = tl != nullptr && blockIdx.x == 3 && blockIdx.y == 40 && lane == 0;   // a CTA of a middle wave
 #define CC_STAMP(ev, tile) do { if (rec) tl[(ev) * 64 + (tile)] = clock64(); } while (0)
   if (warp == 0) CC_STAMP(10, 0);
-  cb_init(sm, warp, lane, &tm_q_stat, &tm_k_strm);
+  cb_init<KATOMS>(sm, warp, lane, &tm_q_stat, &tm_k_strm, q0, bn);
   const uint32_t tmem = sm.tmem_base;
   if (warp == 0) CC_STAMP(10, 1);
 
   if (warp == CB_W_TMA) {
     if (lane == 0) {
-      tc::mbar_arrive_expect_tx(&sm.bar_stat, KATOMS * CB_BM * 64 * 2);
-      for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.stat[a], &tm_q_stat, &sm.bar_stat, a * 64, q0, bn);
       Ring rg;
       for (int j = 0; j < ntiles; ++j, rg.next(CB_STAGES)) {
         const int s = rg.i;
@@ -560,17 +563,35 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dq_cc_kernel(
     tc::mbar_wait(&sm.bar_final, 0);
     tc::tc_fence_after();
     if (warp == 0) CC_STAMP(10, 5);
-    for (int c0 = wg * 32; c0 < NQ; c0 += 32 * CB_NWG) {
-      tc::tmem_ld_x32(tlane + COL_DQ + c0, rs[0]);
-      tc::tmem_ld_wait();
-      if (qi < L) {
-        if ((KD & 3) == 0) {
+    if ((KD & 3) == 0) {
+      // dQa tile -> shared memory (the streamed-tile ring is idle now) -> ONE bulk store of nrows x KD contiguous floats.
+      // Direct per-row stores from the accumulator layout (lane = row, 400-byte row pitch) cost ~3.8 k cycles per CTA.
+      float* stage = reinterpret_cast<float*>(&sm.strm[0][0][0]);
+      static_assert(sizeof(sm.strm) >= CB_BM * KATOMS * 64 * 4, "dQa staging tile must fit in the stream ring");
+      for (int c0 = wg * 32; c0 < NQ; c0 += 32 * CB_NWG) {
+        tc::tmem_ld_x32(tlane + COL_DQ + c0, rs[0]);
+        tc::tmem_ld_wait();
+        const uint32_t dst = smem_u32(stage + rowi * KD + c0);
 #pragma unroll
-          for (int e = 0; e < 32; e += 4)
-            if (c0 + e < KD)
-              *reinterpret_cast<float4*>(dqa + row * KD + c0 + e) =
-                  make_float4(__uint_as_float(rs[0][e]), __uint_as_float(rs[0][e + 1]), __uint_as_float(rs[0][e + 2]), __uint_as_float(rs[0][e + 3]));
-        } else {
+        for (int e = 0; e < 32; e += 4)
+          if (c0 + e < KD)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + e * 4), "r"(rs[0][e]), "r"(rs[0][e + 1]),
+                         "r"(rs[0][e + 2]), "r"(rs[0][e + 3]) : "memory");
+      }
+      tc::fence_proxy_async();
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * CB_NWG) : "memory");
+      if (threadIdx.x == 0) {
+        const int nrows = min(CB_BM, L - q0);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dqa + ((size_t)bn * L + q0) * KD),
+                     "r"(smem_u32(stage)), "r"((uint32_t)(nrows * KD * 4)) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+    } else {
+      for (int c0 = wg * 32; c0 < NQ; c0 += 32 * CB_NWG) {
+        tc::tmem_ld_x32(tlane + COL_DQ + c0, rs[0]);
+        tc::tmem_ld_wait();
+        if (qi < L) {
 #pragma unroll
           for (int e = 0; e < 32; ++e)
             if (c0 + e < KD) dqa[row * KD + c0 + e] = __uint_as_float(rs[0][e]);
@@ -603,13 +624,11 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
   const uint32_t COL_SLOT0 = KATOMS * 32, COL_DK = COL_SLOT0 + 64 * NS;
   __shared__ float dv_xch[CB_NWG - 1][CB_BM][DVH];     // dV partials of warpgroups 1.. (dV = P^T dO is accumulated in registers)
 
-  cb_init(sm, warp, lane, &tm_k_stat, &tm_q_strm);
+  cb_init<KATOMS>(sm, warp, lane, &tm_k_stat, &tm_q_strm, k0, bn);
   const uint32_t tmem = sm.tmem_base;
 
   if (warp == CB_W_TMA) {
     if (lane == 0) {
-      tc::mbar_arrive_expect_tx(&sm.bar_stat, KATOMS * CB_BM * 64 * 2);
-      for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.stat[a], &tm_k_stat, &sm.bar_stat, a * 64, k0, bn);
       Ring rg;
       for (int j = 0; j < ntiles; ++j, rg.next(CB_STAGES)) {
         const int s = rg.i;

@@ -119,57 +119,77 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_tc_kernel(const __gr
     }
   } else {
     // ===================== epilogue: thread == tile pixel == TMEM lane; chunk c as soon as its MMAs are done =====================
+    // One epilogue warp per scheduler: nothing hides instruction latency, so every store is one pointer bump + STG -- the
+    // job's geometry is copied to registers once (p is selected by blockIdx.y: its fields are indexed constant loads)
+    // and per-channel addresses advance by a precomputed stride (profiles/r01_c_head.md: ~30 dependent instructions per
+    // store made this epilogue 5x longer than the MMAs of the CTA).
     const int m = threadIdx.x;                       // 0..127
-    const int hh = m / p.Wt, ww = m - hh * p.Wt;
+    const int Wt = p.Wt, nchunks = p.nchunks;
+    const int hh = m / Wt, ww = m - hh * Wt;
     const int hrow = h0 + hh;
-    const bool valid = m < p.r * p.Wt && hrow < p.Ht;
+    const bool valid = m < p.r * Wt && hrow < p.Ht;
     const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
     uint32_t rr[32];
     if (p.mode == 0) {
+      const int L = p.L, Cc = p.Cc, Nqkv = p.Nqkv, dk = p.dk, dkh = p.dkh, dvh = p.dvh, nh = p.nh;
+      const float qscale = p.qscale;
       const int l = hrow * p.W + ww;
-      const bool vec = (p.dkh & 3) == 0;             // aligned groups of 4 columns never straddle a head
-      for (int c = 0; c < p.nchunks; ++c) {
+      const bool vec = (dkh & 3) == 0;               // aligned groups of 4 columns never straddle a head
+      float* const ybase = p.out0 + (size_t)b * p.Cout * L + l;
+      const size_t hs = (size_t)L * dkh;             // head stride of q / k
+      float* const qbase = p.q + ((size_t)b * nh * L + l) * dkh;
+      float* const kbase = p.k + ((size_t)b * nh * L + l) * dkh;
+      float* const vbase = p.v + ((size_t)b * nh * L + l) * dvh;
+      for (int c = 0; c < nchunks; ++c) {
         const PGChunk ch = p.chunks[c];
         tc::mbar_wait(&sm.bar_acc[c], 0);
         tc::tc_fence_after();
         for (int cb = 0; cb < 4; ++cb) {
-          if (ch.n0 + cb * 32 >= (ch.kind == 0 ? p.Cc : p.Nqkv)) break;   // uniform
+          const int nb = ch.n0 + cb * 32;
+          if (nb >= (ch.kind == 0 ? Cc : Nqkv)) break;   // uniform
           tc::tmem_ld_x32(tlane + c * 128 + cb * 32, rr);
           tc::tmem_ld_wait();
           if (!valid) continue;
           if (ch.kind == 0) {                        // conv channels -> y NCHW (lanes = consecutive pixels: coalesced)
+            float* dst = ybase + (size_t)nb * L;
+            if (nb + 32 <= Cc) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const int n = ch.n0 + cb * 32 + e;
-              if (n < p.Cc) p.out0[((size_t)b * p.Cout + n) * p.L + l] = __uint_as_float(rr[e]);
+              for (int e = 0; e < 32; ++e, dst += L) *dst = __uint_as_float(rr[e]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e, dst += L)
+                if (nb + e < Cc) *dst = __uint_as_float(rr[e]);
             }
-          } else {                                   // qkv channels -> head-split q (scaled), k, v
+          } else if (vec && (nb + 32 <= dk || (nb >= dk && nb + 32 <= 2 * dk))) {
+            // 32 columns inside q or inside k: float4 groups walk the heads with a running (head, dim) position
+            const bool isq = nb < dk;
+            const int cc0 = isq ? nb : nb - dk;
+            const int hd0 = cc0 / dkh;
+            int ee = cc0 - hd0 * dkh;
+            float* dst = (isq ? qbase : kbase) + (size_t)hd0 * hs + ee;
+            const float sc = isq ? qscale : 1.f;
 #pragma unroll
             for (int e4 = 0; e4 < 32; e4 += 4) {
-              const int n = ch.n0 + cb * 32 + e4;
-              if (vec && n + 3 < 2 * p.dk) {         // whole group inside q or inside k
-                const bool isq = n < p.dk;
-                const int cc = isq ? n : n - p.dk, hd = cc / p.dkh, ee = cc - hd * p.dkh;
-                const float sc = isq ? p.qscale : 1.f;
-                float* dst = (isq ? p.q : p.k) + ((size_t)(b * p.nh + hd) * p.L + l) * p.dkh + ee;
-                *reinterpret_cast<float4*>(dst) = make_float4(__uint_as_float(rr[e4]) * sc, __uint_as_float(rr[e4 + 1]) * sc,
-                                                              __uint_as_float(rr[e4 + 2]) * sc, __uint_as_float(rr[e4 + 3]) * sc);
-              } else {
+              *reinterpret_cast<float4*>(dst) = make_float4(__uint_as_float(rr[e4]) * sc, __uint_as_float(rr[e4 + 1]) * sc,
+                                                            __uint_as_float(rr[e4 + 2]) * sc, __uint_as_float(rr[e4 + 3]) * sc);
+              ee += 4;
+              dst += 4;
+              if (ee >= dkh) { ee = 0; dst += hs - dkh; }
+            }
+          } else {                                   // generic: q (scaled) | k | v, element by element
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int nn = n + j;
-                  const float val = __uint_as_float(rr[e4 + j]);
-                  if (nn < p.dk) {
-                    const int hd = nn / p.dkh, ee = nn - hd * p.dkh;
-                    p.q[((size_t)(b * p.nh + hd) * p.L + l) * p.dkh + ee] = val * p.qscale;
-                  } else if (nn < 2 * p.dk) {
-                    const int cc = nn - p.dk, hd = cc / p.dkh, ee = cc - hd * p.dkh;
-                    p.k[((size_t)(b * p.nh + hd) * p.L + l) * p.dkh + ee] = val;
-                  } else if (nn < p.Nqkv) {
-                    const int cc = nn - 2 * p.dk, hd = cc / p.dvh, ee = cc - hd * p.dvh;
-                    p.v[((size_t)(b * p.nh + hd) * p.L + l) * p.dvh + ee] = val;
-                  }
-                }
+            for (int e = 0; e < 32; ++e) {
+              const int nn = nb + e;
+              const float val = __uint_as_float(rr[e]);
+              if (nn < dk) {
+                const int hd = nn / dkh, ed = nn - hd * dkh;
+                qbase[(size_t)hd * hs + ed] = val * qscale;
+              } else if (nn < 2 * dk) {
+                const int cc = nn - dk, hd = cc / dkh, ed = cc - hd * dkh;
+                kbase[(size_t)hd * hs + ed] = val;
+              } else if (nn < Nqkv) {
+                const int cc = nn - 2 * dk, hd = cc / dvh, ed = cc - hd * dvh;
+                vbase[(size_t)hd * L * dvh + ed] = val;
               }
             }
           }
@@ -179,55 +199,65 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_tc_kernel(const __gr
       // dgrad: chunks come in pairs (2i, 2i+1) = the two column-parity classes (rw = 0, 1) of the same 128 channels;
       // a thread owns input pixels (hi, 2*ww) and (hi, 2*ww+1) -> one 8-byte store per channel, fully coalesced rows.
       // With stride 1 (pair == 0) every chunk is its own class.
-      const int hi = hrow * p.stride + p.rh;
-      const bool v0 = valid && hi < p.Hin && ww * p.stride + p.rw < p.Win;
+      const int Cin = p.Cin, Hin = p.Hin, Win = p.Win, stride = p.stride;
+      const size_t plane = (size_t)Hin * Win;
+      const int hi = hrow * stride + p.rh;
+      const bool v0 = valid && hi < Hin && ww * stride + p.rw < Win;
       if (p.pair) {
         const int wi = ww * 2;
-        const bool v1 = valid && hi < p.Hin && wi + 1 < p.Win;
-        const bool vec2 = (p.Win & 1) == 0;
+        const bool v1 = valid && hi < Hin && wi + 1 < Win;
+        const bool vec2 = (Win & 1) == 0;
+        float* const base = p.out0 + (size_t)b * Cin * plane + (size_t)hi * Win + wi;
         uint32_t r2[32];
-        for (int c = 0; c < p.nchunks; c += 2) {
-          const PGChunk ch = p.chunks[c];
+        for (int c = 0; c < nchunks; c += 2) {
+          const int n0 = p.chunks[c].n0;
           tc::mbar_wait(&sm.bar_acc[c], 0);
           tc::mbar_wait(&sm.bar_acc[c + 1], 0);
           tc::tc_fence_after();
           for (int cb = 0; cb < 4; ++cb) {
-            if (ch.n0 + cb * 32 >= p.Cin) break;
+            const int nb = n0 + cb * 32;
+            if (nb >= Cin) break;
             tc::tmem_ld_x32(tlane + c * 128 + cb * 32, rr);
             tc::tmem_ld_x32(tlane + (c + 1) * 128 + cb * 32, r2);
             tc::tmem_ld_wait();
             if (!v0) continue;
+            float* dst = base + (size_t)nb * plane;
+            if (vec2 && nb + 32 <= Cin) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const int n = ch.n0 + cb * 32 + e;
-              if (n < p.Cin) {
-                float* dst = p.out0 + (((size_t)b * p.Cin + n) * p.Hin + hi) * p.Win + wi;
-                if (vec2) {
-                  *reinterpret_cast<float2*>(dst) = make_float2(__uint_as_float(rr[e]), __uint_as_float(r2[e]));
-                } else {
-                  dst[0] = __uint_as_float(rr[e]);
-                  if (v1) dst[1] = __uint_as_float(r2[e]);
+              for (int e = 0; e < 32; ++e, dst += plane)
+                *reinterpret_cast<float2*>(dst) = make_float2(__uint_as_float(rr[e]), __uint_as_float(r2[e]));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e, dst += plane) {
+                if (nb + e < Cin) {
+                  if (vec2) {
+                    *reinterpret_cast<float2*>(dst) = make_float2(__uint_as_float(rr[e]), __uint_as_float(r2[e]));
+                  } else {
+                    dst[0] = __uint_as_float(rr[e]);
+                    if (v1) dst[1] = __uint_as_float(r2[e]);
+                  }
                 }
               }
             }
           }
         }
       } else {
-        const int wi = ww * p.stride + p.rw;
-        for (int c = 0; c < p.nchunks; ++c) {
-          const PGChunk ch = p.chunks[c];
+        const int wi = ww * stride + p.rw;
+        float* const base = p.out0 + (size_t)b * Cin * plane + (size_t)hi * Win + wi;
+        for (int c = 0; c < nchunks; ++c) {
+          const int n0 = p.chunks[c].n0;
           tc::mbar_wait(&sm.bar_acc[c], 0);
           tc::tc_fence_after();
           for (int cb = 0; cb < 4; ++cb) {
-            if (ch.n0 + cb * 32 >= p.Cin) break;
+            const int nb = n0 + cb * 32;
+            if (nb >= Cin) break;
             tc::tmem_ld_x32(tlane + c * 128 + cb * 32, rr);
             tc::tmem_ld_wait();
             if (!v0) continue;
+            float* dst = base + (size_t)nb * plane;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const int n = ch.n0 + cb * 32 + e;
-              if (n < p.Cin) p.out0[(((size_t)b * p.Cin + n) * p.Hin + hi) * p.Win + wi] = __uint_as_float(rr[e]);
-            }
+            for (int e = 0; e < 32; ++e, dst += plane)
+              if (nb + e < Cin) *dst = __uint_as_float(rr[e]);
           }
         }
       }
