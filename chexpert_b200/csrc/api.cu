@@ -6,6 +6,9 @@ namespace aaconv {
 int bce_launch(const float* z, const float* targets, int ld, const int32_t* cols, int B, int C, float* el,
                float* loss, float* dz, const float* grad_scale, cudaStream_t st);
 
+int ensemble_mean_launch(const float* logits, int M, size_t n, float* mean, cudaStream_t st);
+int auroc_launch(const float* z, const float* t, int N, int C, float* auroc, void* workspace, cudaStream_t st);
+
 static int validate(const aaconv_dims* dd, int precision) {
   if (!dd) return fail(AACONV_E_ARG, "dims is NULL");
   const aaconv_dims& d = *dd;
@@ -74,6 +77,18 @@ int aaconv_bce_forward_backward(const float* z, const float* targets, int ld, co
                                 float* element_loss, float* loss, float* dz, const float* grad_scale, void* stream) {
   if (!z || !targets || B <= 0 || C <= 0 || ld < (cols ? 1 : C)) return fail(AACONV_E_ARG, "bad BCE arguments");
   return bce_launch(z, targets, ld, cols, B, C, element_loss, loss, dz, grad_scale, static_cast<cudaStream_t>(stream));
+}
+
+int aaconv_ensemble_mean(const float* logits, int n_models, int N, int C, float* mean, void* stream) {
+  if (!logits || !mean || n_models <= 0 || N <= 0 || C <= 0) return fail(AACONV_E_ARG, "bad ensemble_mean arguments");
+  return ensemble_mean_launch(logits, n_models, (size_t)N * C, mean, static_cast<cudaStream_t>(stream));
+}
+
+size_t aaconv_auroc_workspace_bytes(int C) { return C > 0 ? align256(sizeof(unsigned long long) * 3 * (size_t)C) : 0; }
+
+int aaconv_auroc(const float* logits, const float* targets, int N, int C, float* auroc, void* workspace, void* stream) {
+  if (!logits || !targets || !auroc || !workspace || N <= 0 || C <= 0 || C > 1024) return fail(AACONV_E_ARG, "bad auroc arguments");
+  return auroc_launch(logits, targets, N, C, auroc, workspace, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

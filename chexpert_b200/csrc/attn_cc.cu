@@ -10,6 +10,7 @@
 // slot to the S' columns alone, so that four slots fit in TMEM and the issuing warps run far enough ahead of the math
 // warpgroups to keep both busy.  v / dO / delta tiles come as fp32 through 1-D bulk copies on the K/Q tile's barrier.
 // Reference rows a3-a8 (attn_aug_conv.py:75-91) and their adjoint; layouts as in attn_tc_bwd.cu.
+#include <algorithm>
 #include "tc_common.cuh"
 #include "bf16_path.cuh"
 
@@ -21,7 +22,6 @@ typedef __nv_bfloat16 bf16;
 // ablation switches for tools/attn_ablate.py (0 in production): 1 no MUFU, 2 no global traffic after the first tiles,
 // 4 no gradient MMAs, 8 no math at all
 int g_attn_dbg_mode = 0;
-extern long long* g_attn_dbg;      // attn_tc_bwd.cu: timeline buffer (tools/attn_timeline.py)
 extern "C" void aaconv_debug_set_mode(int m) { g_attn_dbg_mode = m; }
 
 namespace {
@@ -119,12 +119,28 @@ __device__ __forceinline__ void fwd_cc_half(uint32_t (&r)[2][32], uint32_t vt, i
 }
 
 // ================================================================================================
+// Persistent CTAs.  One CTA per SM walks a static list of work items (item = blockIdx.x + i * gridDim.x; an item is one
+// stationary tile of one (batch, head) pair).  All rings (streamed-tile stages, TMEM score slots, warpgroup rotation)
+// run on a GLOBAL tile counter across items, so the TMA warp streams the next item's tiles while the math warpgroups
+// finish the current one, the stationary operand is double-buffered in TMEM, and the only per-item serial work left is
+// the accumulator drain.  Measured before (profiles/r01_c_head.md + tools/attn_timeline.py): one CTA per item spent
+// ~2.4 k cycles before its first MMA, ~4 k after its last and ~5 k between CTAs, out of ~30 k per item.
+// ================================================================================================
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ================================================================================================
 // forward
 // ================================================================================================
 constexpr int CF_BM = 128, CF_BN = 128, CF_SLOTS = 3;
-// three softmax warpgroups (tile j -> warpgroup j % 3), one TMA warp, one score-MMA issuer (+TMEM alloc)
+// three softmax warpgroups (global tile t -> warpgroup t % 3), one TMA warp, one score-MMA issuer (+TMEM alloc)
 constexpr int CF_NWG = 3, CF_W_TMA = 4 * CF_NWG, CF_W_S = CF_W_TMA + 1, CF_THREADS = 32 * (CF_W_S + 1);
 template <int KATOMS> struct CfStages { static constexpr int value = KATOMS >= 3 ? 3 : 4; };
+// Qa buffers in TMEM: two when they fit next to the three 128-column score slots
+template <int KATOMS> struct CfQBuf { static constexpr int value = (2 * KATOMS * 32 + CF_SLOTS * 128 <= 512) ? 2 : 1; };
 
 template <int KATOMS, int DVH>
 struct __align__(1024) CfSmem {
@@ -132,52 +148,63 @@ struct __align__(1024) CfSmem {
   bf16 q[KATOMS][CF_BM * 64];
   bf16 k[ST][KATOMS][CF_BN * 64];
   float vt[ST][CF_BN * DVH];                  // fp32 values of the key tile
-  float xch[CF_NWG - 1][CF_BM][4];            // WG1.. -> WG0 hand-over of (m, l, o[0..DVH))
-  uint64_t bar_q, bar_a_ready, bar_full[ST], bar_empty[ST], bar_s_full[CF_SLOTS], bar_slot_free[CF_SLOTS];
+  float xch[2][CF_NWG - 1][CF_BM][4];         // WG1.. -> WG0 hand-over of (m, l, o[0..DVH)), double-buffered by item parity
+  uint64_t bar_q, bar_q_free, bar_a_ready, bar_final, bar_full[ST], bar_empty[ST], bar_s_full[CF_SLOTS], bar_slot_free[CF_SLOTS];
   uint32_t tmem_base;
 };
 
 template <int KATOMS, int NKS, class Smem>
-__device__ __forceinline__ void cf_score_loop(Smem& sm, uint32_t tmem, int ntiles) {
-  constexpr int ST = Smem::ST, NS = CF_SLOTS;
-  constexpr uint32_t COL_SLOT0 = KATOMS * 32;
+__device__ __forceinline__ void cf_score_loop(Smem& sm, uint32_t tmem, int ntiles, int my_items) {
+  constexpr int ST = Smem::ST, NS = CF_SLOTS, QB = CfQBuf<KATOMS>::value;
+  constexpr uint32_t COL_SLOT0 = QB * KATOMS * 32;
   constexpr uint32_t idesc_s = tc::idesc_bf16_f32(CF_BM, CF_BN);
   constexpr uint32_t K_ATOM = (CF_BN * 128) >> 4, K_STAGE = KATOMS * K_ATOM;
   const uint32_t k_lo = tc::desc_lo_k(smem_u32(sm.k[0][0]));
   Ring rst, rsl;
-  for (int j = 0; j < ntiles; ++j, rst.next(ST), rsl.next(NS)) {
-    const int st = rst.i, slot = rsl.i;
-    tc::mbar_wait(&sm.bar_full[st], rst.ph);
-    if (j >= NS) tc::mbar_wait(&sm.bar_slot_free[slot], rsl.ph ^ 1);
+  int filled = 0;                                // the first NS tiles find their slot free
+  for (int it = 0; it < my_items; ++it) {
+    tc::mbar_wait(&sm.bar_a_ready, it & 1);
     tc::tc_fence_after();
-    if (tc::elect_one()) {
-      tc::issue_ts_ksteps<NKS, 0, K_ATOM>(tmem + COL_SLOT0 + 128 * slot, 0u, tmem, k_lo + st * K_STAGE, idesc_s);
-      tc::mma_commit(&sm.bar_s_full[slot]);
-      tc::mma_commit(&sm.bar_empty[st]);        // the K tile is free once these MMAs are done (+128 arrivals for vt)
+    const uint32_t qa = tmem + (uint32_t)((it & (QB - 1)) * KATOMS * 32);
+    for (int j = 0; j < ntiles; ++j, rst.next(ST), rsl.next(NS)) {
+      const int st = rst.i, slot = rsl.i;
+      tc::mbar_wait(&sm.bar_full[st], rst.ph);
+      if (filled >= NS) tc::mbar_wait(&sm.bar_slot_free[slot], rsl.ph ^ 1);
+      else ++filled;
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+        tc::issue_ts_ksteps<NKS, 0, K_ATOM>(tmem + COL_SLOT0 + 128 * slot, 0u, qa, k_lo + st * K_STAGE, idesc_s);
+        tc::mma_commit(&sm.bar_s_full[slot]);
+        tc::mma_commit(&sm.bar_empty[st]);        // the K tile is free once these MMAs are done (+128 arrivals for vt)
+        if (QB == 1 && j == ntiles - 1) tc::mma_commit(&sm.bar_final);   // single Qa buffer: refill only after the item's last MMA
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
 template <int KATOMS, int DVH>
 __global__ void __launch_bounds__(CF_THREADS, 1) attn_fwd_cc_kernel(
     const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, const float* __restrict__ v,
-    float* __restrict__ o, float* __restrict__ lse, int L, int C1, int dbg) {
+    float* __restrict__ o, float* __restrict__ lse, int L, int C1, int nqt, int nitems, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   typedef CfSmem<KATOMS, DVH> Smem;
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int ST = Smem::ST, NS = CF_SLOTS;
-  constexpr uint32_t COL_SLOT0 = KATOMS * 32;
+  constexpr int ST = Smem::ST, NS = CF_SLOTS, QB = CfQBuf<KATOMS>::value;
+  constexpr uint32_t COL_SLOT0 = QB * KATOMS * 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bn = blockIdx.y, q0 = blockIdx.x * CF_BM;
   const int ntiles = (L + CF_BN - 1) / CF_BN;
+  const int my_items = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  if (warp == CF_W_TMA && lane == 0) {   // barrier set-up + the Q tile load before the CTA-wide sync (see cb_init)
+  if (warp == CF_W_TMA && lane == 0) {   // barrier set-up + the first Q tile load before the CTA-wide sync
     tc::mbar_init(&sm.bar_q, 1);
+    tc::mbar_init(&sm.bar_q_free, 128);
     tc::mbar_init(&sm.bar_a_ready, 128);
+    tc::mbar_init(&sm.bar_final, 1);
     for (int s = 0; s < ST; ++s) { tc::mbar_init(&sm.bar_full[s], 1); tc::mbar_init(&sm.bar_empty[s], 129); }
     for (int s = 0; s < NS; ++s) { tc::mbar_init(&sm.bar_s_full[s], 1); tc::mbar_init(&sm.bar_slot_free[s], 128); }
     tc::fence_barrier_init();
+    const int item = blockIdx.x, bn = item / nqt, q0 = (item - bn * nqt) * CF_BM;
     tc::mbar_arrive_expect_tx(&sm.bar_q, KATOMS * CF_BM * 64 * 2);
     for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.q[a], &tm_q, &sm.bar_q, a * 64, q0, bn);
     tc::tma_prefetch_desc(&tm_k);
@@ -191,105 +218,126 @@ __global__ void __launch_bounds__(CF_THREADS, 1) attn_fwd_cc_kernel(
   if (warp == CF_W_TMA) {
     if (lane == 0) {
       Ring rg;
-      for (int j = 0; j < ntiles; ++j, rg.next(ST)) {
-        const int s = rg.i;
-        const int nvalid = min(CF_BN, L - j * CF_BN);
-        tc::mbar_wait(&sm.bar_empty[s], rg.ph ^ 1);
-        tc::mbar_arrive_expect_tx(&sm.bar_full[s], KATOMS * CF_BN * 64 * 2 + nvalid * DVH * 4);
-        for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.k[s][a], &tm_k, &sm.bar_full[s], a * 64, j * CF_BN, bn);
-        bulk_g2s(sm.vt[s], v + ((size_t)bn * L + (size_t)j * CF_BN) * DVH, nvalid * DVH * 4, &sm.bar_full[s]);
+      const int jq = min(1, ntiles - 1);
+      for (int it = 0; it < my_items; ++it) {
+        const int item = blockIdx.x + it * gridDim.x, bn = item / nqt;
+        for (int j = 0; j < ntiles; ++j, rg.next(ST)) {
+          if (j == jq && it + 1 < my_items) {          // next item's Q tile: its staging buffer is free once WG0 has moved
+            const int nitem = item + gridDim.x, nbn = nitem / nqt, nq0 = (nitem - nbn * nqt) * CF_BM;   // this item's to TMEM
+            tc::mbar_wait(&sm.bar_q_free, it & 1);
+            tc::mbar_arrive_expect_tx(&sm.bar_q, KATOMS * CF_BM * 64 * 2);
+            for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.q[a], &tm_q, &sm.bar_q, a * 64, nq0, nbn);
+          }
+          const int s = rg.i;
+          const int nvalid = min(CF_BN, L - j * CF_BN);
+          tc::mbar_wait(&sm.bar_empty[s], rg.ph ^ 1);
+          tc::mbar_arrive_expect_tx(&sm.bar_full[s], KATOMS * CF_BN * 64 * 2 + nvalid * DVH * 4);
+          for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.k[s][a], &tm_k, &sm.bar_full[s], a * 64, j * CF_BN, bn);
+          bulk_g2s(sm.vt[s], v + ((size_t)bn * L + (size_t)j * CF_BN) * DVH, nvalid * DVH * 4, &sm.bar_full[s]);
+        }
       }
     }
   } else if (warp == CF_W_S) {
     const int nks = C1 >> 4;
-    tc::mbar_wait(&sm.bar_a_ready, 0);
-    tc::tc_fence_after();
-    switch (nks) {      // dispatched once, outside the tile loop
-      case 1: cf_score_loop<KATOMS, 1>(sm, tmem, ntiles); break;
-      case 2: cf_score_loop<KATOMS, 2>(sm, tmem, ntiles); break;
-      case 3: cf_score_loop<KATOMS, 3>(sm, tmem, ntiles); break;
-      case 4: cf_score_loop<KATOMS, 4>(sm, tmem, ntiles); break;
-      case 5: cf_score_loop<KATOMS, 5>(sm, tmem, ntiles); break;
-      case 6: cf_score_loop<KATOMS, 6>(sm, tmem, ntiles); break;
-      case 7: cf_score_loop<KATOMS, 7>(sm, tmem, ntiles); break;
-      case 8: cf_score_loop<KATOMS, 8>(sm, tmem, ntiles); break;
-      case 9: cf_score_loop<KATOMS, 9>(sm, tmem, ntiles); break;
-      case 10: cf_score_loop<KATOMS, 10>(sm, tmem, ntiles); break;
-      default: cf_score_loop<KATOMS, 11>(sm, tmem, ntiles); break;
+    switch (nks) {      // dispatched once, outside the loops
+      case 1: cf_score_loop<KATOMS, 1>(sm, tmem, ntiles, my_items); break;
+      case 2: cf_score_loop<KATOMS, 2>(sm, tmem, ntiles, my_items); break;
+      case 3: cf_score_loop<KATOMS, 3>(sm, tmem, ntiles, my_items); break;
+      case 4: cf_score_loop<KATOMS, 4>(sm, tmem, ntiles, my_items); break;
+      case 5: cf_score_loop<KATOMS, 5>(sm, tmem, ntiles, my_items); break;
+      case 6: cf_score_loop<KATOMS, 6>(sm, tmem, ntiles, my_items); break;
+      case 7: cf_score_loop<KATOMS, 7>(sm, tmem, ntiles, my_items); break;
+      case 8: cf_score_loop<KATOMS, 8>(sm, tmem, ntiles, my_items); break;
+      case 9: cf_score_loop<KATOMS, 9>(sm, tmem, ntiles, my_items); break;
+      case 10: cf_score_loop<KATOMS, 10>(sm, tmem, ntiles, my_items); break;
+      default: cf_score_loop<KATOMS, 11>(sm, tmem, ntiles, my_items); break;
     }
   } else {
     // ===================== softmax warpgroups (thread == query row == TMEM lane) =====================
     const int wg = warp >> 2;
     const int rowi = (warp & 3) * 32 + lane;
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    if (wg == 0) {
-      tc::mbar_wait(&sm.bar_q, 0);
-      stationary_to_tmem<KATOMS>(sm.q, tlane, rowi);
+    auto stage_q = [&](int it) {                      // WG0: Q tile of item `it` -> its TMEM buffer
+      tc::mbar_wait(&sm.bar_q, it & 1);
+      stationary_to_tmem<KATOMS>(sm.q, tlane + (uint32_t)((it & (QB - 1)) * KATOMS * 32), rowi);
       tc::mbar_arrive(&sm.bar_a_ready);
-    }
-    float m = -INFINITY, l = 0.f, acc[DVH];
-#pragma unroll
-    for (int e = 0; e < DVH; ++e) acc[e] = 0.f;
+      tc::mbar_arrive(&sm.bar_q_free);
+    };
+    if (wg == 0) stage_q(0);
     uint32_t r[2][32];
     Ring rst, rsl;
-    for (int i = 0; i < wg; ++i) { rst.next(ST); rsl.next(NS); }
-    for (int j = wg; j < ntiles; j += CF_NWG) {
-      const int slot = rsl.i, st = rst.i;
-      const uint32_t tslot = tlane + COL_SLOT0 + 128 * slot;
-      const int nvalid = L - j * CF_BN;           // >= CF_BN for every tile but (possibly) the last
-      const uint32_t vt = smem_u32(sm.vt[st]);
-      tc::mbar_wait(&sm.bar_s_full[slot], rsl.ph);
-      tc::tc_fence_after();
-      tc::tmem_ld_x32(tslot + 0, r[0]);
-      tc::tmem_ld_x32(tslot + 32, r[1]);
-      tc::tmem_ld_wait();
-      if (dbg & 8) l += __uint_as_float(r[0][0]);
-      else if (nvalid < 64) fwd_cc_half<DVH, true>(r, vt, nvalid, m, l, acc);
-      else fwd_cc_half<DVH, false>(r, vt, nvalid, m, l, acc);
-      tc::tmem_ld_x32(tslot + 64, r[0]);
-      tc::tmem_ld_x32(tslot + 96, r[1]);
-      tc::tmem_ld_wait();
-      tc::tc_fence_before();
-      tc::mbar_arrive(&sm.bar_slot_free[slot]);   // all scores of the tile have been read: the slot can be refilled
-      if (dbg & 8) l += __uint_as_float(r[0][0]);
-      else if (nvalid < CF_BN) { if (nvalid > 64) fwd_cc_half<DVH, true>(r, vt + 64 * DVH * 4, nvalid - 64, m, l, acc); }
-      else fwd_cc_half<DVH, false>(r, vt + 64 * DVH * 4, nvalid - 64, m, l, acc);
-      tc::mbar_arrive(&sm.bar_empty[st]);          // value tile consumed
+    int tcur = 0;                                     // global tile index the rings stand at
+    for (int it = 0; it < my_items; ++it) {
+      const int item = blockIdx.x + it * gridDim.x, bn = item / nqt, qt = item - bn * nqt, q0 = qt * CF_BM;
+      float m = -INFINITY, l = 0.f, acc[DVH];
 #pragma unroll
-      for (int i = 0; i < CF_NWG; ++i) { rst.next(ST); rsl.next(NS); }
-    }
-    // ---- merge the warpgroups' partial results ----
-    if (wg > 0) {
-      float* x = sm.xch[wg - 1][rowi];
-      x[0] = m;
-      x[1] = l;
-#pragma unroll
-      for (int e = 0; e < DVH; ++e) x[2 + e] = acc[e];
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(128 * CF_NWG) : "memory");
-    if (wg == 0) {
-      float mm = m;
-#pragma unroll
-      for (int g = 0; g < CF_NWG - 1; ++g) mm = fmaxf(mm, sm.xch[g][rowi][0]);
-      const float a0 = tc::ex2f(m - mm);
-      float lt = a0 * l, ot[DVH];
-#pragma unroll
-      for (int e = 0; e < DVH; ++e) ot[e] = a0 * acc[e];
-#pragma unroll
-      for (int g = 0; g < CF_NWG - 1; ++g) {
-        const float mg = sm.xch[g][rowi][0];
-        const float ag = (mg == -INFINITY) ? 0.f : tc::ex2f(mg - mm);
-        lt = fmaf(ag, sm.xch[g][rowi][1], lt);
-#pragma unroll
-        for (int e = 0; e < DVH; ++e) ot[e] = fmaf(ag, sm.xch[g][rowi][2 + e], ot[e]);
+      for (int e = 0; e < DVH; ++e) acc[e] = 0.f;
+      // tile j of this item belongs to warpgroup (j + qt) % 3: a function of the item alone (results do not depend on
+      // which CTA / in which order the item runs -- batch independence bit for bit), rotating with qt for balance
+      for (int j = (wg + CF_NWG - qt % CF_NWG) % CF_NWG; j < ntiles; j += CF_NWG) {
+        for (const int t = it * ntiles + j; tcur < t; ++tcur) { rst.next(ST); rsl.next(NS); }
+        const int slot = rsl.i, st = rst.i;
+        const uint32_t tslot = tlane + COL_SLOT0 + 128 * slot;
+        const int nvalid = L - j * CF_BN;           // >= CF_BN for every tile but (possibly) the last
+        const uint32_t vt = smem_u32(sm.vt[st]);
+        tc::mbar_wait(&sm.bar_s_full[slot], rsl.ph);
+        tc::tc_fence_after();
+        tc::tmem_ld_x32(tslot + 0, r[0]);
+        tc::tmem_ld_x32(tslot + 32, r[1]);
+        tc::tmem_ld_wait();
+        if (dbg & 8) l += __uint_as_float(r[0][0]);
+        else if (nvalid < 64) fwd_cc_half<DVH, true>(r, vt, nvalid, m, l, acc);
+        else fwd_cc_half<DVH, false>(r, vt, nvalid, m, l, acc);
+        tc::tmem_ld_x32(tslot + 64, r[0]);
+        tc::tmem_ld_x32(tslot + 96, r[1]);
+        tc::tmem_ld_wait();
+        tc::tc_fence_before();
+        tc::mbar_arrive(&sm.bar_slot_free[slot]);   // all scores of the tile have been read: the slot can be refilled
+        if (dbg & 8) l += __uint_as_float(r[0][0]);
+        else if (nvalid < CF_BN) { if (nvalid > 64) fwd_cc_half<DVH, true>(r, vt + 64 * DVH * 4, nvalid - 64, m, l, acc); }
+        else fwd_cc_half<DVH, false>(r, vt + 64 * DVH * 4, nvalid - 64, m, l, acc);
+        tc::mbar_arrive(&sm.bar_empty[st]);          // value tile consumed
       }
-      const int qi = q0 + rowi;
-      if (qi < L) {
-        const float inv = 1.f / lt;
-        const size_t row = (size_t)bn * L + qi;
+      // the next item's Q tile goes to TMEM as early as possible: with two buffers right away (the score issuer then
+      // runs ahead while the warpgroups merge), with one buffer after the item's last score MMA
+      if (wg == 0 && it + 1 < my_items) {
+        if (QB == 1) { tc::mbar_wait(&sm.bar_final, it & 1); tc::tc_fence_after(); }
+        stage_q(it + 1);
+      }
+      // ---- merge the warpgroups' partial results ----
+      float(*xch)[CF_BM][4] = sm.xch[it & 1];
+      if (wg > 0) {
+        float* x = xch[wg - 1][rowi];
+        x[0] = m;
+        x[1] = l;
 #pragma unroll
-        for (int e = 0; e < DVH; ++e) o[row * DVH + e] = ot[e] * inv;
-        lse[row] = (mm + log2f(lt)) * 0.6931471805599453f;
+        for (int e = 0; e < DVH; ++e) x[2 + e] = acc[e];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * CF_NWG) : "memory");
+      if (wg == 0) {
+        float mm = m;
+#pragma unroll
+        for (int g = 0; g < CF_NWG - 1; ++g) mm = fmaxf(mm, xch[g][rowi][0]);
+        const float a0 = tc::ex2f(m - mm);
+        float lt = a0 * l, ot[DVH];
+#pragma unroll
+        for (int e = 0; e < DVH; ++e) ot[e] = a0 * acc[e];
+#pragma unroll
+        for (int g = 0; g < CF_NWG - 1; ++g) {
+          const float mg = xch[g][rowi][0];
+          const float ag = (mg == -INFINITY) ? 0.f : tc::ex2f(mg - mm);
+          lt = fmaf(ag, xch[g][rowi][1], lt);
+#pragma unroll
+          for (int e = 0; e < DVH; ++e) ot[e] = fmaf(ag, xch[g][rowi][2 + e], ot[e]);
+        }
+        const int qi = q0 + rowi;
+        if (qi < L) {
+          const float inv = 1.f / lt;
+          const size_t row = (size_t)bn * L + qi;
+#pragma unroll
+          for (int e = 0; e < DVH; ++e) o[row * DVH + e] = ot[e] * inv;
+          lse[row] = (mm + log2f(lt)) * 0.6931471805599453f;
+        }
       }
     }
   }
@@ -301,37 +349,53 @@ __global__ void __launch_bounds__(CF_THREADS, 1) attn_fwd_cc_kernel(
 // ================================================================================================
 // backward
 // ================================================================================================
-constexpr int CB_BM = 128, CB_BN = 64, CB_STAGES = 6, CB_MAXSLOTS = 4;
-// three math warpgroups (tile j -> warpgroup j % 3): three warps per scheduler keep the MUFU pipe busy while the others sit
+constexpr int CB_BM = 128, CB_BN = 64, CB_MAXSLOTS = 4;
+// three math warpgroups (global tile t -> warpgroup t % 3): three warps per scheduler keep the MUFU pipe busy while the others sit
 // in TMEM load / store / barrier latencies;  then one TMA warp, the score-MMA issuer (+TMEM alloc) and the gradient-MMA issuer
 constexpr int CB_NWG = 3, CB_W_TMA = 4 * CB_NWG, CB_W_S = CB_W_TMA + 1, CB_W_G = CB_W_TMA + 2, CB_THREADS = 32 * (CB_W_G + 1);
+template <int KATOMS> struct CbStages { static constexpr int value = KATOMS >= 3 ? 3 : 6; };
 
-template <int KATOMS, int SIDE_FLOATS>
+// TMEM plan of a backward kernel whose accumulator needs ACC columns: QB stationary buffers, NS score slots of 64 columns
+struct CbPlan { int QB, NS; uint32_t col_slot0, col_acc; };
+__device__ __forceinline__ CbPlan cb_plan(int katoms, int acc_cols) {
+  CbPlan p;
+  p.QB = (512 - 2 * katoms * 32 - acc_cols) / 64 >= 3 ? 2 : 1;
+  p.NS = min(CB_MAXSLOTS, (512 - p.QB * katoms * 32 - acc_cols) / 64);
+  p.col_slot0 = p.QB * katoms * 32;
+  p.col_acc = p.col_slot0 + 64 * p.NS;
+  return p;
+}
+
+template <int KATOMS, int SIDE_FLOATS, int OUT_FLOATS>
 struct __align__(1024) CbSmem {
+  static constexpr int ST = CbStages<KATOMS>::value;
   bf16 stat[KATOMS][CB_BM * 64];
-  bf16 strm[CB_STAGES][KATOMS][CB_BN * 64];
-  float side[CB_STAGES][SIDE_FLOATS];          // fp32 side tile: v (dq kernel) or dO | delta (dkv kernel)
-  uint64_t bar_stat, bar_a_ready, bar_full[CB_STAGES], bar_empty[CB_STAGES];
-  uint64_t bar_s_full[CB_MAXSLOTS], bar_p_ready[CB_MAXSLOTS], bar_slot_free[CB_MAXSLOTS], bar_final;
+  bf16 strm[ST][KATOMS][CB_BN * 64];
+  float side[ST][SIDE_FLOATS];                 // fp32 side tile: v (dq kernel) or dO | delta (dkv kernel)
+  float out[OUT_FLOATS > 0 ? OUT_FLOATS : 4];  // accumulator staging for the bulk store (dq kernel)
+  uint64_t bar_stat, bar_stat_free, bar_a_ready, bar_final, bar_acc_free, bar_full[ST], bar_empty[ST];
+  uint64_t bar_s_full[CB_MAXSLOTS], bar_p_ready[CB_MAXSLOTS], bar_slot_free[CB_MAXSLOTS];
   uint32_t tmem_base;
 };
 
-// CTA set-up.  The TMA lane initialises the barriers itself and issues the stationary-tile load right away, so that its
-// ~1.4 k cycles of latency run under the TMEM allocation and the CTA-wide sync instead of after them.
+// CTA set-up.  The TMA lane initialises the barriers itself and issues the first stationary-tile load right away, so
+// that its latency runs under the TMEM allocation and the CTA-wide sync instead of after them.
 template <int KATOMS, class Smem>
-__device__ __forceinline__ void cb_init(Smem& sm, int warp, int lane, const CUtensorMap* m_stat, const CUtensorMap* m_strm, int row0,
-                                        int bn) {
+__device__ __forceinline__ void cb_init(Smem& sm, int warp, int lane, const CUtensorMap* m_stat, const CUtensorMap* m_strm, int nqt) {
   if (warp == CB_W_TMA && lane == 0) {
     tc::mbar_init(&sm.bar_stat, 1);
+    tc::mbar_init(&sm.bar_stat_free, 128);
     tc::mbar_init(&sm.bar_a_ready, 128);
-    for (int s = 0; s < CB_STAGES; ++s) { tc::mbar_init(&sm.bar_full[s], 1); tc::mbar_init(&sm.bar_empty[s], 129); }
+    tc::mbar_init(&sm.bar_final, 1);
+    tc::mbar_init(&sm.bar_acc_free, 128 * CB_NWG);
+    for (int s = 0; s < Smem::ST; ++s) { tc::mbar_init(&sm.bar_full[s], 1); tc::mbar_init(&sm.bar_empty[s], 129); }
     for (int s = 0; s < CB_MAXSLOTS; ++s) {
       tc::mbar_init(&sm.bar_s_full[s], 1);
       tc::mbar_init(&sm.bar_p_ready[s], 128);
       tc::mbar_init(&sm.bar_slot_free[s], 1);
     }
-    tc::mbar_init(&sm.bar_final, 1);
     tc::fence_barrier_init();
+    const int item = blockIdx.x, bn = item / nqt, row0 = (item - bn * nqt) * CB_BM;
     tc::mbar_arrive_expect_tx(&sm.bar_stat, KATOMS * CB_BM * 64 * 2);
     for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.stat[a], m_stat, &sm.bar_stat, a * 64, row0, bn);
     tc::tma_prefetch_desc(m_strm);
@@ -342,48 +406,106 @@ __device__ __forceinline__ void cb_init(Smem& sm, int warp, int lane, const CUte
   tc::tc_fence_after();
 }
 
+// TMA producer of both backward kernels: per item the stationary tile (once its staging buffer is free), then the streamed
+// tiles with their fp32 side rows (side0: SW0 floats per row, side1: SW1 floats per row or NULL)
+template <int KATOMS, class Smem>
+__device__ __forceinline__ void cb_producer(Smem& sm, const CUtensorMap* m_stat, const CUtensorMap* m_strm, const float* side0,
+                                            int SW0, const float* side1, int SW1, int L, int nqt, int ntiles, int my_items, int dbg) {
+  Ring rg;
+  const int jq = min(1, ntiles - 1);
+  for (int it = 0; it < my_items; ++it) {
+    const int item = blockIdx.x + it * gridDim.x, bn = item / nqt;
+    for (int j = 0; j < ntiles; ++j, rg.next(Smem::ST)) {
+      if (j == jq && it + 1 < my_items) {              // next item's stationary tile: the staging buffer is free once WG0
+        const int nitem = item + gridDim.x, nbn = nitem / nqt, nrow0 = (nitem - nbn * nqt) * CB_BM;   // has moved this item's to TMEM
+        tc::mbar_wait(&sm.bar_stat_free, it & 1);
+        tc::mbar_arrive_expect_tx(&sm.bar_stat, KATOMS * CB_BM * 64 * 2);
+        for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.stat[a], m_stat, &sm.bar_stat, a * 64, nrow0, nbn);
+      }
+      const int s = rg.i;
+      const int nvalid = min(CB_BN, L - j * CB_BN);
+      const size_t r0 = (size_t)bn * L + (size_t)j * CB_BN;
+      tc::mbar_wait(&sm.bar_empty[s], rg.ph ^ 1);
+      if ((dbg & 2) && (it > 0 || j >= Smem::ST)) { tc::mbar_arrive(&sm.bar_full[s]); continue; }     // ablation: no global traffic
+      tc::mbar_arrive_expect_tx(&sm.bar_full[s], KATOMS * CB_BN * 64 * 2 + nvalid * (SW0 + SW1) * 4);
+      for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.strm[s][a], m_strm, &sm.bar_full[s], a * 64, j * CB_BN, bn);
+      bulk_g2s(sm.side[s], side0 + r0 * SW0, nvalid * SW0 * 4, &sm.bar_full[s]);
+      if (SW1) bulk_g2s(sm.side[s] + CB_BN * SW0, side1 + r0 * SW1, nvalid * SW1 * 4, &sm.bar_full[s]);
+    }
+  }
+}
+
 template <int KATOMS, int NKS, class Smem>
-__device__ __forceinline__ void cb_score_loop(Smem& sm, uint32_t tmem, uint32_t col_slot0, int NS, int ntiles, long long* tl) {
+__device__ __forceinline__ void cb_score_loop(Smem& sm, uint32_t tmem, CbPlan pl, int ntiles, int my_items) {
   constexpr uint32_t idesc_s = tc::idesc_bf16_f32(CB_BM, CB_BN);
   constexpr uint32_t STRM_ATOM = (CB_BN * 128) >> 4, STAGE = KATOMS * STRM_ATOM;
   const uint32_t strm_lo = tc::desc_lo_k(smem_u32(sm.strm[0][0]));
+  const int NS = pl.NS;
   Ring rst, rsl;
-  for (int j = 0; j < ntiles; ++j, rst.next(CB_STAGES), rsl.next(NS)) {
-    const int st = rst.i, slot = rsl.i;
-    if (tl) tl[8 * 64 + j] = clock64();
-    tc::mbar_wait(&sm.bar_full[st], rst.ph);
-    if (tl) tl[0 * 64 + j] = clock64();
-    if (j >= NS) tc::mbar_wait(&sm.bar_slot_free[slot], rsl.ph ^ 1);
+  int filled = 0;
+  for (int it = 0; it < my_items; ++it) {
+    tc::mbar_wait(&sm.bar_a_ready, it & 1);
     tc::tc_fence_after();
-    if (tl) tl[9 * 64 + j] = clock64();
-    if (tc::elect_one()) {
-      tc::issue_ts_ksteps<NKS, 0, STRM_ATOM>(tmem + col_slot0 + 64 * slot, 0u, tmem, strm_lo + st * STAGE, idesc_s);
-      tc::mma_commit(&sm.bar_s_full[slot]);
+    const uint32_t a_tmem = tmem + (uint32_t)((it & (pl.QB - 1)) * KATOMS * 32);
+    for (int j = 0; j < ntiles; ++j, rst.next(Smem::ST), rsl.next(NS)) {
+      const int st = rst.i, slot = rsl.i;
+      tc::mbar_wait(&sm.bar_full[st], rst.ph);
+      if (filled >= NS) tc::mbar_wait(&sm.bar_slot_free[slot], rsl.ph ^ 1);
+      else ++filled;
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+        tc::issue_ts_ksteps<NKS, 0, STRM_ATOM>(tmem + pl.col_slot0 + 64 * slot, 0u, a_tmem, strm_lo + st * STAGE, idesc_s);
+        tc::mma_commit(&sm.bar_s_full[slot]);
+      }
+      __syncwarp();
     }
-    __syncwarp();
-    if (tl) tl[1 * 64 + j] = clock64();
   }
 }
-// score-MMA issuer shared by both backward kernels: S'(j) -> slot j % NS as soon as the K/Q tile has landed and the
-// slot's previous gradient MMAs are done.  The k-step count is dispatched ONCE, outside the tile loop (an indirect
+// score-MMA issuer shared by both backward kernels: S'(t) -> slot t % NS as soon as the K/Q tile has landed and the
+// slot's previous gradient MMAs are done.  The k-step count is dispatched ONCE, outside the loops (an indirect
 // branch per tile costs hundreds of cycles on the issuing warp, which is the critical resource).
 template <int KATOMS, class Smem>
-__device__ __forceinline__ void cb_score_issuer(Smem& sm, uint32_t tmem, uint32_t col_slot0, int NS, int nks, int ntiles,
-                                                long long* tl = nullptr) {
-  tc::mbar_wait(&sm.bar_a_ready, 0);
-  tc::tc_fence_after();
+__device__ __forceinline__ void cb_score_issuer(Smem& sm, uint32_t tmem, CbPlan pl, int nks, int ntiles, int my_items) {
   switch (nks) {
-    case 1: cb_score_loop<KATOMS, 1>(sm, tmem, col_slot0, NS, ntiles, tl); break;
-    case 2: cb_score_loop<KATOMS, 2>(sm, tmem, col_slot0, NS, ntiles, tl); break;
-    case 3: cb_score_loop<KATOMS, 3>(sm, tmem, col_slot0, NS, ntiles, tl); break;
-    case 4: cb_score_loop<KATOMS, 4>(sm, tmem, col_slot0, NS, ntiles, tl); break;
-    case 5: cb_score_loop<KATOMS, 5>(sm, tmem, col_slot0, NS, ntiles, tl); break;
-    case 6: cb_score_loop<KATOMS, 6>(sm, tmem, col_slot0, NS, ntiles, tl); break;
-    case 7: cb_score_loop<KATOMS, 7>(sm, tmem, col_slot0, NS, ntiles, tl); break;
-    case 8: cb_score_loop<KATOMS, 8>(sm, tmem, col_slot0, NS, ntiles, tl); break;
-    case 9: cb_score_loop<KATOMS, 9>(sm, tmem, col_slot0, NS, ntiles, tl); break;
-    case 10: cb_score_loop<KATOMS, 10>(sm, tmem, col_slot0, NS, ntiles, tl); break;
-    default: cb_score_loop<KATOMS, 11>(sm, tmem, col_slot0, NS, ntiles, tl); break;
+    case 1: cb_score_loop<KATOMS, 1>(sm, tmem, pl, ntiles, my_items); break;
+    case 2: cb_score_loop<KATOMS, 2>(sm, tmem, pl, ntiles, my_items); break;
+    case 3: cb_score_loop<KATOMS, 3>(sm, tmem, pl, ntiles, my_items); break;
+    case 4: cb_score_loop<KATOMS, 4>(sm, tmem, pl, ntiles, my_items); break;
+    case 5: cb_score_loop<KATOMS, 5>(sm, tmem, pl, ntiles, my_items); break;
+    case 6: cb_score_loop<KATOMS, 6>(sm, tmem, pl, ntiles, my_items); break;
+    case 7: cb_score_loop<KATOMS, 7>(sm, tmem, pl, ntiles, my_items); break;
+    case 8: cb_score_loop<KATOMS, 8>(sm, tmem, pl, ntiles, my_items); break;
+    case 9: cb_score_loop<KATOMS, 9>(sm, tmem, pl, ntiles, my_items); break;
+    case 10: cb_score_loop<KATOMS, 10>(sm, tmem, pl, ntiles, my_items); break;
+    default: cb_score_loop<KATOMS, 11>(sm, tmem, pl, ntiles, my_items); break;
+  }
+}
+
+// gradient-MMA issuer shared by both backward kernels: acc (+)= dS(t)[TMEM slot] . streamed tile (MN-major view), N = n_acc
+template <int KATOMS, class Smem>
+__device__ __forceinline__ void cb_grad_issuer(Smem& sm, uint32_t tmem, CbPlan pl, uint32_t idesc, int ntiles, int my_items, int dbg) {
+  constexpr uint32_t STRM_ATOM = (CB_BN * 128) >> 4, STAGE = KATOMS * STRM_ATOM;
+  const uint32_t b_lo = tc::desc_lo_mn(smem_u32(sm.strm[0][0]), CB_BN * 128);
+  const int NS = pl.NS;
+  Ring rst, rsl;
+  for (int it = 0; it < my_items; ++it) {
+    for (int jj = 0; jj < ntiles; ++jj, rst.next(Smem::ST), rsl.next(NS)) {
+      const int st = rst.i, slot = rsl.i;
+      const uint32_t tslot = tmem + pl.col_slot0 + 64 * slot;
+      tc::mbar_wait(&sm.bar_p_ready[slot], rsl.ph);
+      if (jj == 0 && it > 0) tc::mbar_wait(&sm.bar_acc_free, (it - 1) & 1);   // previous item's accumulator has been drained
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+        const uint32_t bb = b_lo + st * STAGE;
+#pragma unroll
+        for (int ks = 0; ks < CB_BN / 16; ++ks)
+          if (!(dbg & 4) || jj == 0) tc::mma_ts(tmem + pl.col_acc, tslot + ks * 8, tc::desc64(bb + ks * 128), idesc, (jj > 0 || ks > 0) ? 1u : 0u);
+        tc::mma_commit(&sm.bar_empty[st]);
+        tc::mma_commit(&sm.bar_slot_free[slot]);
+        if (jj == ntiles - 1) tc::mma_commit(&sm.bar_final);
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -450,275 +572,211 @@ __device__ __forceinline__ void dkv_cc_tile(const uint32_t (&rs)[2][32], uint32_
 }
 
 // ---- query-stationary: dQa ------------------------------------------------------------------------
-// TMEM: Qa [0, 32K); slot s: S' at 32K + 64 s (dS, bf16, over its first 32 columns); dQa behind the slots.
+// TMEM: Qa buffers [0, QB*32K); slot s: S' at col_slot0 + 64 s (dS, bf16, over its first 32 columns); dQa behind the slots.
 template <int KATOMS, int DVH>
 __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dq_cc_kernel(
     const __grid_constant__ CUtensorMap tm_q_stat, const __grid_constant__ CUtensorMap tm_k_strm,
     const float* __restrict__ v, const float* __restrict__ d_o, const float* __restrict__ delta, float* __restrict__ dqa, int L,
-    int KD, int NQ, int C1, int dbg, long long* __restrict__ tl) {
+    int KD, int NQ, int C1, int nqt, int nitems, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  typedef CbSmem<KATOMS, CB_BN * DVH> Smem;
+  typedef CbSmem<KATOMS, CB_BN * DVH, CB_BM * KATOMS * 64> Smem;
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int ST = Smem::ST;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bn = blockIdx.y, q0 = blockIdx.x * CB_BM;
   const int ntiles = (L + CB_BN - 1) / CB_BN;
-  const int NS = min(CB_MAXSLOTS, (512 - KATOMS * 32 - NQ) / 64);
-  const uint32_t COL_SLOT0 = KATOMS * 32, COL_DQ = COL_SLOT0 + 64 * NS;
+  const int my_items = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const CbPlan pl = cb_plan(KATOMS, NQ);
 
-  const bool rec = tl != nullptr && blockIdx.x == 3 && blockIdx.y == 40 && lane == 0;   // a CTA of a middle wave
-#define CC_STAMP(ev, tile) do { if (rec) tl[(ev) * 64 + (tile)] = clock64(); } while (0)
-  if (warp == 0) CC_STAMP(10, 0);
-  cb_init<KATOMS>(sm, warp, lane, &tm_q_stat, &tm_k_strm, q0, bn);
+  cb_init<KATOMS>(sm, warp, lane, &tm_q_stat, &tm_k_strm, nqt);
   const uint32_t tmem = sm.tmem_base;
-  if (warp == 0) CC_STAMP(10, 1);
 
   if (warp == CB_W_TMA) {
-    if (lane == 0) {
-      Ring rg;
-      for (int j = 0; j < ntiles; ++j, rg.next(CB_STAGES)) {
-        const int s = rg.i;
-        const int nvalid = min(CB_BN, L - j * CB_BN);
-        tc::mbar_wait(&sm.bar_empty[s], rg.ph ^ 1);
-        if ((dbg & 2) && j >= CB_STAGES) { tc::mbar_arrive(&sm.bar_full[s]); continue; }     // ablation: no global traffic
-        tc::mbar_arrive_expect_tx(&sm.bar_full[s], KATOMS * CB_BN * 64 * 2 + nvalid * DVH * 4);
-        for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.strm[s][a], &tm_k_strm, &sm.bar_full[s], a * 64, j * CB_BN, bn);
-        bulk_g2s(sm.side[s], v + ((size_t)bn * L + (size_t)j * CB_BN) * DVH, nvalid * DVH * 4, &sm.bar_full[s]);
-      }
-    }
+    if (lane == 0) cb_producer<KATOMS>(sm, &tm_q_stat, &tm_k_strm, v, DVH, nullptr, 0, L, nqt, ntiles, my_items, dbg);
   } else if (warp == CB_W_S) {
-    cb_score_issuer<KATOMS>(sm, tmem, COL_SLOT0, NS, C1 >> 4, ntiles, rec ? tl : nullptr);
+    cb_score_issuer<KATOMS>(sm, tmem, pl, C1 >> 4, ntiles, my_items);
   } else if (warp == CB_W_G) {
-    const uint32_t idesc_dq = tc::idesc_bf16_f32(CB_BM, NQ) | (1u << 16);
-    constexpr uint32_t STRM_ATOM = (CB_BN * 128) >> 4, STAGE = KATOMS * STRM_ATOM;
-    const uint32_t k_lo = tc::desc_lo_mn(smem_u32(sm.strm[0][0]), CB_BN * 128);
-    Ring rst, rsl;
-    for (int jj = 0; jj < ntiles; ++jj, rst.next(CB_STAGES), rsl.next(NS)) {
-      const int st = rst.i, slot = rsl.i;
-      const uint32_t tslot = tmem + COL_SLOT0 + 64 * slot;
-      tc::mbar_wait(&sm.bar_p_ready[slot], rsl.ph);
-      tc::tc_fence_after();
-      CC_STAMP(2, jj);
-      if (tc::elect_one()) {
-        const uint32_t kb = k_lo + st * STAGE;
-#pragma unroll
-        for (int ks = 0; ks < CB_BN / 16; ++ks)
-          if (!(dbg & 4) || jj == 0) tc::mma_ts(tmem + COL_DQ, tslot + ks * 8, tc::desc64(kb + ks * 128), idesc_dq, (jj > 0 || ks > 0) ? 1u : 0u);
-        tc::mma_commit(&sm.bar_empty[st]);
-        tc::mma_commit(&sm.bar_slot_free[slot]);
-        if (jj == ntiles - 1) tc::mma_commit(&sm.bar_final);
-      }
-      __syncwarp();
-    }
+    cb_grad_issuer<KATOMS>(sm, tmem, pl, tc::idesc_bf16_f32(CB_BM, NQ) | (1u << 16), ntiles, my_items, dbg);
   } else {
     const int wg = warp >> 2;
     const int rowi = (warp & 3) * 32 + lane;
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    if (wg == 0) {
-      tc::mbar_wait(&sm.bar_stat, 0);
-      if (warp == 0) CC_STAMP(10, 2);
-      stationary_to_tmem<KATOMS>(sm.stat, tlane, rowi);
+    const int NS = pl.NS;
+    auto stage_stat = [&](int it) {                   // WG0: stationary tile of item `it` -> its TMEM buffer
+      tc::mbar_wait(&sm.bar_stat, it & 1);
+      stationary_to_tmem<KATOMS>(sm.stat, tlane + (uint32_t)((it & (pl.QB - 1)) * KATOMS * 32), rowi);
       tc::mbar_arrive(&sm.bar_a_ready);
-      if (warp == 0) CC_STAMP(10, 3);
-    }
-    const int qi = q0 + rowi;
-    const size_t row = (size_t)bn * L + qi;
-    float go[DVH], ndelta = 0.f;
-#pragma unroll
-    for (int e = 0; e < DVH; ++e) go[e] = qi < L ? d_o[row * DVH + e] : 0.f;
-    if (qi < L) ndelta = -delta[row];
+      tc::mbar_arrive(&sm.bar_stat_free);
+    };
+    if (wg == 0) stage_stat(0);
     uint32_t rs[2][32], pd[32];
     Ring rst, rsl;
-    for (int i = 0; i < wg; ++i) { rst.next(CB_STAGES); rsl.next(NS); }
-    for (int j = wg; j < ntiles; j += CB_NWG) {
-      const int slot = rsl.i, st = rst.i;
-      const uint32_t tslot = tlane + COL_SLOT0 + 64 * slot;
-      const int nvalid = L - j * CB_BN;
-      const bool tail = nvalid < CB_BN;
-      if ((warp & 3) == 0) CC_STAMP(3, j);
-      tc::mbar_wait(&sm.bar_s_full[slot], rsl.ph);
+    int tcur = 0;                                     // global tile index the rings stand at
+    const bool bulk_out = (KD & 3) == 0;
+    for (int it = 0; it < my_items; ++it) {
+      const int item = blockIdx.x + it * gridDim.x, bn = item / nqt, qt = item - bn * nqt, q0 = qt * CB_BM;
+      const int qi = q0 + rowi;
+      const size_t row = (size_t)bn * L + qi;
+      float go[DVH], ndelta = 0.f;
+#pragma unroll
+      for (int e = 0; e < DVH; ++e) go[e] = qi < L ? d_o[row * DVH + e] : 0.f;
+      if (qi < L) ndelta = -delta[row];
+      for (int j = (wg + CB_NWG - qt % CB_NWG) % CB_NWG; j < ntiles; j += CB_NWG) {   // tile -> warpgroup (j + qt) % 3
+        for (const int t = it * ntiles + j; tcur < t; ++tcur) { rst.next(ST); rsl.next(NS); }
+        const int slot = rsl.i, st = rst.i;
+        const uint32_t tslot = tlane + pl.col_slot0 + 64 * slot;
+        const int nvalid = L - j * CB_BN;
+        const bool tail = nvalid < CB_BN;
+        tc::mbar_wait(&sm.bar_s_full[slot], rsl.ph);
+        tc::tc_fence_after();
+        tc::tmem_ld_x32(tslot, rs[0]);
+        tc::tmem_ld_x32(tslot + 32, rs[1]);
+        tc::tmem_ld_wait();
+        const uint32_t vt = smem_u32(sm.side[st]);
+        if (dbg & 8) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pd[i] = rs[0][i];
+        } else if (dbg & 1) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pd[i] = tc::pack_bf16x2(__uint_as_float(rs[0][i]) * ndelta, __uint_as_float(rs[1][i]) * go[0]);
+        } else if (tail) dq_cc_tile<DVH, true>(rs, pd, vt, nvalid, go, ndelta);
+        else dq_cc_tile<DVH, false>(rs, pd, vt, nvalid, go, ndelta);
+        tc::tmem_st_x32(tslot, pd);                    // dS (bf16) over S'[0,32): all of S' is in registers
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        tc::mbar_arrive(&sm.bar_p_ready[slot]);
+        tc::mbar_arrive(&sm.bar_empty[st]);            // value tile consumed
+      }
+      if (wg == 0 && pl.QB == 2 && it + 1 < my_items) stage_stat(it + 1);   // lets the score issuer run ahead during the drain
+      // ---- drain dQa: TMEM -> shared staging tile -> one bulk store of nrows x KD contiguous floats ----
+      tc::mbar_wait(&sm.bar_final, it & 1);
       tc::tc_fence_after();
-      if ((warp & 3) == 0) CC_STAMP(4, j);
-      tc::tmem_ld_x32(tslot, rs[0]);
-      tc::tmem_ld_x32(tslot + 32, rs[1]);
-      tc::tmem_ld_wait();
-      const uint32_t vt = smem_u32(sm.side[st]);
-      if (dbg & 8) {
+      if (bulk_out) {
+        if (threadIdx.x == 0) bulk_wait_read();        // the previous item's store has finished reading the staging tile
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * CB_NWG) : "memory");
+        for (int c0 = wg * 32; c0 < NQ; c0 += 32 * CB_NWG) {
+          tc::tmem_ld_x32(tlane + pl.col_acc + c0, rs[0]);
+          tc::tmem_ld_wait();
+          const uint32_t dst = smem_u32(sm.out + rowi * KD + c0);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) pd[i] = rs[0][i];
-      } else if (dbg & 1) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) pd[i] = tc::pack_bf16x2(__uint_as_float(rs[0][i]) * ndelta, __uint_as_float(rs[1][i]) * go[0]);
-      } else if (tail) dq_cc_tile<DVH, true>(rs, pd, vt, nvalid, go, ndelta);
-      else dq_cc_tile<DVH, false>(rs, pd, vt, nvalid, go, ndelta);
-      tc::tmem_st_x32(tslot, pd);                    // dS (bf16) over S'[0,32): all of S' is in registers
-      tc::tmem_st_wait();
-      tc::tc_fence_before();
-      tc::mbar_arrive(&sm.bar_p_ready[slot]);
-      tc::mbar_arrive(&sm.bar_empty[st]);            // value tile consumed
-      if ((warp & 3) == 0) CC_STAMP(6, j);
-#pragma unroll
-      for (int i = 0; i < CB_NWG; ++i) { rst.next(CB_STAGES); rsl.next(NS); }
-    }
-    if (warp == 0) CC_STAMP(10, 4);
-    tc::mbar_wait(&sm.bar_final, 0);
-    tc::tc_fence_after();
-    if (warp == 0) CC_STAMP(10, 5);
-    if ((KD & 3) == 0) {
-      // dQa tile -> shared memory (the streamed-tile ring is idle now) -> ONE bulk store of nrows x KD contiguous floats.
-      // Direct per-row stores from the accumulator layout (lane = row, 400-byte row pitch) cost ~3.8 k cycles per CTA.
-      float* stage = reinterpret_cast<float*>(&sm.strm[0][0][0]);
-      static_assert(sizeof(sm.strm) >= CB_BM * KATOMS * 64 * 4, "dQa staging tile must fit in the stream ring");
-      for (int c0 = wg * 32; c0 < NQ; c0 += 32 * CB_NWG) {
-        tc::tmem_ld_x32(tlane + COL_DQ + c0, rs[0]);
-        tc::tmem_ld_wait();
-        const uint32_t dst = smem_u32(stage + rowi * KD + c0);
-#pragma unroll
-        for (int e = 0; e < 32; e += 4)
-          if (c0 + e < KD)
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + e * 4), "r"(rs[0][e]), "r"(rs[0][e + 1]),
-                         "r"(rs[0][e + 2]), "r"(rs[0][e + 3]) : "memory");
-      }
-      tc::fence_proxy_async();
-      asm volatile("bar.sync 1, %0;" ::"n"(128 * CB_NWG) : "memory");
-      if (threadIdx.x == 0) {
-        const int nrows = min(CB_BM, L - q0);
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dqa + ((size_t)bn * L + q0) * KD),
-                     "r"(smem_u32(stage)), "r"((uint32_t)(nrows * KD * 4)) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      }
-    } else {
-      for (int c0 = wg * 32; c0 < NQ; c0 += 32 * CB_NWG) {
-        tc::tmem_ld_x32(tlane + COL_DQ + c0, rs[0]);
-        tc::tmem_ld_wait();
-        if (qi < L) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (c0 + e < KD) dqa[row * KD + c0 + e] = __uint_as_float(rs[0][e]);
+          for (int e = 0; e < 32; e += 4)
+            if (c0 + e < KD)
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + e * 4), "r"(rs[0][e]), "r"(rs[0][e + 1]),
+                           "r"(rs[0][e + 2]), "r"(rs[0][e + 3]) : "memory");
         }
+        tc::tc_fence_before();
+        tc::mbar_arrive(&sm.bar_acc_free);             // the accumulator columns may be overwritten by the next item
+        tc::fence_proxy_async();
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * CB_NWG) : "memory");
+        if (threadIdx.x == 0) bulk_s2g(dqa + ((size_t)bn * L + q0) * KD, sm.out, (uint32_t)(min(CB_BM, L - q0) * KD * 4));
+      } else {
+        for (int c0 = wg * 32; c0 < NQ; c0 += 32 * CB_NWG) {
+          tc::tmem_ld_x32(tlane + pl.col_acc + c0, rs[0]);
+          tc::tmem_ld_wait();
+          if (qi < L) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (c0 + e < KD) dqa[row * KD + c0 + e] = __uint_as_float(rs[0][e]);
+          }
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive(&sm.bar_acc_free);
       }
+      if (wg == 0 && pl.QB == 1 && it + 1 < my_items) stage_stat(it + 1);
     }
+    if (threadIdx.x == 0) bulk_wait_read();
   }
-  if (warp == 0) CC_STAMP(10, 6);
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 0) CC_STAMP(10, 7);
-#undef CC_STAMP
   if (warp == CB_W_S) tc::tmem_dealloc<512>(tmem);
 }
 
 // ---- key-stationary: dK, dV ------------------------------------------------------------------------
-// TMEM: Ka [0, 32K); slot s: S'^T at 32K + 64 s (P^T over columns [0,32), dS^T over [32,64)); dV (16), dK (32) behind the slots.
+// TMEM: Ka buffers [0, QB*32K); slot s: S'^T at col_slot0 + 64 s (dS^T, bf16, over its first 32 columns); dK (32) behind the slots.
 template <int KATOMS, int DVH>
 __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
     const __grid_constant__ CUtensorMap tm_k_stat, const __grid_constant__ CUtensorMap tm_q_strm,
     const float* __restrict__ v, const float* __restrict__ d_o, const float* __restrict__ delta, float* __restrict__ dk,
-    float* __restrict__ dv, bf16* __restrict__ dqkvh, int KPq, int nh, int L, int dkh, int C1) {
+    float* __restrict__ dv, bf16* __restrict__ dqkvh, int KPq, int nh, int L, int dkh, int C1, int nqt, int nitems) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  typedef CbSmem<KATOMS, CB_BN * (DVH + 1)> Smem;
+  typedef CbSmem<KATOMS, CB_BN * (DVH + 1), 0> Smem;
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int ST = Smem::ST;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bn = blockIdx.y, k0 = blockIdx.x * CB_BM;
   const int ntiles = (L + CB_BN - 1) / CB_BN;
-  const int NS = min(CB_MAXSLOTS, (512 - KATOMS * 32 - 32) / 64);
-  const uint32_t COL_SLOT0 = KATOMS * 32, COL_DK = COL_SLOT0 + 64 * NS;
-  __shared__ float dv_xch[CB_NWG - 1][CB_BM][DVH];     // dV partials of warpgroups 1.. (dV = P^T dO is accumulated in registers)
+  const int my_items = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const CbPlan pl = cb_plan(KATOMS, 32);
+  __shared__ float dv_xch[2][CB_NWG - 1][CB_BM][DVH];   // dV partials of warpgroups 1.. (registers -> WG0), by item parity
 
-  cb_init<KATOMS>(sm, warp, lane, &tm_k_stat, &tm_q_strm, k0, bn);
+  cb_init<KATOMS>(sm, warp, lane, &tm_k_stat, &tm_q_strm, nqt);
   const uint32_t tmem = sm.tmem_base;
 
   if (warp == CB_W_TMA) {
-    if (lane == 0) {
-      Ring rg;
-      for (int j = 0; j < ntiles; ++j, rg.next(CB_STAGES)) {
-        const int s = rg.i;
-        const int nvalid = min(CB_BN, L - j * CB_BN);
-        const size_t r0 = (size_t)bn * L + (size_t)j * CB_BN;
-        tc::mbar_wait(&sm.bar_empty[s], rg.ph ^ 1);
-        tc::mbar_arrive_expect_tx(&sm.bar_full[s], KATOMS * CB_BN * 64 * 2 + nvalid * (DVH + 1) * 4);
-        for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.strm[s][a], &tm_q_strm, &sm.bar_full[s], a * 64, j * CB_BN, bn);
-        bulk_g2s(sm.side[s], d_o + r0 * DVH, nvalid * DVH * 4, &sm.bar_full[s]);
-        bulk_g2s(sm.side[s] + CB_BN * DVH, delta + r0, nvalid * 4, &sm.bar_full[s]);
-      }
-    }
+    if (lane == 0) cb_producer<KATOMS>(sm, &tm_k_stat, &tm_q_strm, d_o, DVH, delta, 1, L, nqt, ntiles, my_items, 0);
   } else if (warp == CB_W_S) {
-    cb_score_issuer<KATOMS>(sm, tmem, COL_SLOT0, NS, C1 >> 4, ntiles);
+    cb_score_issuer<KATOMS>(sm, tmem, pl, C1 >> 4, ntiles, my_items);
   } else if (warp == CB_W_G) {
-    constexpr uint32_t idesc_dk = tc::idesc_bf16_f32(CB_BM, 32) | (1u << 16);
-    constexpr uint32_t STRM_ATOM = (CB_BN * 128) >> 4, STAGE = KATOMS * STRM_ATOM;
-    const uint32_t q_lo = tc::desc_lo_mn(smem_u32(sm.strm[0][0]), CB_BN * 128);
-    Ring rst, rsl;
-    for (int jj = 0; jj < ntiles; ++jj, rst.next(CB_STAGES), rsl.next(NS)) {
-      const int st = rst.i, slot = rsl.i;
-      const uint32_t tslot = tmem + COL_SLOT0 + 64 * slot;
-      tc::mbar_wait(&sm.bar_p_ready[slot], rsl.ph);
-      tc::tc_fence_after();
-      if (tc::elect_one()) {
-        const uint32_t qb = q_lo + st * STAGE;
-#pragma unroll
-        for (int ks = 0; ks < CB_BN / 16; ++ks)
-          tc::mma_ts(tmem + COL_DK, tslot + ks * 8, tc::desc64(qb + ks * 128), idesc_dk, (jj > 0 || ks > 0) ? 1u : 0u);
-        tc::mma_commit(&sm.bar_empty[st]);
-        tc::mma_commit(&sm.bar_slot_free[slot]);
-        if (jj == ntiles - 1) tc::mma_commit(&sm.bar_final);
-      }
-      __syncwarp();
-    }
+    cb_grad_issuer<KATOMS>(sm, tmem, pl, tc::idesc_bf16_f32(CB_BM, 32) | (1u << 16), ntiles, my_items, 0);
   } else {
     const int wg = warp >> 2;
     const int rowi = (warp & 3) * 32 + lane;
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    if (wg == 0) {
-      tc::mbar_wait(&sm.bar_stat, 0);
-      stationary_to_tmem<KATOMS>(sm.stat, tlane, rowi);
+    const int NS = pl.NS;
+    auto stage_stat = [&](int it) {
+      tc::mbar_wait(&sm.bar_stat, it & 1);
+      stationary_to_tmem<KATOMS>(sm.stat, tlane + (uint32_t)((it & (pl.QB - 1)) * KATOMS * 32), rowi);
       tc::mbar_arrive(&sm.bar_a_ready);
-    }
-    const int kj = k0 + rowi;
-    const size_t row = (size_t)bn * L + kj;
-    float vk[DVH];
-#pragma unroll
-    for (int e = 0; e < DVH; ++e) vk[e] = kj < L ? v[row * DVH + e] : 0.f;
-    float dvacc[DVH];
-#pragma unroll
-    for (int e = 0; e < DVH; ++e) dvacc[e] = 0.f;
+      tc::mbar_arrive(&sm.bar_stat_free);
+    };
+    if (wg == 0) stage_stat(0);
     uint32_t rs[2][32], pd[32];
     Ring rst, rsl;
-    for (int i = 0; i < wg; ++i) { rst.next(CB_STAGES); rsl.next(NS); }
-    for (int j = wg; j < ntiles; j += CB_NWG) {
-      const int slot = rsl.i, st = rst.i;
-      const uint32_t tslot = tlane + COL_SLOT0 + 64 * slot;
-      const int nvalid = L - j * CB_BN;
-      const bool tail = nvalid < CB_BN;
-      tc::mbar_wait(&sm.bar_s_full[slot], rsl.ph);
-      tc::tc_fence_after();
-      tc::tmem_ld_x32(tslot, rs[0]);
-      tc::tmem_ld_x32(tslot + 32, rs[1]);
-      tc::tmem_ld_wait();
-      const uint32_t dot = smem_u32(sm.side[st]), dlt = dot + CB_BN * DVH * 4;
-      if (tail) dkv_cc_tile<DVH, true>(rs, pd, dot, dlt, nvalid, vk, dvacc);
-      else dkv_cc_tile<DVH, false>(rs, pd, dot, dlt, nvalid, vk, dvacc);
-      tc::tmem_st_x32(tslot, pd);                    // dS^T (bf16) over S'^T[0,32): all of S'^T is in registers
-      tc::tmem_st_wait();
-      tc::tc_fence_before();
-      tc::mbar_arrive(&sm.bar_p_ready[slot]);
-      tc::mbar_arrive(&sm.bar_empty[st]);
-#pragma unroll
-      for (int i = 0; i < CB_NWG; ++i) { rst.next(CB_STAGES); rsl.next(NS); }
-    }
-    if (wg > 0) {
-#pragma unroll
-      for (int e = 0; e < DVH; ++e) dv_xch[wg - 1][rowi][e] = dvacc[e];
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(128 * CB_NWG) : "memory");
-    tc::mbar_wait(&sm.bar_final, 0);
-    tc::tc_fence_after();
+    int tcur = 0;                                        // global tile index the rings stand at
     const float LN2 = 0.6931471805599453f;               // Qa carries log2(e)*q
-    const int b = bn / nh, n = bn - b * nh;
-    bf16* prow = dqkvh ? dqkvh + ((size_t)b * L + kj) * KPq : nullptr;
-    if (wg == 0) {
-      tc::tmem_ld_x32(tlane + COL_DK, rs[0]);
-      tc::tmem_ld_wait();
-      if (kj < L) {
+    for (int it = 0; it < my_items; ++it) {
+      const int item = blockIdx.x + it * gridDim.x, bn = item / nqt, qt = item - bn * nqt, k0 = qt * CB_BM;
+      const int kj = k0 + rowi;
+      const size_t row = (size_t)bn * L + kj;
+      float vk[DVH], dvacc[DVH];
+#pragma unroll
+      for (int e = 0; e < DVH; ++e) { vk[e] = kj < L ? v[row * DVH + e] : 0.f; dvacc[e] = 0.f; }
+      // tile -> warpgroup (j + qt) % 3: fixed per item, so the dV partial sums do not depend on where the item runs
+      for (int j = (wg + CB_NWG - qt % CB_NWG) % CB_NWG; j < ntiles; j += CB_NWG) {
+        for (const int t = it * ntiles + j; tcur < t; ++tcur) { rst.next(ST); rsl.next(NS); }
+        const int slot = rsl.i, st = rst.i;
+        const uint32_t tslot = tlane + pl.col_slot0 + 64 * slot;
+        const int nvalid = L - j * CB_BN;
+        const bool tail = nvalid < CB_BN;
+        tc::mbar_wait(&sm.bar_s_full[slot], rsl.ph);
+        tc::tc_fence_after();
+        tc::tmem_ld_x32(tslot, rs[0]);
+        tc::tmem_ld_x32(tslot + 32, rs[1]);
+        tc::tmem_ld_wait();
+        const uint32_t dot = smem_u32(sm.side[st]), dlt = dot + CB_BN * DVH * 4;
+        if (tail) dkv_cc_tile<DVH, true>(rs, pd, dot, dlt, nvalid, vk, dvacc);
+        else dkv_cc_tile<DVH, false>(rs, pd, dot, dlt, nvalid, vk, dvacc);
+        tc::tmem_st_x32(tslot, pd);                    // dS^T (bf16) over S'^T[0,32): all of S'^T is in registers
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        tc::mbar_arrive(&sm.bar_p_ready[slot]);
+        tc::mbar_arrive(&sm.bar_empty[st]);
+      }
+      if (wg == 0 && pl.QB == 2 && it + 1 < my_items) stage_stat(it + 1);
+      if (wg > 0) {
+#pragma unroll
+        for (int e = 0; e < DVH; ++e) dv_xch[it & 1][wg - 1][rowi][e] = dvacc[e];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * CB_NWG) : "memory");
+      tc::mbar_wait(&sm.bar_final, it & 1);
+      tc::tc_fence_after();
+      const int b = bn / nh, n = bn - b * nh;
+      bf16* prow = dqkvh ? dqkvh + ((size_t)b * L + kj) * KPq : nullptr;
+      if (wg == 0) {
+        tc::tmem_ld_x32(tlane + pl.col_acc, rs[0]);
+        tc::tmem_ld_wait();
+      }
+      tc::tc_fence_before();
+      tc::mbar_arrive(&sm.bar_acc_free);               // dK is in WG0's registers: the accumulator may be overwritten
+      if (wg == 0 && kj < L) {
         if (prow) {
           bf16* dst = prow + nh * dkh + n * dkh;
           if (((dkh | KPq) & 3) == 0) {
@@ -740,22 +798,31 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
           for (int e = 0; e < 32; ++e)
             if (e < dkh) dk[row * dkh + e] = __uint_as_float(rs[0][e]) * LN2;
         }
-      }
-    }
-    if (wg == 0 && kj < L) {                             // dV: own partial + the other warpgroups' (fixed order)
 #pragma unroll
-      for (int e = 0; e < DVH; ++e) {
-        float t = dvacc[e];
+        for (int e = 0; e < DVH; ++e) {                  // dV: own partial + the other warpgroups' (fixed order)
+          float t = dvacc[e];
 #pragma unroll
-        for (int g = 0; g < CB_NWG - 1; ++g) t += dv_xch[g][rowi][e];
-        if (prow) prow[2 * nh * dkh + n * DVH + e] = __float2bfloat16(t);
-        else dv[row * DVH + e] = t;
+          for (int g = 0; g < CB_NWG - 1; ++g) t += dv_xch[it & 1][g][rowi][e];
+          if (prow) prow[2 * nh * dkh + n * DVH + e] = __float2bfloat16(t);
+          else dv[row * DVH + e] = t;
+        }
       }
+      if (wg == 0 && pl.QB == 1 && it + 1 < my_items) stage_stat(it + 1);
     }
   }
   tc::tc_fence_before();
   __syncthreads();
   if (warp == CB_W_S) tc::tmem_dealloc<512>(tmem);
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
 }
 
 int make_aug_map(const Dims& d, const void* t, int KP, uint32_t box_rows, CUtensorMap* out) {
@@ -774,7 +841,8 @@ int launch_fwd_cc(const Dims& d, const AugLayout& a, const void* qa, const void*
   const size_t smem = sizeof(CfSmem<KATOMS, DVH>) + 1024;
   auto kern = attn_fwd_cc_kernel<KATOMS, DVH>;
   AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<dim3(cdiv(d.L, CF_BM), d.BN), CF_THREADS, smem, st>>>(tq, tk, v, o, lse, d.L, a.C1, g_attn_dbg_mode);
+  const int nqt = cdiv(d.L, CF_BM), nitems = nqt * d.BN;
+  kern<<<std::min(nitems, sm_count()), CF_THREADS, smem, st>>>(tq, tk, v, o, lse, d.L, a.C1, nqt, nitems, g_attn_dbg_mode);
   AACONV_LAUNCH_OK("attn_fwd_cc");
   return 0;
 }
@@ -787,19 +855,21 @@ int launch_bwd_cc(const Dims& d, const AugLayout& a, const void* qa, const void*
   AACONV_TRY(make_aug_map(d, ka, a.KP, CB_BN, &tk_strm));
   AACONV_TRY(make_aug_map(d, ka, a.KP, CB_BM, &tk_stat));
   AACONV_TRY(make_aug_map(d, qa, a.KP, CB_BN, &tq_strm));
-  dim3 grid(cdiv(d.L, CB_BM), d.BN);
+  const int nqt = cdiv(d.L, CB_BM), nitems = nqt * d.BN;
+  const int grid = std::min(nitems, sm_count());
   {
-    const size_t smem = sizeof(CbSmem<KATOMS, CB_BN * (DVH + 1)>) + 1024;
+    const size_t smem = sizeof(CbSmem<KATOMS, CB_BN * (DVH + 1), 0>) + 1024;
     auto kern = attn_bwd_dkv_cc_kernel<KATOMS, DVH>;
     AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, CB_THREADS, smem, st>>>(tk_stat, tq_strm, v, d_o, delta, dk, dv, static_cast<bf16*>(dqkvh), KPq, d.nh, d.L, d.dkh, a.C1);
+    kern<<<grid, CB_THREADS, smem, st>>>(tk_stat, tq_strm, v, d_o, delta, dk, dv, static_cast<bf16*>(dqkvh), KPq, d.nh, d.L, d.dkh, a.C1,
+                                         nqt, nitems);
     AACONV_LAUNCH_OK("attn_bwd_dkv_cc");
   }
   {
-    const size_t smem = sizeof(CbSmem<KATOMS, CB_BN * DVH>) + 1024;
+    const size_t smem = sizeof(CbSmem<KATOMS, CB_BN * DVH, CB_BM * KATOMS * 64>) + 1024;
     auto kern = attn_bwd_dq_cc_kernel<KATOMS, DVH>;
     AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, CB_THREADS, smem, st>>>(tq_stat, tk_strm, v, d_o, delta, dqa, d.L, a.KD, a.NQ, a.C1, g_attn_dbg_mode, g_attn_dbg);
+    kern<<<grid, CB_THREADS, smem, st>>>(tq_stat, tk_strm, v, d_o, delta, dqa, d.L, a.KD, a.NQ, a.C1, nqt, nitems, g_attn_dbg_mode);
     AACONV_LAUNCH_OK("attn_bwd_dq_cc");
   }
   return 0;

@@ -106,6 +106,16 @@ int aaconv_bce_forward_backward(const float* z, const float* targets, int ld, co
                                 int B, int C, float* element_loss, float* loss, float* dz,
                                 const float* grad_scale, void* stream);
 
+/* Ensemble evaluation: replaces torch.stack(outputs, 2).mean(2) (chexpert.py:233) and the
+ * per-class sklearn roc_curve + auc on raw logits (chexpert.py:130-135).
+ *   aaconv_ensemble_mean  logits (n_models, N, C) -> mean (N, C), summed in checkpoint order.
+ *   aaconv_auroc          logits (N, C), targets (N, C) in {0,1} -> auroc (C): tie-corrected pair counting in integers
+ *                         (== area under sklearn's ROC polygon); NaN for a class with a single label value.
+ *                         workspace: aaconv_auroc_workspace_bytes(C) bytes of device memory.                  */
+int aaconv_ensemble_mean(const float* logits, int n_models, int N, int C, float* mean, void* stream);
+size_t aaconv_auroc_workspace_bytes(int C);
+int aaconv_auroc(const float* logits, const float* targets, int N, int C, float* auroc, void* workspace, void* stream);
+
 /* Accounting / measurement helpers used by bench.py (no reference counterpart).
  *   aaconv_launch_count   kernels launched by this library since it was loaded (all threads).
  *   aaconv_profile_begin  start recording a CUDA event after every launch made on `stream`.
