@@ -22,6 +22,9 @@ typedef __nv_bfloat16 bf16;
 // ablation switches for tools/attn_ablate.py (0 in production): 1 no MUFU, 2 no global traffic after the first tiles,
 // 4 no gradient MMAs, 8 no math at all
 int g_attn_dbg_mode = 0;
+extern long long* g_attn_dbg;      // attn_tc_bwd.cu: timeline buffer of TL_EVENTS x TL_COLS stamps (tools/attn_timeline.py)
+constexpr int TL_COLS = 96, TL_CTA = 40;
+#define TL_STAMP(tl, ev, col) do { if ((tl) && (col) < TL_COLS) (tl)[(ev) * TL_COLS + (col)] = clock64(); } while (0)
 extern "C" void aaconv_debug_set_mode(int m) { g_attn_dbg_mode = m; }
 
 namespace {
@@ -34,10 +37,13 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 
 // index + phase of a ring of n entries, advanced without integer division (a runtime modulo costs a MUFU.RCP, and the MUFU
 // pipe is what the math warps saturate)
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
 struct Ring {
   int i = 0;
   uint32_t ph = 0;
   __device__ __forceinline__ void next(int n) { if (++i == n) { i = 0; ph ^= 1; } }
+  __device__ __forceinline__ void advance(int k, int n) { i += k; if (i >= n) { i -= n; ph ^= 1; } }   // k <= n
 };
 
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
@@ -218,7 +224,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) attn_fwd_cc_kernel(
   if (warp == CF_W_TMA) {
     if (lane == 0) {
       Ring rg;
-      const int jq = min(1, ntiles - 1);
+      const int jq = ntiles / 2;                    // see cb_producer
       for (int it = 0; it < my_items; ++it) {
         const int item = blockIdx.x + it * gridDim.x, bn = item / nqt;
         for (int j = 0; j < ntiles; ++j, rg.next(ST)) {
@@ -349,45 +355,72 @@ __global__ void __launch_bounds__(CF_THREADS, 1) attn_fwd_cc_kernel(
 // ================================================================================================
 // backward
 // ================================================================================================
-constexpr int CB_BM = 128, CB_BN = 64, CB_MAXSLOTS = 4;
+constexpr int CB_BM = 128, CB_BN = 64, CB_MAXSLOTS = 5;
 // three math warpgroups (global tile t -> warpgroup t % 3): three warps per scheduler keep the MUFU pipe busy while the others sit
 // in TMEM load / store / barrier latencies;  then one TMA warp, the score-MMA issuer (+TMEM alloc) and the gradient-MMA issuer
-constexpr int CB_NWG = 3, CB_W_TMA = 4 * CB_NWG, CB_W_S = CB_W_TMA + 1, CB_W_G = CB_W_TMA + 2, CB_THREADS = 32 * (CB_W_G + 1);
-template <int KATOMS> struct CbStages { static constexpr int value = KATOMS >= 3 ? 3 : 6; };
+// (warp CB_W_G), and TWO score-MMA issuers (CB_W_S even global tiles + TMEM alloc, CB_W_S2 odd ones): the timeline showed a
+// single score issuer busy back to back (~600 cycles of waits + issue per tile) with every warpgroup waiting on it
+constexpr int CB_NWG = 3, CB_W_TMA = 4 * CB_NWG, CB_W_S = CB_W_TMA + 1, CB_W_G = CB_W_TMA + 2, CB_W_S2 = CB_W_TMA + 3,
+              CB_THREADS = 32 * (CB_W_S2 + 1);
+// Streamed-tile stages.  A stage is held from its TMA issue until the tile's GRADIENT MMA has completed (~3.5 tiles of
+// pipeline), so the prefetch lead is ST - 4.5 tiles; with 6 stages the score issuer waited 400-900 cycles per tile for the
+// K tile to land (timeline).  The dQa kernel also holds a 56-88 KB staging tile, the dK/dV kernel does not.
+template <int KATOMS, bool HAS_OUT> struct CbStages {
+  static constexpr int value = HAS_OUT ? (KATOMS >= 3 ? 3 : KATOMS == 2 ? 7 : 10) : (KATOMS >= 3 ? 7 : 10);
+};
 
 // TMEM plan of a backward kernel whose accumulator needs ACC columns: QB stationary buffers, NS score slots of 64 columns
+// The pipeline is latency-bound by (tiles in flight) / (S' MMA + TMEM round trip + math + gradient MMA ~ 2700 cycles), i.e. by
+// the number of score slots: the stationary operand gets ONE buffer (it is refilled right after the item's last score MMA,
+// which is when a second buffer would have been filled too) and every remaining column goes to slots.
 struct CbPlan { int QB, NS; uint32_t col_slot0, col_acc; };
 __device__ __forceinline__ CbPlan cb_plan(int katoms, int acc_cols) {
   CbPlan p;
-  p.QB = (512 - 2 * katoms * 32 - acc_cols) / 64 >= 3 ? 2 : 1;
+  p.QB = 1;
   p.NS = min(CB_MAXSLOTS, (512 - p.QB * katoms * 32 - acc_cols) / 64);
   p.col_slot0 = p.QB * katoms * 32;
   p.col_acc = p.col_slot0 + 64 * p.NS;
   return p;
 }
 
-template <int KATOMS, int SIDE_FLOATS, int OUT_FLOATS>
+template <int KATOMS, int SIDE_FLOATS, int OUT_FLOATS, int ROW_FLOATS>
 struct __align__(1024) CbSmem {
-  static constexpr int ST = CbStages<KATOMS>::value;
+  static constexpr int ST = CbStages<KATOMS, (OUT_FLOATS > 0)>::value;
   bf16 stat[KATOMS][CB_BM * 64];
   bf16 strm[ST][KATOMS][CB_BN * 64];
   float side[ST][SIDE_FLOATS];                 // fp32 side tile: v (dq kernel) or dO | delta (dkv kernel)
+  float rowside[2][CB_BM * ROW_FLOATS];        // fp32 rows of the stationary tile (dO | delta, or v), by item parity
   float out[OUT_FLOATS > 0 ? OUT_FLOATS : 4];  // accumulator staging for the bulk store (dq kernel)
-  uint64_t bar_stat, bar_stat_free, bar_a_ready, bar_final, bar_acc_free, bar_full[ST], bar_empty[ST];
+  uint64_t bar_stat, bar_stat_free, bar_a_ready, bar_s_done, bar_final, bar_acc_free, bar_dv, bar_full[ST], bar_empty[ST];
   uint64_t bar_s_full[CB_MAXSLOTS], bar_p_ready[CB_MAXSLOTS], bar_slot_free[CB_MAXSLOTS];
   uint32_t tmem_base;
 };
 
 // CTA set-up.  The TMA lane initialises the barriers itself and issues the first stationary-tile load right away, so
 // that its latency runs under the TMEM allocation and the CTA-wide sync instead of after them.
+// stationary tile of item (bn, row0) + its fp32 row data (r0: RW0 floats per row, r1: RW1 floats per row or NULL) -> bar_stat
 template <int KATOMS, class Smem>
-__device__ __forceinline__ void cb_init(Smem& sm, int warp, int lane, const CUtensorMap* m_stat, const CUtensorMap* m_strm, int nqt) {
+__device__ __forceinline__ void cb_load_stat(Smem& sm, const CUtensorMap* m_stat, const float* r0, int RW0, const float* r1, int RW1,
+                                             int L, int bn, int row0, int parity) {
+  const int nrows = min(CB_BM, L - row0);
+  const size_t g0 = (size_t)bn * L + row0;
+  tc::mbar_arrive_expect_tx(&sm.bar_stat, KATOMS * CB_BM * 64 * 2 + nrows * (RW0 + RW1) * 4);
+  for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.stat[a], m_stat, &sm.bar_stat, a * 64, row0, bn);
+  bulk_g2s(sm.rowside[parity], r0 + g0 * RW0, nrows * RW0 * 4, &sm.bar_stat);
+  if (RW1) bulk_g2s(sm.rowside[parity] + CB_BM * RW0, r1 + g0 * RW1, nrows * RW1 * 4, &sm.bar_stat);
+}
+
+template <int KATOMS, class Smem>
+__device__ __forceinline__ void cb_init(Smem& sm, int warp, int lane, const CUtensorMap* m_stat, const CUtensorMap* m_strm, int nqt,
+                                        const float* r0, int RW0, const float* r1, int RW1, int L) {
   if (warp == CB_W_TMA && lane == 0) {
     tc::mbar_init(&sm.bar_stat, 1);
-    tc::mbar_init(&sm.bar_stat_free, 128);
+    tc::mbar_init(&sm.bar_stat_free, 128 * CB_NWG);   // every math thread has read its row data (WG0: and moved the tile to TMEM)
     tc::mbar_init(&sm.bar_a_ready, 128);
+    tc::mbar_init(&sm.bar_s_done, 2);                 // both score issuers have committed their last tile of the item
     tc::mbar_init(&sm.bar_final, 1);
-    tc::mbar_init(&sm.bar_acc_free, 128 * CB_NWG);
+    tc::mbar_init(&sm.bar_acc_free, 128);             // warpgroup 0 drains the accumulator
+    tc::mbar_init(&sm.bar_dv, 128 * (CB_NWG - 1));
     for (int s = 0; s < Smem::ST; ++s) { tc::mbar_init(&sm.bar_full[s], 1); tc::mbar_init(&sm.bar_empty[s], 129); }
     for (int s = 0; s < CB_MAXSLOTS; ++s) {
       tc::mbar_init(&sm.bar_s_full[s], 1);
@@ -396,8 +429,7 @@ __device__ __forceinline__ void cb_init(Smem& sm, int warp, int lane, const CUte
     }
     tc::fence_barrier_init();
     const int item = blockIdx.x, bn = item / nqt, row0 = (item - bn * nqt) * CB_BM;
-    tc::mbar_arrive_expect_tx(&sm.bar_stat, KATOMS * CB_BM * 64 * 2);
-    for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.stat[a], m_stat, &sm.bar_stat, a * 64, row0, bn);
+    cb_load_stat<KATOMS>(sm, m_stat, r0, RW0, r1, RW1, L, bn, row0, 0);
     tc::tma_prefetch_desc(m_strm);
   }
   if (warp == CB_W_S) tc::tmem_alloc<512>(&sm.tmem_base);
@@ -410,22 +442,25 @@ __device__ __forceinline__ void cb_init(Smem& sm, int warp, int lane, const CUte
 // tiles with their fp32 side rows (side0: SW0 floats per row, side1: SW1 floats per row or NULL)
 template <int KATOMS, class Smem>
 __device__ __forceinline__ void cb_producer(Smem& sm, const CUtensorMap* m_stat, const CUtensorMap* m_strm, const float* side0,
-                                            int SW0, const float* side1, int SW1, int L, int nqt, int ntiles, int my_items, int dbg) {
+                                            int SW0, const float* side1, int SW1, const float* r0, int RW0, const float* r1, int RW1,
+                                            int L, int nqt, int ntiles, int my_items, int dbg, long long* tl = nullptr) {
   Ring rg;
-  const int jq = min(1, ntiles - 1);
+  // the next item's stationary tile is requested half-way through the item: by then every warpgroup has started the item
+  // (bar_stat_free), so this wait never holds up the tile stream, and the tile still lands long before it is needed
+  const int jq = ntiles / 2;
   for (int it = 0; it < my_items; ++it) {
     const int item = blockIdx.x + it * gridDim.x, bn = item / nqt;
     for (int j = 0; j < ntiles; ++j, rg.next(Smem::ST)) {
       if (j == jq && it + 1 < my_items) {              // next item's stationary tile: the staging buffer is free once WG0
         const int nitem = item + gridDim.x, nbn = nitem / nqt, nrow0 = (nitem - nbn * nqt) * CB_BM;   // has moved this item's to TMEM
         tc::mbar_wait(&sm.bar_stat_free, it & 1);
-        tc::mbar_arrive_expect_tx(&sm.bar_stat, KATOMS * CB_BM * 64 * 2);
-        for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.stat[a], m_stat, &sm.bar_stat, a * 64, nrow0, nbn);
+        cb_load_stat<KATOMS>(sm, m_stat, r0, RW0, r1, RW1, L, nbn, nrow0, (it + 1) & 1);
       }
       const int s = rg.i;
       const int nvalid = min(CB_BN, L - j * CB_BN);
       const size_t r0 = (size_t)bn * L + (size_t)j * CB_BN;
       tc::mbar_wait(&sm.bar_empty[s], rg.ph ^ 1);
+      TL_STAMP(tl, 14, it * ntiles + j);
       if ((dbg & 2) && (it > 0 || j >= Smem::ST)) { tc::mbar_arrive(&sm.bar_full[s]); continue; }     // ablation: no global traffic
       tc::mbar_arrive_expect_tx(&sm.bar_full[s], KATOMS * CB_BN * 64 * 2 + nvalid * (SW0 + SW1) * 4);
       for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.strm[s][a], m_strm, &sm.bar_full[s], a * 64, j * CB_BN, bn);
@@ -436,54 +471,73 @@ __device__ __forceinline__ void cb_producer(Smem& sm, const CUtensorMap* m_stat,
 }
 
 template <int KATOMS, int NKS, class Smem>
-__device__ __forceinline__ void cb_score_loop(Smem& sm, uint32_t tmem, CbPlan pl, int ntiles, int my_items) {
+__device__ __forceinline__ void cb_score_loop(Smem& sm, uint32_t tmem, CbPlan pl, int ntiles, int my_items, int sidx, long long* tl) {
   constexpr uint32_t idesc_s = tc::idesc_bf16_f32(CB_BM, CB_BN);
   constexpr uint32_t STRM_ATOM = (CB_BN * 128) >> 4, STAGE = KATOMS * STRM_ATOM;
   const uint32_t strm_lo = tc::desc_lo_k(smem_u32(sm.strm[0][0]));
-  const int NS = pl.NS;
+  const int NS = pl.NS, total = my_items * ntiles;
   Ring rst, rsl;
-  int filled = 0;
-  for (int it = 0; it < my_items; ++it) {
-    tc::mbar_wait(&sm.bar_a_ready, it & 1);
-    tc::tc_fence_after();
-    const uint32_t a_tmem = tmem + (uint32_t)((it & (pl.QB - 1)) * KATOMS * 32);
-    for (int j = 0; j < ntiles; ++j, rst.next(Smem::ST), rsl.next(NS)) {
-      const int st = rst.i, slot = rsl.i;
-      tc::mbar_wait(&sm.bar_full[st], rst.ph);
-      if (filled >= NS) tc::mbar_wait(&sm.bar_slot_free[slot], rsl.ph ^ 1);
-      else ++filled;
-      tc::tc_fence_after();
-      if (tc::elect_one()) {
-        tc::issue_ts_ksteps<NKS, 0, STRM_ATOM>(tmem + pl.col_slot0 + 64 * slot, 0u, a_tmem, strm_lo + st * STAGE, idesc_s);
-        tc::mma_commit(&sm.bar_s_full[slot]);
-      }
-      __syncwarp();
+  for (int i = 0; i < sidx; ++i) { rst.next(Smem::ST); rsl.next(NS); }
+  int it = 0, j = sidx, a_it = -1;
+  bool had_tile = false;                           // (ntiles == 1: an issuer sees only every other item and still owes bar_s_done)
+  uint32_t a_tmem = tmem;
+  for (int t = sidx; t < total; t += 2) {
+    while (j >= ntiles) {
+      j -= ntiles;
+      if (!had_tile && lane_id() == 0) tc::mbar_arrive(&sm.bar_s_done);
+      had_tile = false;
+      ++it;
     }
+    had_tile = true;
+    if (it != a_it) {                              // first tile of an item for this issuer: its stationary operand is in TMEM
+      tc::mbar_wait(&sm.bar_a_ready, it & 1);
+      a_it = it;
+      a_tmem = tmem + (uint32_t)((it & (pl.QB - 1)) * KATOMS * 32);
+    }
+    const int st = rst.i, slot = rsl.i;
+    TL_STAMP(tl, 0, t);
+    tc::mbar_wait(&sm.bar_full[st], rst.ph);
+    TL_STAMP(tl, 1, t);
+    if (t >= NS) tc::mbar_wait(&sm.bar_slot_free[slot], rsl.ph ^ 1);
+    tc::tc_fence_after();
+    TL_STAMP(tl, 2, t);
+    if (tc::elect_one()) {
+      tc::issue_ts_ksteps<NKS, 0, STRM_ATOM>(tmem + pl.col_slot0 + 64 * slot, 0u, a_tmem, strm_lo + st * STAGE, idesc_s);
+      tc::mma_commit(&sm.bar_s_full[slot]);
+      if (j + 2 >= ntiles) tc::mma_commit(&sm.bar_s_done);   // this issuer's last tile of the item
+    }
+    __syncwarp();
+    TL_STAMP(tl, 3, t);
+    j += 2;
+    rst.next(Smem::ST); rst.next(Smem::ST);
+    rsl.next(NS); rsl.next(NS);
   }
 }
 // score-MMA issuer shared by both backward kernels: S'(t) -> slot t % NS as soon as the K/Q tile has landed and the
 // slot's previous gradient MMAs are done.  The k-step count is dispatched ONCE, outside the loops (an indirect
 // branch per tile costs hundreds of cycles on the issuing warp, which is the critical resource).
 template <int KATOMS, class Smem>
-__device__ __forceinline__ void cb_score_issuer(Smem& sm, uint32_t tmem, CbPlan pl, int nks, int ntiles, int my_items) {
+__device__ __forceinline__ void cb_score_issuer(Smem& sm, uint32_t tmem, CbPlan pl, int nks, int ntiles, int my_items, int sidx,
+                                                long long* tl = nullptr) {
   switch (nks) {
-    case 1: cb_score_loop<KATOMS, 1>(sm, tmem, pl, ntiles, my_items); break;
-    case 2: cb_score_loop<KATOMS, 2>(sm, tmem, pl, ntiles, my_items); break;
-    case 3: cb_score_loop<KATOMS, 3>(sm, tmem, pl, ntiles, my_items); break;
-    case 4: cb_score_loop<KATOMS, 4>(sm, tmem, pl, ntiles, my_items); break;
-    case 5: cb_score_loop<KATOMS, 5>(sm, tmem, pl, ntiles, my_items); break;
-    case 6: cb_score_loop<KATOMS, 6>(sm, tmem, pl, ntiles, my_items); break;
-    case 7: cb_score_loop<KATOMS, 7>(sm, tmem, pl, ntiles, my_items); break;
-    case 8: cb_score_loop<KATOMS, 8>(sm, tmem, pl, ntiles, my_items); break;
-    case 9: cb_score_loop<KATOMS, 9>(sm, tmem, pl, ntiles, my_items); break;
-    case 10: cb_score_loop<KATOMS, 10>(sm, tmem, pl, ntiles, my_items); break;
-    default: cb_score_loop<KATOMS, 11>(sm, tmem, pl, ntiles, my_items); break;
+    case 1: cb_score_loop<KATOMS, 1>(sm, tmem, pl, ntiles, my_items, sidx, tl); break;
+    case 2: cb_score_loop<KATOMS, 2>(sm, tmem, pl, ntiles, my_items, sidx, tl); break;
+    case 3: cb_score_loop<KATOMS, 3>(sm, tmem, pl, ntiles, my_items, sidx, tl); break;
+    case 4: cb_score_loop<KATOMS, 4>(sm, tmem, pl, ntiles, my_items, sidx, tl); break;
+    case 5: cb_score_loop<KATOMS, 5>(sm, tmem, pl, ntiles, my_items, sidx, tl); break;
+    case 6: cb_score_loop<KATOMS, 6>(sm, tmem, pl, ntiles, my_items, sidx, tl); break;
+    case 7: cb_score_loop<KATOMS, 7>(sm, tmem, pl, ntiles, my_items, sidx, tl); break;
+    case 8: cb_score_loop<KATOMS, 8>(sm, tmem, pl, ntiles, my_items, sidx, tl); break;
+    case 9: cb_score_loop<KATOMS, 9>(sm, tmem, pl, ntiles, my_items, sidx, tl); break;
+    case 10: cb_score_loop<KATOMS, 10>(sm, tmem, pl, ntiles, my_items, sidx, tl); break;
+    default: cb_score_loop<KATOMS, 11>(sm, tmem, pl, ntiles, my_items, sidx, tl); break;
   }
 }
 
 // gradient-MMA issuer shared by both backward kernels: acc (+)= dS(t)[TMEM slot] . streamed tile (MN-major view), N = n_acc
 template <int KATOMS, class Smem>
-__device__ __forceinline__ void cb_grad_issuer(Smem& sm, uint32_t tmem, CbPlan pl, uint32_t idesc, int ntiles, int my_items, int dbg) {
+__device__ __forceinline__ void cb_grad_issuer(Smem& sm, uint32_t tmem, CbPlan pl, uint32_t idesc, int ntiles, int my_items, int dbg,
+                                               long long* tl = nullptr) {
   constexpr uint32_t STRM_ATOM = (CB_BN * 128) >> 4, STAGE = KATOMS * STRM_ATOM;
   const uint32_t b_lo = tc::desc_lo_mn(smem_u32(sm.strm[0][0]), CB_BN * 128);
   const int NS = pl.NS;
@@ -492,9 +546,11 @@ __device__ __forceinline__ void cb_grad_issuer(Smem& sm, uint32_t tmem, CbPlan p
     for (int jj = 0; jj < ntiles; ++jj, rst.next(Smem::ST), rsl.next(NS)) {
       const int st = rst.i, slot = rsl.i;
       const uint32_t tslot = tmem + pl.col_slot0 + 64 * slot;
+      TL_STAMP(tl, 4, it * ntiles + jj);
       tc::mbar_wait(&sm.bar_p_ready[slot], rsl.ph);
       if (jj == 0 && it > 0) tc::mbar_wait(&sm.bar_acc_free, (it - 1) & 1);   // previous item's accumulator has been drained
       tc::tc_fence_after();
+      TL_STAMP(tl, 5, it * ntiles + jj);
       if (tc::elect_one()) {
         const uint32_t bb = b_lo + st * STAGE;
 #pragma unroll
@@ -505,6 +561,7 @@ __device__ __forceinline__ void cb_grad_issuer(Smem& sm, uint32_t tmem, CbPlan p
         if (jj == ntiles - 1) tc::mma_commit(&sm.bar_final);
       }
       __syncwarp();
+      TL_STAMP(tl, 6, it * ntiles + jj);
     }
   }
 }
@@ -577,25 +634,28 @@ template <int KATOMS, int DVH>
 __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dq_cc_kernel(
     const __grid_constant__ CUtensorMap tm_q_stat, const __grid_constant__ CUtensorMap tm_k_strm,
     const float* __restrict__ v, const float* __restrict__ d_o, const float* __restrict__ delta, float* __restrict__ dqa, int L,
-    int KD, int NQ, int C1, int nqt, int nitems, int dbg) {
+    int KD, int NQ, int C1, int nqt, int nitems, int dbg, long long* __restrict__ tl_buf) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  typedef CbSmem<KATOMS, CB_BN * DVH, CB_BM * KATOMS * 64> Smem;
+  typedef CbSmem<KATOMS, CB_BN * DVH, CB_BM * (KATOMS * 64 - 16), DVH + 1> Smem;
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int ST = Smem::ST;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = (L + CB_BN - 1) / CB_BN;
   const int my_items = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const CbPlan pl = cb_plan(KATOMS, NQ);
+  // clock timeline of one CTA (tools/attn_timeline.py): lane 0 of the issuing warps and of each warpgroup's first warp
+  long long* const tl = (tl_buf != nullptr && blockIdx.x == TL_CTA && lane == 0) ? tl_buf : nullptr;
 
-  cb_init<KATOMS>(sm, warp, lane, &tm_q_stat, &tm_k_strm, nqt);
+  cb_init<KATOMS>(sm, warp, lane, &tm_q_stat, &tm_k_strm, nqt, d_o, DVH, delta, 1, L);
   const uint32_t tmem = sm.tmem_base;
 
   if (warp == CB_W_TMA) {
-    if (lane == 0) cb_producer<KATOMS>(sm, &tm_q_stat, &tm_k_strm, v, DVH, nullptr, 0, L, nqt, ntiles, my_items, dbg);
-  } else if (warp == CB_W_S) {
-    cb_score_issuer<KATOMS>(sm, tmem, pl, C1 >> 4, ntiles, my_items);
+    if (lane == 0)
+      cb_producer<KATOMS>(sm, &tm_q_stat, &tm_k_strm, v, DVH, nullptr, 0, d_o, DVH, delta, 1, L, nqt, ntiles, my_items, dbg, tl);
+  } else if (warp == CB_W_S || warp == CB_W_S2) {
+    cb_score_issuer<KATOMS>(sm, tmem, pl, C1 >> 4, ntiles, my_items, warp == CB_W_S ? 0 : 1, warp == CB_W_S ? tl : nullptr);
   } else if (warp == CB_W_G) {
-    cb_grad_issuer<KATOMS>(sm, tmem, pl, tc::idesc_bf16_f32(CB_BM, NQ) | (1u << 16), ntiles, my_items, dbg);
+    cb_grad_issuer<KATOMS>(sm, tmem, pl, tc::idesc_bf16_f32(CB_BM, NQ) | (1u << 16), ntiles, my_items, dbg, tl);
   } else {
     const int wg = warp >> 2;
     const int rowi = (warp & 3) * 32 + lane;
@@ -605,7 +665,6 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dq_cc_kernel(
       tc::mbar_wait(&sm.bar_stat, it & 1);
       stationary_to_tmem<KATOMS>(sm.stat, tlane + (uint32_t)((it & (pl.QB - 1)) * KATOMS * 32), rowi);
       tc::mbar_arrive(&sm.bar_a_ready);
-      tc::mbar_arrive(&sm.bar_stat_free);
     };
     if (wg == 0) stage_stat(0);
     uint32_t rs[2][32], pd[32];
@@ -616,21 +675,36 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dq_cc_kernel(
       const int item = blockIdx.x + it * gridDim.x, bn = item / nqt, qt = item - bn * nqt, q0 = qt * CB_BM;
       const int qi = q0 + rowi;
       const size_t row = (size_t)bn * L + qi;
+      // this row's dO and delta came with the stationary tile (a global load here would sit on the item's critical path)
+      if (wg != 0) tc::mbar_wait(&sm.bar_stat, it & 1);
       float go[DVH], ndelta = 0.f;
+      {
+        const float* rsd = sm.rowside[it & 1];
 #pragma unroll
-      for (int e = 0; e < DVH; ++e) go[e] = qi < L ? d_o[row * DVH + e] : 0.f;
-      if (qi < L) ndelta = -delta[row];
+        for (int e = 0; e < DVH; ++e) go[e] = qi < L ? rsd[rowi * DVH + e] : 0.f;
+        if (qi < L) ndelta = -rsd[CB_BM * DVH + rowi];
+      }
+      tc::mbar_arrive(&sm.bar_stat_free);
       for (int j = (wg + CB_NWG - qt % CB_NWG) % CB_NWG; j < ntiles; j += CB_NWG) {   // tile -> warpgroup (j + qt) % 3
-        for (const int t = it * ntiles + j; tcur < t; ++tcur) { rst.next(ST); rsl.next(NS); }
+        {
+          const int t = it * ntiles + j, dlt = t - tcur;             // 3 inside an item, 1..5 across an item boundary
+          if (dlt == CB_NWG && ST >= CB_NWG && NS >= CB_NWG) { rst.advance(CB_NWG, ST); rsl.advance(CB_NWG, NS); }
+          else for (int i = 0; i < dlt; ++i) { rst.next(ST); rsl.next(NS); }
+          tcur = t;
+        }
         const int slot = rsl.i, st = rst.i;
         const uint32_t tslot = tlane + pl.col_slot0 + 64 * slot;
         const int nvalid = L - j * CB_BN;
         const bool tail = nvalid < CB_BN;
+        long long* const tw = (warp & 3) == 0 ? tl : nullptr;
+        TL_STAMP(tw, 7, it * ntiles + j);
         tc::mbar_wait(&sm.bar_s_full[slot], rsl.ph);
         tc::tc_fence_after();
+        TL_STAMP(tw, 8, it * ntiles + j);
         tc::tmem_ld_x32(tslot, rs[0]);
         tc::tmem_ld_x32(tslot + 32, rs[1]);
         tc::tmem_ld_wait();
+        TL_STAMP(tw, 9, it * ntiles + j);
         const uint32_t vt = smem_u32(sm.side[st]);
         if (dbg & 8) {
 #pragma unroll
@@ -640,48 +714,64 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dq_cc_kernel(
           for (int i = 0; i < 32; ++i) pd[i] = tc::pack_bf16x2(__uint_as_float(rs[0][i]) * ndelta, __uint_as_float(rs[1][i]) * go[0]);
         } else if (tail) dq_cc_tile<DVH, true>(rs, pd, vt, nvalid, go, ndelta);
         else dq_cc_tile<DVH, false>(rs, pd, vt, nvalid, go, ndelta);
+        TL_STAMP(tw, 10, it * ntiles + j);
         tc::tmem_st_x32(tslot, pd);                    // dS (bf16) over S'[0,32): all of S' is in registers
         tc::tmem_st_wait();
         tc::tc_fence_before();
         tc::mbar_arrive(&sm.bar_p_ready[slot]);
         tc::mbar_arrive(&sm.bar_empty[st]);            // value tile consumed
+        TL_STAMP(tw, 11, it * ntiles + j);
       }
-      if (wg == 0 && pl.QB == 2 && it + 1 < my_items) stage_stat(it + 1);   // lets the score issuer run ahead during the drain
-      // ---- drain dQa: TMEM -> shared staging tile -> one bulk store of nrows x KD contiguous floats ----
-      tc::mbar_wait(&sm.bar_final, it & 1);
-      tc::tc_fence_after();
-      if (bulk_out) {
-        if (threadIdx.x == 0) bulk_wait_read();        // the previous item's store has finished reading the staging tile
-        asm volatile("bar.sync 1, %0;" ::"n"(128 * CB_NWG) : "memory");
-        for (int c0 = wg * 32; c0 < NQ; c0 += 32 * CB_NWG) {
-          tc::tmem_ld_x32(tlane + pl.col_acc + c0, rs[0]);
-          tc::tmem_ld_wait();
-          const uint32_t dst = smem_u32(sm.out + rowi * KD + c0);
-#pragma unroll
-          for (int e = 0; e < 32; e += 4)
-            if (c0 + e < KD)
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + e * 4), "r"(rs[0][e]), "r"(rs[0][e + 1]),
-                           "r"(rs[0][e + 2]), "r"(rs[0][e + 3]) : "memory");
+      // ---- drain dQa (warpgroup 0 alone; the others go straight on with the next item's tiles, so the score slots are full
+      //      again when the accumulator is released): TMEM -> shared staging tile -> one bulk store of nrows x KD floats ----
+      if (wg == 0) {
+        TL_STAMP(tl, 12, it * 4 + 0);
+        if (it + 1 < my_items) {                       // single stationary buffer: refill once the item's score MMAs are done
+          tc::mbar_wait(&sm.bar_s_done, it & 1);
+          tc::tc_fence_after();
+          stage_stat(it + 1);
         }
-        tc::tc_fence_before();
-        tc::mbar_arrive(&sm.bar_acc_free);             // the accumulator columns may be overwritten by the next item
-        tc::fence_proxy_async();
-        asm volatile("bar.sync 1, %0;" ::"n"(128 * CB_NWG) : "memory");
-        if (threadIdx.x == 0) bulk_s2g(dqa + ((size_t)bn * L + q0) * KD, sm.out, (uint32_t)(min(CB_BM, L - q0) * KD * 4));
-      } else {
-        for (int c0 = wg * 32; c0 < NQ; c0 += 32 * CB_NWG) {
-          tc::tmem_ld_x32(tlane + pl.col_acc + c0, rs[0]);
-          tc::tmem_ld_wait();
-          if (qi < L) {
+        tc::mbar_wait(&sm.bar_final, it & 1);
+        tc::tc_fence_after();
+        TL_STAMP(tl, 12, it * 4 + 1);
+        if (bulk_out) {
+          if (threadIdx.x == 0) bulk_wait_read();      // the previous item's store has finished reading the staging tile
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int c0 = 0; c0 < NQ; c0 += 64) {        // two TMEM loads in flight
+            tc::tmem_ld_x32(tlane + pl.col_acc + c0, rs[0]);
+            if (c0 + 32 < NQ) tc::tmem_ld_x32(tlane + pl.col_acc + c0 + 32, rs[1]);
+            tc::tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (c0 + e < KD) dqa[row * KD + c0 + e] = __uint_as_float(rs[0][e]);
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t dst = smem_u32(sm.out + rowi * KD + c0 + 32 * h);
+#pragma unroll
+              for (int e = 0; e < 32; e += 4)
+                if (c0 + 32 * h + e < KD)
+                  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + e * 4), "r"(rs[h][e]), "r"(rs[h][e + 1]),
+                               "r"(rs[h][e + 2]), "r"(rs[h][e + 3]) : "memory");
+            }
           }
+          tc::tc_fence_before();
+          tc::mbar_arrive(&sm.bar_acc_free);           // the accumulator columns may be overwritten by the next item
+          TL_STAMP(tl, 12, it * 4 + 2);
+          tc::fence_proxy_async();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (threadIdx.x == 0) bulk_s2g(dqa + ((size_t)bn * L + q0) * KD, sm.out, (uint32_t)(min(CB_BM, L - q0) * KD * 4));
+          TL_STAMP(tl, 12, it * 4 + 3);
+        } else {
+          for (int c0 = 0; c0 < NQ; c0 += 32) {
+            tc::tmem_ld_x32(tlane + pl.col_acc + c0, rs[0]);
+            tc::tmem_ld_wait();
+            if (qi < L) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (c0 + e < KD) dqa[row * KD + c0 + e] = __uint_as_float(rs[0][e]);
+            }
+          }
+          tc::tc_fence_before();
+          tc::mbar_arrive(&sm.bar_acc_free);
         }
-        tc::tc_fence_before();
-        tc::mbar_arrive(&sm.bar_acc_free);
       }
-      if (wg == 0 && pl.QB == 1 && it + 1 < my_items) stage_stat(it + 1);
     }
     if (threadIdx.x == 0) bulk_wait_read();
   }
@@ -698,7 +788,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
     const float* __restrict__ v, const float* __restrict__ d_o, const float* __restrict__ delta, float* __restrict__ dk,
     float* __restrict__ dv, bf16* __restrict__ dqkvh, int KPq, int nh, int L, int dkh, int C1, int nqt, int nitems) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  typedef CbSmem<KATOMS, CB_BN * (DVH + 1), 0> Smem;
+  typedef CbSmem<KATOMS, CB_BN * (DVH + 1), 0, DVH> Smem;
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int ST = Smem::ST;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -707,13 +797,14 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
   const CbPlan pl = cb_plan(KATOMS, 32);
   __shared__ float dv_xch[2][CB_NWG - 1][CB_BM][DVH];   // dV partials of warpgroups 1.. (registers -> WG0), by item parity
 
-  cb_init<KATOMS>(sm, warp, lane, &tm_k_stat, &tm_q_strm, nqt);
+  cb_init<KATOMS>(sm, warp, lane, &tm_k_stat, &tm_q_strm, nqt, v, DVH, nullptr, 0, L);
   const uint32_t tmem = sm.tmem_base;
 
   if (warp == CB_W_TMA) {
-    if (lane == 0) cb_producer<KATOMS>(sm, &tm_k_stat, &tm_q_strm, d_o, DVH, delta, 1, L, nqt, ntiles, my_items, 0);
-  } else if (warp == CB_W_S) {
-    cb_score_issuer<KATOMS>(sm, tmem, pl, C1 >> 4, ntiles, my_items);
+    if (lane == 0)
+      cb_producer<KATOMS>(sm, &tm_k_stat, &tm_q_strm, d_o, DVH, delta, 1, v, DVH, nullptr, 0, L, nqt, ntiles, my_items, 0);
+  } else if (warp == CB_W_S || warp == CB_W_S2) {
+    cb_score_issuer<KATOMS>(sm, tmem, pl, C1 >> 4, ntiles, my_items, warp == CB_W_S ? 0 : 1);
   } else if (warp == CB_W_G) {
     cb_grad_issuer<KATOMS>(sm, tmem, pl, tc::idesc_bf16_f32(CB_BM, 32) | (1u << 16), ntiles, my_items, 0);
   } else {
@@ -725,7 +816,6 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
       tc::mbar_wait(&sm.bar_stat, it & 1);
       stationary_to_tmem<KATOMS>(sm.stat, tlane + (uint32_t)((it & (pl.QB - 1)) * KATOMS * 32), rowi);
       tc::mbar_arrive(&sm.bar_a_ready);
-      tc::mbar_arrive(&sm.bar_stat_free);
     };
     if (wg == 0) stage_stat(0);
     uint32_t rs[2][32], pd[32];
@@ -736,12 +826,19 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
       const int item = blockIdx.x + it * gridDim.x, bn = item / nqt, qt = item - bn * nqt, k0 = qt * CB_BM;
       const int kj = k0 + rowi;
       const size_t row = (size_t)bn * L + kj;
+      if (wg != 0) tc::mbar_wait(&sm.bar_stat, it & 1);   // this row's v came with the stationary tile
       float vk[DVH], dvacc[DVH];
 #pragma unroll
-      for (int e = 0; e < DVH; ++e) { vk[e] = kj < L ? v[row * DVH + e] : 0.f; dvacc[e] = 0.f; }
+      for (int e = 0; e < DVH; ++e) { vk[e] = kj < L ? sm.rowside[it & 1][rowi * DVH + e] : 0.f; dvacc[e] = 0.f; }
+      tc::mbar_arrive(&sm.bar_stat_free);
       // tile -> warpgroup (j + qt) % 3: fixed per item, so the dV partial sums do not depend on where the item runs
       for (int j = (wg + CB_NWG - qt % CB_NWG) % CB_NWG; j < ntiles; j += CB_NWG) {
-        for (const int t = it * ntiles + j; tcur < t; ++tcur) { rst.next(ST); rsl.next(NS); }
+        {
+          const int t = it * ntiles + j, dlt = t - tcur;             // 3 inside an item, 1..5 across an item boundary
+          if (dlt == CB_NWG && ST >= CB_NWG && NS >= CB_NWG) { rst.advance(CB_NWG, ST); rsl.advance(CB_NWG, NS); }
+          else for (int i = 0; i < dlt; ++i) { rst.next(ST); rsl.next(NS); }
+          tcur = t;
+        }
         const int slot = rsl.i, st = rst.i;
         const uint32_t tslot = tlane + pl.col_slot0 + 64 * slot;
         const int nvalid = L - j * CB_BN;
@@ -760,23 +857,28 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
         tc::mbar_arrive(&sm.bar_p_ready[slot]);
         tc::mbar_arrive(&sm.bar_empty[st]);
       }
-      if (wg == 0 && pl.QB == 2 && it + 1 < my_items) stage_stat(it + 1);
+      // warpgroups 1, 2 hand their dV partials over and go on with the next item; warpgroup 0 finishes the item
       if (wg > 0) {
 #pragma unroll
         for (int e = 0; e < DVH; ++e) dv_xch[it & 1][wg - 1][rowi][e] = dvacc[e];
+        tc::mbar_arrive(&sm.bar_dv);
+        continue;
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(128 * CB_NWG) : "memory");
+      if (it + 1 < my_items) {                         // single stationary buffer: refill once the item's score MMAs are done
+        tc::mbar_wait(&sm.bar_s_done, it & 1);
+        tc::tc_fence_after();
+        stage_stat(it + 1);
+      }
       tc::mbar_wait(&sm.bar_final, it & 1);
       tc::tc_fence_after();
+      tc::mbar_wait(&sm.bar_dv, it & 1);
       const int b = bn / nh, n = bn - b * nh;
       bf16* prow = dqkvh ? dqkvh + ((size_t)b * L + kj) * KPq : nullptr;
-      if (wg == 0) {
-        tc::tmem_ld_x32(tlane + pl.col_acc, rs[0]);
-        tc::tmem_ld_wait();
-      }
+      tc::tmem_ld_x32(tlane + pl.col_acc, rs[0]);
+      tc::tmem_ld_wait();
       tc::tc_fence_before();
-      tc::mbar_arrive(&sm.bar_acc_free);               // dK is in WG0's registers: the accumulator may be overwritten
-      if (wg == 0 && kj < L) {
+      tc::mbar_arrive(&sm.bar_acc_free);               // dK is in registers: the accumulator may be overwritten
+      if (kj < L) {
         if (prow) {
           bf16* dst = prow + nh * dkh + n * dkh;
           if (((dkh | KPq) & 3) == 0) {
@@ -807,7 +909,6 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
           else dv[row * DVH + e] = t;
         }
       }
-      if (wg == 0 && pl.QB == 1 && it + 1 < my_items) stage_stat(it + 1);
     }
   }
   tc::tc_fence_before();
@@ -858,7 +959,7 @@ int launch_bwd_cc(const Dims& d, const AugLayout& a, const void* qa, const void*
   const int nqt = cdiv(d.L, CB_BM), nitems = nqt * d.BN;
   const int grid = std::min(nitems, sm_count());
   {
-    const size_t smem = sizeof(CbSmem<KATOMS, CB_BN * (DVH + 1), 0>) + 1024;
+    const size_t smem = sizeof(CbSmem<KATOMS, CB_BN * (DVH + 1), 0, DVH>) + 1024;
     auto kern = attn_bwd_dkv_cc_kernel<KATOMS, DVH>;
     AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, CB_THREADS, smem, st>>>(tk_stat, tq_strm, v, d_o, delta, dk, dv, static_cast<bf16*>(dqkvh), KPq, d.nh, d.L, d.dkh, a.C1,
@@ -866,10 +967,10 @@ int launch_bwd_cc(const Dims& d, const AugLayout& a, const void* qa, const void*
     AACONV_LAUNCH_OK("attn_bwd_dkv_cc");
   }
   {
-    const size_t smem = sizeof(CbSmem<KATOMS, CB_BN * DVH, CB_BM * KATOMS * 64>) + 1024;
+    const size_t smem = sizeof(CbSmem<KATOMS, CB_BN * DVH, CB_BM * (KATOMS * 64 - 16), DVH + 1>) + 1024;
     auto kern = attn_bwd_dq_cc_kernel<KATOMS, DVH>;
     AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, CB_THREADS, smem, st>>>(tq_stat, tk_strm, v, d_o, delta, dqa, d.L, a.KD, a.NQ, a.C1, nqt, nitems, g_attn_dbg_mode);
+    kern<<<grid, CB_THREADS, smem, st>>>(tq_stat, tk_strm, v, d_o, delta, dqa, d.L, a.KD, a.NQ, a.C1, nqt, nitems, g_attn_dbg_mode, g_attn_dbg);
     AACONV_LAUNCH_OK("attn_bwd_dq_cc");
   }
   return 0;

@@ -123,7 +123,7 @@ int aaconv_auroc(const float* logits, const float* targets, int N, int C, float*
  *                         '\n'-joined kernel names; returns the number of entries written (<= max_entries). */
 long long aaconv_launch_count(void);
 /* Debug hooks of the attention kernels (tools/attn_timeline.py, tools/attn_ablate.py); both default to off.
- *   aaconv_debug_set_timeline  device buffer of 12 x 64 int64: CTA-level clock64 stamps of the dQa kernel (NULL = off)
+ *   aaconv_debug_set_timeline  device buffer of 16 x 96 int64: clock64 stamps of one persistent CTA of the dQa kernel (NULL = off)
  *   aaconv_debug_set_mode      ablation bits: 1 no MUFU, 2 no global traffic after the first tiles, 4 no gradient MMAs,
  *                              8 no math -- results are WRONG when non-zero; timing experiments only                */
 void aaconv_debug_set_timeline(void* device_buffer);

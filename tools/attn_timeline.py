@@ -1,8 +1,11 @@
-"""Dump the clock64 timeline CTA (0,0) of attn_bwd_dq_tc_kernel records through the debug hook (GPU box).
+"""Clock64 timeline of one persistent CTA (blockIdx.x == 40) of attn_bwd_dq_cc_kernel through the debug hook (GPU box).
 
-python tools/attn_timeline.py  -> per-tile stamps relative to the first one (cycles)
-events: 0 MMA: K tile landed   1 MMA: S,dP issued   2 MMA: p_ready seen   3 WG: start waiting for S   4 WG: S ready
-        5 WG: first TMEM load done   6 WG: arrived p_ready   7 [wg, ...] epilogue: loop end / final seen / stores done
+python tools/attn_timeline.py [ablation mode]  -> per-tile stamps relative to the first one (cycles); column = global tile
+index of the CTA (item * ntiles + tile).  Events (chexpert_b200/csrc/attn_cc.cu, TL_STAMP):
+   0 S: loop top   1 S: K tile landed   2 S: slot free   3 S: issued+committed     4 G: loop top   5 G: dS ready   6 G: issued
+   7 WG: waiting for S'   8 WG: S' ready   9 WG: S' in registers   10 WG: math done   11 WG: dS stored, arrived
+  12 drain, per item (warpgroup 0): final wait begin / final seen / accumulator free / bulk store issued
+  14 TMA: stage free
 """
 import ctypes
 import os
@@ -13,13 +16,14 @@ import chexpert_b200 as cb  # noqa: E402
 from chexpert_b200 import _lib  # noqa: E402
 from bench import SHAPES    # noqa: E402
 
+EV, COLS = 16, 96
 cin, hin, cout, dk, dv = SHAPES['T1']
 H = hin // 2
 torch.manual_seed(0)
 m = cb.AAConv2d(cin, cout, 3, 2, dk, dv, 8, True, (H, H), precision='bf16').cuda()
 x = torch.relu(torch.randn(16, cin, hin, hin, device='cuda')).requires_grad_(True)
 dy = torch.randn(16, cout, H, H, device='cuda')
-buf = torch.zeros(12 * 64, dtype=torch.int64, device='cuda')
+buf = torch.zeros(EV * COLS, dtype=torch.int64, device='cuda')
 lib = _lib.load()
 if len(sys.argv) > 1:
     lib.aaconv_debug_set_mode(int(sys.argv[1]))
@@ -32,11 +36,14 @@ for it in range(3):
     y.backward(dy)
 torch.cuda.synchronize()
 lib.aaconv_debug_set_timeline(None)
-t = buf.cpu().reshape(12, 64)
+lib.aaconv_debug_set_mode(0)
+t = buf.cpu().reshape(EV, COLS)
 t0 = int(t[t > 0].min())
-names = ['S:top', 'S:K landed', 'S:slot free', 'S:issued', 'G:p_ready', 'wg:wait S', 'wg:S ready', 'wg:arrive']
-order = [8, 0, 9, 1, 2, 3, 4, 6]
-print('tile ' + ' '.join(f'{n:>13s}' for n in names))
-for j in range(26):
-    print(f'{j:4d} ' + ' '.join(f'{(int(t[e, j]) - t0) if t[e, j] > 0 else -1:13d}' for e in order))
-print('CTA [entry, init done, stat landed, A in TMEM, loop end, final seen, stores done, after sync]:', [int(v) - t0 for v in t[10, :8]])
+names = ['TMA:free', 'S:top', 'S:landed', 'S:slot', 'S:issued', 'wg:wait', 'wg:S rdy', 'wg:in reg', 'wg:math', 'wg:arrive', 'G:top', 'G:dS rdy', 'G:issued']
+order = [14, 0, 1, 2, 3, 7, 8, 9, 10, 11, 4, 5, 6]
+print('tile ' + ' '.join(f'{n:>9s}' for n in names))
+for j in range(0, 80):
+    print(f'{j:4d} ' + ' '.join(f'{(int(t[e, j]) - t0) if t[e, j] > 0 else -1:9d}' for e in order))
+print('drain per item (warpgroup 0): [wait final, final seen, accumulator free, store issued]')
+for i in range(0, 4):
+    print(i, [int(v) - t0 if v > 0 else -1 for v in t[12, i * 4:i * 4 + 4]])
