@@ -112,7 +112,7 @@ __device__ __forceinline__ void fwd_cc_half(uint32_t (&r)[2][32], uint32_t vt, i
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float p = tc::ex2f(__uint_as_float(r[c][i + u]) + mneg);
+        const float p = tc::ex2_mixed(__uint_as_float(r[c][i + u]) + mneg, u);
         if (u & 1) l2 += p; else l += p;
 #pragma unroll
         for (int e = 0; e < DVH; ++e) {
@@ -586,7 +586,7 @@ __device__ __forceinline__ void dq_cc_tile(const uint32_t (&rs)[2][32], uint32_t
         float dp = ndelta;
 #pragma unroll
         for (int e = 0; e < DVH; ++e) dp = fmaf(go[e], vv[u * DVH + e], dp);
-        ds[u] = tc::ex2f(__uint_as_float(rs[c][i + u])) * dp;
+        ds[u] = tc::ex2_mixed(__uint_as_float(rs[c][i + u]), u) * dp;
         if (TAIL && c * 32 + i + u >= nvalid) ds[u] = 0.f;     // zero-filled keys past L
       }
       pd[c * 16 + (i >> 1)] = tc::pack_bf16x2(ds[0], ds[1]);
@@ -616,7 +616,7 @@ __device__ __forceinline__ void dkv_cc_tile(const uint32_t (&rs)[2][32], uint32_
         float dp = -dls[u];
 #pragma unroll
         for (int e = 0; e < DVH; ++e) dp = fmaf(gg[u * DVH + e], vk[e], dp);
-        float p = tc::ex2f(__uint_as_float(rs[c][i + u]));
+        float p = tc::ex2_mixed(__uint_as_float(rs[c][i + u]), u);
         const bool dead = TAIL && c * 32 + i + u >= nvalid;    // zero-filled queries past L: the side tile holds stale data there
         if (dead) { p = 0.f; dp = 0.f; }
 #pragma unroll

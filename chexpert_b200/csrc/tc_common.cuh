@@ -244,6 +244,29 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax polynomial for
+// 2^f (max relative error 7.5e-5, far inside the bf16 budget of everything these exponentials feed), exponent added in the
+// integer domain -- the FlashAttention-4 trick for loops bound by MUFU.EX2 (16 / clk / SM).  x is clamped at -126 (result
+// 2^-126 instead of 0: these terms are sums' far tails); callers guarantee x < 127.
+// MEASURED (B200, T1, B=16, round 1): moving 1 of every 4 exponentials here made all three attention kernels 3-6 % SLOWER
+// (fwd 131 -> 135 us, dK/dV 170 -> 178, dQa 153 -> 162): with three math warps per scheduler the loops are bound by the
+// dependent-issue latency of each warp's own instruction stream, not by MUFU throughput, and the polynomial adds ~9
+// instructions per element.  Kept behind AACONV_EX2_POLY_OF_4 (default 0 = every exponential on MUFU).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;                    // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 0.0551716610789299f, 0.2426111251115799f);
+  p = fmaf(f, p, 0.6932609677314758f);
+  p = fmaf(f, p, 0.9999280571937561f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+#ifndef AACONV_EX2_POLY_OF_4
+#define AACONV_EX2_POLY_OF_4 0
+#endif
+// element u (0..3) of an unrolled group of four: the last EX2_POLY_OF_4 of them take the polynomial
+__device__ __forceinline__ float ex2_mixed(float x, int u) { return u >= 4 - AACONV_EX2_POLY_OF_4 ? ex2_poly(x) : ex2f(x); }
+
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------------
