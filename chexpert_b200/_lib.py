@@ -48,6 +48,7 @@ SYMBOLS = {
     'aaconv_launch_count': (ctypes.c_longlong, []),
     'aaconv_debug_set_timeline': (None, [_P]),
     'aaconv_debug_set_mode': (None, [ctypes.c_int]),
+    'aaconv_debug_read_mbar_log': (ctypes.c_int, [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]),
     'aaconv_profile_begin': (ctypes.c_int, [_P]),
     'aaconv_profile_end': (ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_float), ctypes.c_int]),
 }

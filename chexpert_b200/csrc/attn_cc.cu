@@ -22,10 +22,33 @@ typedef __nv_bfloat16 bf16;
 // ablation switches for tools/attn_ablate.py (0 in production): 1 no MUFU, 2 no global traffic after the first tiles,
 // 4 no gradient MMAs, 8 no math at all
 int g_attn_dbg_mode = 0;
+static unsigned long long* g_mbar_host_log = nullptr;
 extern long long* g_attn_dbg;      // attn_tc_bwd.cu: timeline buffer of TL_EVENTS x TL_COLS stamps (tools/attn_timeline.py)
 constexpr int TL_COLS = 96, TL_CTA = 40;
 #define TL_STAMP(tl, ev, col) do { if ((tl) && (col) < TL_COLS) (tl)[(ev) * TL_COLS + (col)] = clock64(); } while (0)
-extern "C" void aaconv_debug_set_mode(int m) { g_attn_dbg_mode = m; }
+extern "C" void aaconv_debug_set_mode(int m) {
+  g_attn_dbg_mode = m & 47;            // bit 32: dQa drain by per-row stores instead of the bulk store
+  const unsigned soft = (m >> 4) & 1;                    // bit 16: soft mbarrier timeouts in this file's kernels (see tc_common.cuh)
+  static unsigned long long* host_log = nullptr;
+  if (soft && !host_log) cudaHostAlloc(reinterpret_cast<void**>(&host_log), 65 * sizeof(unsigned long long), cudaHostAllocMapped);
+  if (host_log) {
+    for (int i = 0; i < 65; ++i) host_log[i] = 0;
+    unsigned long long* dev = nullptr;
+    cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev), host_log, 0);
+    cudaMemcpyToSymbol(tc::g_mbar_log, &dev, sizeof dev);
+  }
+  cudaMemcpyToSymbol(tc::g_mbar_soft, &soft, sizeof soft);
+  g_mbar_host_log = host_log;
+}
+// -> number of timed-out waits logged since the mode was set (readable even after the kernel faulted: the log lives in mapped
+// host memory); out[i] = smem barrier address << 32 | parity << 31 | block << 12 | thread
+extern "C" void* aaconv_debug_host_log(void) { return g_mbar_host_log; }
+extern "C" int aaconv_debug_read_mbar_log(unsigned long long* out, int max_entries) {
+  if (!g_mbar_host_log) return 0;
+  const int n = (int)g_mbar_host_log[0];
+  for (int i = 0; i < n && i < 64 && i < max_entries; ++i) out[i] = g_mbar_host_log[1 + i];
+  return n;
+}
 
 namespace {
 
@@ -154,7 +177,7 @@ struct __align__(1024) CfSmem {
   bf16 q[KATOMS][CF_BM * 64];
   bf16 k[ST][KATOMS][CF_BN * 64];
   float vt[ST][CF_BN * DVH];                  // fp32 values of the key tile
-  float xch[2][CF_NWG - 1][CF_BM][4];         // WG1.. -> WG0 hand-over of (m, l, o[0..DVH)), double-buffered by item parity
+  float xch[2][CF_NWG][CF_BM][4];             // per tile class (j % 3): partial (m, l, o[0..DVH)), double-buffered by item parity
   uint64_t bar_q, bar_q_free, bar_a_ready, bar_final, bar_full[ST], bar_empty[ST], bar_s_full[CF_SLOTS], bar_slot_free[CF_SLOTS];
   uint32_t tmem_base;
 };
@@ -278,9 +301,13 @@ __global__ void __launch_bounds__(CF_THREADS, 1) attn_fwd_cc_kernel(
       float m = -INFINITY, l = 0.f, acc[DVH];
 #pragma unroll
       for (int e = 0; e < DVH; ++e) acc[e] = 0.f;
-      // tile j of this item belongs to warpgroup (j + qt) % 3: a function of the item alone (results do not depend on
-      // which CTA / in which order the item runs -- batch independence bit for bit), rotating with qt for balance
-      for (int j = (wg + CF_NWG - qt % CF_NWG) % CF_NWG; j < ntiles; j += CF_NWG) {
+      // GLOBAL tile t belongs to warpgroup t % 3, so a warpgroup meets a given score slot at a fixed stride and observes its
+      // barrier phases in order (an item-dependent map let a warpgroup jump 4-5 tiles at an item boundary and mistake
+      // an unfinished phase for a finished one: parity waits only tell neighbours apart).  Inside the item the warpgroup
+      // therefore owns the tiles of ONE class j % 3 = cls; partial results are stored and merged BY CLASS, in class order,
+      // so the output does not depend on where or when the item runs (batch independence bit for bit).
+      const int cls = (wg + CF_NWG - (it * ntiles) % CF_NWG) % CF_NWG;
+      for (int j = cls; j < ntiles; j += CF_NWG) {
         for (const int t = it * ntiles + j; tcur < t; ++tcur) { rst.next(ST); rsl.next(NS); }
         const int slot = rsl.i, st = rst.i;
         const uint32_t tslot = tlane + COL_SLOT0 + 128 * slot;
@@ -312,8 +339,8 @@ __global__ void __launch_bounds__(CF_THREADS, 1) attn_fwd_cc_kernel(
       }
       // ---- merge the warpgroups' partial results ----
       float(*xch)[CF_BM][4] = sm.xch[it & 1];
-      if (wg > 0) {
-        float* x = xch[wg - 1][rowi];
+      {
+        float* x = xch[cls][rowi];
         x[0] = m;
         x[1] = l;
 #pragma unroll
@@ -321,15 +348,14 @@ __global__ void __launch_bounds__(CF_THREADS, 1) attn_fwd_cc_kernel(
       }
       asm volatile("bar.sync 1, %0;" ::"n"(128 * CF_NWG) : "memory");
       if (wg == 0) {
-        float mm = m;
+        float mm = -INFINITY;
 #pragma unroll
-        for (int g = 0; g < CF_NWG - 1; ++g) mm = fmaxf(mm, xch[g][rowi][0]);
-        const float a0 = tc::ex2f(m - mm);
-        float lt = a0 * l, ot[DVH];
+        for (int g = 0; g < CF_NWG; ++g) mm = fmaxf(mm, xch[g][rowi][0]);
+        float lt = 0.f, ot[DVH];
 #pragma unroll
-        for (int e = 0; e < DVH; ++e) ot[e] = a0 * acc[e];
+        for (int e = 0; e < DVH; ++e) ot[e] = 0.f;
 #pragma unroll
-        for (int g = 0; g < CF_NWG - 1; ++g) {
+        for (int g = 0; g < CF_NWG; ++g) {            // classes in order 0, 1, 2
           const float mg = xch[g][rowi][0];
           const float ag = (mg == -INFINITY) ? 0.f : tc::ex2f(mg - mm);
           lt = fmaf(ag, xch[g][rowi][1], lt);
@@ -373,11 +399,19 @@ template <int KATOMS, bool HAS_OUT> struct CbStages {
 // The pipeline is latency-bound by (tiles in flight) / (S' MMA + TMEM round trip + math + gradient MMA ~ 2700 cycles), i.e. by
 // the number of score slots: the stationary operand gets ONE buffer (it is refilled right after the item's last score MMA,
 // which is when a second buffer would have been filled too) and every remaining column goes to slots.
+// Phase-parity invariant of the two score issuers: with an odd stage count a stage alternates between the issuers, so each
+// of them skips every other phase of bar_full[stage] and a parity wait cannot tell phase u from u+2.  It is still exact
+// as long as the skipped phase (the other issuer's tile t+ST) is complete before the issuer reaches tile t+2*ST, which its
+// slot wait (gradient MMA of tile t+2*ST-NS done) guarantees iff ST >= NS.  Hence NS <= ST for odd ST (an even ST keeps
+// every stage with one issuer).  The 512-pixel dQa kernel (3 stages) deadlocked with 4 slots before this rule.
+// Two score issuers when there are enough stages for both to have a tile in flight; one otherwise.
+__host__ __device__ constexpr int cb_issuers(int stages) { return stages >= 4 ? 2 : 1; }
 struct CbPlan { int QB, NS; uint32_t col_slot0, col_acc; };
-__device__ __forceinline__ CbPlan cb_plan(int katoms, int acc_cols) {
+__device__ __forceinline__ CbPlan cb_plan(int katoms, int acc_cols, int stages) {
   CbPlan p;
   p.QB = 1;
   p.NS = min(CB_MAXSLOTS, (512 - p.QB * katoms * 32 - acc_cols) / 64);
+  if (stages & 1) p.NS = min(p.NS, stages);
   p.col_slot0 = p.QB * katoms * 32;
   p.col_acc = p.col_slot0 + 64 * p.NS;
   return p;
@@ -417,10 +451,10 @@ __device__ __forceinline__ void cb_init(Smem& sm, int warp, int lane, const CUte
     tc::mbar_init(&sm.bar_stat, 1);
     tc::mbar_init(&sm.bar_stat_free, 128 * CB_NWG);   // every math thread has read its row data (WG0: and moved the tile to TMEM)
     tc::mbar_init(&sm.bar_a_ready, 128);
-    tc::mbar_init(&sm.bar_s_done, 2);                 // both score issuers have committed their last tile of the item
+    tc::mbar_init(&sm.bar_s_done, cb_issuers(Smem::ST));   // every score issuer has committed its last tile of the item
     tc::mbar_init(&sm.bar_final, 1);
     tc::mbar_init(&sm.bar_acc_free, 128);             // warpgroup 0 drains the accumulator
-    tc::mbar_init(&sm.bar_dv, 128 * (CB_NWG - 1));
+    tc::mbar_init(&sm.bar_dv, 128 * CB_NWG);
     for (int s = 0; s < Smem::ST; ++s) { tc::mbar_init(&sm.bar_full[s], 1); tc::mbar_init(&sm.bar_empty[s], 129); }
     for (int s = 0; s < CB_MAXSLOTS; ++s) {
       tc::mbar_init(&sm.bar_s_full[s], 1);
@@ -453,12 +487,15 @@ __device__ __forceinline__ void cb_producer(Smem& sm, const CUtensorMap* m_stat,
     for (int j = 0; j < ntiles; ++j, rg.next(Smem::ST)) {
       if (j == jq && it + 1 < my_items) {              // next item's stationary tile: the staging buffer is free once WG0
         const int nitem = item + gridDim.x, nbn = nitem / nqt, nrow0 = (nitem - nbn * nqt) * CB_BM;   // has moved this item's to TMEM
+        tc::hb(1, it * 1000 + j);
         tc::mbar_wait(&sm.bar_stat_free, it & 1);
+        tc::hb(1, 500000 + it * 1000 + j);
         cb_load_stat<KATOMS>(sm, m_stat, r0, RW0, r1, RW1, L, nbn, nrow0, (it + 1) & 1);
       }
       const int s = rg.i;
       const int nvalid = min(CB_BN, L - j * CB_BN);
       const size_t r0 = (size_t)bn * L + (size_t)j * CB_BN;
+      tc::hb(0, it * 1000 + j);
       tc::mbar_wait(&sm.bar_empty[s], rg.ph ^ 1);
       TL_STAMP(tl, 14, it * ntiles + j);
       if ((dbg & 2) && (it > 0 || j >= Smem::ST)) { tc::mbar_arrive(&sm.bar_full[s]); continue; }     // ablation: no global traffic
@@ -472,6 +509,8 @@ __device__ __forceinline__ void cb_producer(Smem& sm, const CUtensorMap* m_stat,
 
 template <int KATOMS, int NKS, class Smem>
 __device__ __forceinline__ void cb_score_loop(Smem& sm, uint32_t tmem, CbPlan pl, int ntiles, int my_items, int sidx, long long* tl) {
+  const int nstep = cb_issuers(Smem::ST);          // tiles sidx, sidx + nstep, ...
+  if (sidx >= nstep) return;
   constexpr uint32_t idesc_s = tc::idesc_bf16_f32(CB_BM, CB_BN);
   constexpr uint32_t STRM_ATOM = (CB_BN * 128) >> 4, STAGE = KATOMS * STRM_ATOM;
   const uint32_t strm_lo = tc::desc_lo_k(smem_u32(sm.strm[0][0]));
@@ -481,7 +520,7 @@ __device__ __forceinline__ void cb_score_loop(Smem& sm, uint32_t tmem, CbPlan pl
   int it = 0, j = sidx, a_it = -1;
   bool had_tile = false;                           // (ntiles == 1: an issuer sees only every other item and still owes bar_s_done)
   uint32_t a_tmem = tmem;
-  for (int t = sidx; t < total; t += 2) {
+  for (int t = sidx; t < total; t += nstep) {
     while (j >= ntiles) {
       j -= ntiles;
       if (!had_tile && lane_id() == 0) tc::mbar_arrive(&sm.bar_s_done);
@@ -496,6 +535,7 @@ __device__ __forceinline__ void cb_score_loop(Smem& sm, uint32_t tmem, CbPlan pl
     }
     const int st = rst.i, slot = rsl.i;
     TL_STAMP(tl, 0, t);
+    if (lane_id() == 0) tc::hb(2 + sidx, it * 1000 + j);
     tc::mbar_wait(&sm.bar_full[st], rst.ph);
     TL_STAMP(tl, 1, t);
     if (t >= NS) tc::mbar_wait(&sm.bar_slot_free[slot], rsl.ph ^ 1);
@@ -504,13 +544,13 @@ __device__ __forceinline__ void cb_score_loop(Smem& sm, uint32_t tmem, CbPlan pl
     if (tc::elect_one()) {
       tc::issue_ts_ksteps<NKS, 0, STRM_ATOM>(tmem + pl.col_slot0 + 64 * slot, 0u, a_tmem, strm_lo + st * STAGE, idesc_s);
       tc::mma_commit(&sm.bar_s_full[slot]);
-      if (j + 2 >= ntiles) tc::mma_commit(&sm.bar_s_done);   // this issuer's last tile of the item
+      if (j + nstep >= ntiles) tc::mma_commit(&sm.bar_s_done);   // this issuer's last tile of the item
     }
     __syncwarp();
+    if (lane_id() == 0) tc::hb(2 + sidx, 500000 + it * 1000 + j);
     TL_STAMP(tl, 3, t);
-    j += 2;
-    rst.next(Smem::ST); rst.next(Smem::ST);
-    rsl.next(NS); rsl.next(NS);
+    j += nstep;
+    for (int i = 0; i < nstep; ++i) { rst.next(Smem::ST); rsl.next(NS); }
   }
 }
 // score-MMA issuer shared by both backward kernels: S'(t) -> slot t % NS as soon as the K/Q tile has landed and the
@@ -547,6 +587,7 @@ __device__ __forceinline__ void cb_grad_issuer(Smem& sm, uint32_t tmem, CbPlan p
       const int st = rst.i, slot = rsl.i;
       const uint32_t tslot = tmem + pl.col_slot0 + 64 * slot;
       TL_STAMP(tl, 4, it * ntiles + jj);
+      if (lane_id() == 0) tc::hb(4, it * 1000 + jj);
       tc::mbar_wait(&sm.bar_p_ready[slot], rsl.ph);
       if (jj == 0 && it > 0) tc::mbar_wait(&sm.bar_acc_free, (it - 1) & 1);   // previous item's accumulator has been drained
       tc::tc_fence_after();
@@ -561,6 +602,7 @@ __device__ __forceinline__ void cb_grad_issuer(Smem& sm, uint32_t tmem, CbPlan p
         if (jj == ntiles - 1) tc::mma_commit(&sm.bar_final);
       }
       __syncwarp();
+      if (lane_id() == 0) tc::hb(4, 500000 + it * 1000 + jj);
       TL_STAMP(tl, 6, it * ntiles + jj);
     }
   }
@@ -642,7 +684,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dq_cc_kernel(
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = (L + CB_BN - 1) / CB_BN;
   const int my_items = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const CbPlan pl = cb_plan(KATOMS, NQ);
+  const CbPlan pl = cb_plan(KATOMS, NQ, ST);
   // clock timeline of one CTA (tools/attn_timeline.py): lane 0 of the issuing warps and of each warpgroup's first warp
   long long* const tl = (tl_buf != nullptr && blockIdx.x == TL_CTA && lane == 0) ? tl_buf : nullptr;
 
@@ -670,7 +712,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dq_cc_kernel(
     uint32_t rs[2][32], pd[32];
     Ring rst, rsl;
     int tcur = 0;                                     // global tile index the rings stand at
-    const bool bulk_out = (KD & 3) == 0;
+    const bool bulk_out = (KD & 3) == 0 && !(dbg & 32);
     for (int it = 0; it < my_items; ++it) {
       const int item = blockIdx.x + it * gridDim.x, bn = item / nqt, qt = item - bn * nqt, q0 = qt * CB_BM;
       const int qi = q0 + rowi;
@@ -685,7 +727,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dq_cc_kernel(
         if (qi < L) ndelta = -rsd[CB_BM * DVH + rowi];
       }
       tc::mbar_arrive(&sm.bar_stat_free);
-      for (int j = (wg + CB_NWG - qt % CB_NWG) % CB_NWG; j < ntiles; j += CB_NWG) {   // tile -> warpgroup (j + qt) % 3
+      for (int j = (wg + CB_NWG - (it * ntiles) % CB_NWG) % CB_NWG; j < ntiles; j += CB_NWG) {   // global tile t -> warpgroup t % 3
         {
           const int t = it * ntiles + j, dlt = t - tcur;             // 3 inside an item, 1..5 across an item boundary
           if (dlt == CB_NWG && ST >= CB_NWG && NS >= CB_NWG) { rst.advance(CB_NWG, ST); rsl.advance(CB_NWG, NS); }
@@ -698,6 +740,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dq_cc_kernel(
         const bool tail = nvalid < CB_BN;
         long long* const tw = (warp & 3) == 0 ? tl : nullptr;
         TL_STAMP(tw, 7, it * ntiles + j);
+        if (lane == 0) tc::hb(8 + warp, it * 1000 + j);
         tc::mbar_wait(&sm.bar_s_full[slot], rsl.ph);
         tc::tc_fence_after();
         TL_STAMP(tw, 8, it * ntiles + j);
@@ -720,19 +763,24 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dq_cc_kernel(
         tc::tc_fence_before();
         tc::mbar_arrive(&sm.bar_p_ready[slot]);
         tc::mbar_arrive(&sm.bar_empty[st]);            // value tile consumed
+        if (lane == 0) tc::hb(8 + warp, 500000 + it * 1000 + j);
         TL_STAMP(tw, 11, it * ntiles + j);
       }
       // ---- drain dQa (warpgroup 0 alone; the others go straight on with the next item's tiles, so the score slots are full
       //      again when the accumulator is released): TMEM -> shared staging tile -> one bulk store of nrows x KD floats ----
       if (wg == 0) {
         TL_STAMP(tl, 12, it * 4 + 0);
+        if (lane == 0) tc::hb(24 + warp, 1000 + it);
         if (it + 1 < my_items) {                       // single stationary buffer: refill once the item's score MMAs are done
           tc::mbar_wait(&sm.bar_s_done, it & 1);
           tc::tc_fence_after();
+          if (lane == 0) tc::hb(24 + warp, 2000 + it);
           stage_stat(it + 1);
         }
+        if (lane == 0) tc::hb(24 + warp, 3000 + it);
         tc::mbar_wait(&sm.bar_final, it & 1);
         tc::tc_fence_after();
+        if (lane == 0) tc::hb(24 + warp, 4000 + it);
         TL_STAMP(tl, 12, it * 4 + 1);
         if (bulk_out) {
           if (threadIdx.x == 0) bulk_wait_read();      // the previous item's store has finished reading the staging tile
@@ -757,6 +805,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dq_cc_kernel(
           tc::fence_proxy_async();
           asm volatile("bar.sync 1, 128;" ::: "memory");
           if (threadIdx.x == 0) bulk_s2g(dqa + ((size_t)bn * L + q0) * KD, sm.out, (uint32_t)(min(CB_BM, L - q0) * KD * 4));
+          if (lane == 0) tc::hb(24 + warp, 5000 + it);
           TL_STAMP(tl, 12, it * 4 + 3);
         } else {
           for (int c0 = 0; c0 < NQ; c0 += 32) {
@@ -794,8 +843,8 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = (L + CB_BN - 1) / CB_BN;
   const int my_items = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const CbPlan pl = cb_plan(KATOMS, 32);
-  __shared__ float dv_xch[2][CB_NWG - 1][CB_BM][DVH];   // dV partials of warpgroups 1.. (registers -> WG0), by item parity
+  const CbPlan pl = cb_plan(KATOMS, 32, ST);
+  __shared__ float dv_xch[2][CB_NWG][CB_BM][DVH];       // dV partial of every tile class (j % 3), by item parity
 
   cb_init<KATOMS>(sm, warp, lane, &tm_k_stat, &tm_q_strm, nqt, v, DVH, nullptr, 0, L);
   const uint32_t tmem = sm.tmem_base;
@@ -831,8 +880,10 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
 #pragma unroll
       for (int e = 0; e < DVH; ++e) { vk[e] = kj < L ? sm.rowside[it & 1][rowi * DVH + e] : 0.f; dvacc[e] = 0.f; }
       tc::mbar_arrive(&sm.bar_stat_free);
-      // tile -> warpgroup (j + qt) % 3: fixed per item, so the dV partial sums do not depend on where the item runs
-      for (int j = (wg + CB_NWG - qt % CB_NWG) % CB_NWG; j < ntiles; j += CB_NWG) {
+      // global tile t -> warpgroup t % 3 (see the forward kernel); the dV partials are kept per tile class j % 3 = cls and
+      // summed in class order, so they do not depend on where the item runs
+      const int cls = (wg + CB_NWG - (it * ntiles) % CB_NWG) % CB_NWG;
+      for (int j = cls; j < ntiles; j += CB_NWG) {
         {
           const int t = it * ntiles + j, dlt = t - tcur;             // 3 inside an item, 1..5 across an item boundary
           if (dlt == CB_NWG && ST >= CB_NWG && NS >= CB_NWG) { rst.advance(CB_NWG, ST); rsl.advance(CB_NWG, NS); }
@@ -857,13 +908,11 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
         tc::mbar_arrive(&sm.bar_p_ready[slot]);
         tc::mbar_arrive(&sm.bar_empty[st]);
       }
-      // warpgroups 1, 2 hand their dV partials over and go on with the next item; warpgroup 0 finishes the item
-      if (wg > 0) {
+      // every warpgroup hands its dV partial over; 1 and 2 go on with the next item, warpgroup 0 finishes this one
 #pragma unroll
-        for (int e = 0; e < DVH; ++e) dv_xch[it & 1][wg - 1][rowi][e] = dvacc[e];
-        tc::mbar_arrive(&sm.bar_dv);
-        continue;
-      }
+      for (int e = 0; e < DVH; ++e) dv_xch[it & 1][cls][rowi][e] = dvacc[e];
+      tc::mbar_arrive(&sm.bar_dv);
+      if (wg > 0) continue;
       if (it + 1 < my_items) {                         // single stationary buffer: refill once the item's score MMAs are done
         tc::mbar_wait(&sm.bar_s_done, it & 1);
         tc::tc_fence_after();
@@ -901,10 +950,10 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
             if (e < dkh) dk[row * dkh + e] = __uint_as_float(rs[0][e]) * LN2;
         }
 #pragma unroll
-        for (int e = 0; e < DVH; ++e) {                  // dV: own partial + the other warpgroups' (fixed order)
-          float t = dvacc[e];
+        for (int e = 0; e < DVH; ++e) {                  // dV: the three class partials in class order
+          float t = 0.f;
 #pragma unroll
-          for (int g = 0; g < CB_NWG - 1; ++g) t += dv_xch[it & 1][g][rowi][e];
+          for (int g = 0; g < CB_NWG; ++g) t += dv_xch[it & 1][g][rowi][e];
           if (prow) prow[2 * nh * dkh + n * DVH + e] = __float2bfloat16(t);
           else dv[row * DVH + e] = t;
         }

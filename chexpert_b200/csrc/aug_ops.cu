@@ -260,6 +260,91 @@ __global__ void aug_patch_bwd_kernel(const float* __restrict__ lse, const float*
   dst[C1 + dvh + 1] = lo;
   delta_out[row] = delta;
 }
+
+// ------------------------------------------------------------------------------------------------
+// out_proj adjoint + backward patch of Qa in ONE pass over the pixels (small value widths: dv = NH * DVH <= 16)
+//   dO[b,n,l,e] = sum_c Wout[c, n*dvh+e] dy[b, Cc+c, l]        (attn_aug_conv.py:92 adjoint, data)
+//   dWout[c,j] += dy[b, Cc+c, l] * o[b, n(j), l, e(j)]          (weight; per-block partials, summed in block order by
+//                                                                out_w_reduce_kernel: deterministic)
+//   delta[b,n,l] = dO . o;  Qa columns -lse (hi/lo), dO, -delta (hi/lo) as in aug_patch_bwd_kernel
+// Replaces four launches (out_bwd_data, out_bwd_weight, splitk_reduce, aug_patch_bwd: 56 us at Transition 1) whose
+// work is 25600 pixels x 8 channels.
+// ------------------------------------------------------------------------------------------------
+template <int NH, int DVH>
+__global__ void __launch_bounds__(256) out_bwd_patch_kernel(const float* __restrict__ dy, const float* __restrict__ o,
+                                                            const float* __restrict__ lse, const float* __restrict__ wout,
+                                                            float* __restrict__ d_o, float* __restrict__ delta_out,
+                                                            bf16* __restrict__ qa, float* __restrict__ wpartial, int B, int L,
+                                                            int Ctot, int coff, int KD, int C1, int KP) {
+  constexpr int DV = NH * DVH;
+  __shared__ float ws[DV * DV];
+  __shared__ float red[8][DV * DV];
+  for (int i = threadIdx.x; i < DV * DV; i += blockDim.x) ws[i] = wout[i];
+  __syncthreads();
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = m < B * L;
+  const int b = live ? m / L : 0, l = live ? m - b * L : 0;
+  float dyv[DV], oc[DV];
+#pragma unroll
+  for (int c = 0; c < DV; ++c) dyv[c] = live ? dy[((size_t)b * Ctot + coff + c) * L + l] : 0.f;
+#pragma unroll
+  for (int h = 0; h < NH; ++h)
+#pragma unroll
+    for (int e = 0; e < DVH; ++e) oc[h * DVH + e] = live ? o[((size_t)(b * NH + h) * L + l) * DVH + e] : 0.f;
+  if (live) {
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      const size_t row = (size_t)(b * NH + h) * L + l;
+      bf16* dst = qa + row * KP;
+      bf16 hi, lo;
+      split_bf16(-lse[row] * LOG2E, hi, lo);
+      dst[KD] = hi;
+      dst[KD + 1] = lo;
+      float delta = 0.f;
+#pragma unroll
+      for (int e = 0; e < DVH; ++e) {
+        const int j = h * DVH + e;
+        float g = 0.f;
+#pragma unroll
+        for (int c = 0; c < DV; ++c) g = fmaf(ws[c * DV + j], dyv[c], g);
+        d_o[row * DVH + e] = g;
+        delta = fmaf(g, oc[j], delta);
+        dst[C1 + e] = __float2bfloat16(g);
+      }
+      split_bf16(-delta, hi, lo);
+      dst[C1 + DVH] = hi;
+      dst[C1 + DVH + 1] = lo;
+      delta_out[row] = delta;
+    }
+  }
+  if (wpartial) {                                   // block partial of dWout: warp shuffles, then the 8 warps in fixed order
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < DV; ++c)
+#pragma unroll
+      for (int j = 0; j < DV; ++j) {
+        float v = dyv[c] * oc[j];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        if (lane == 0) red[warp][c * DV + j] = v;
+      }
+    __syncthreads();
+    for (int i = threadIdx.x; i < DV * DV; i += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][i];
+      wpartial[(size_t)blockIdx.x * DV * DV + i] = t;
+    }
+  }
+}
+
+__global__ void out_w_reduce_kernel(const float* __restrict__ wpartial, int nblocks, int n, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float t = 0.f;
+  for (int k = 0; k < nblocks; ++k) t += wpartial[(size_t)k * n + i];
+  dw[i] = t;
+}
 }  // namespace
 
 size_t aug_build_smem(const Dims& d) {
@@ -300,6 +385,30 @@ int aug_patch_bwd(const Dims& d, const float* lse, const float* d_o, const float
   const unsigned grid = (unsigned)((rows + 255) / 256);
   aug_patch_bwd_kernel<<<grid, 256, 0, st>>>(lse, d_o, o, static_cast<bf16*>(qa), delta, rows, d.dvh, a.KD, a.C1, a.KP);
   AACONV_LAUNCH_OK("aug_patch_bwd");
+  return 0;
+}
+
+
+int out_bwd_patch_supported(const Dims& d) { return (d.nh == 8 && (d.dvh == 1 || d.dvh == 2)) ? 0 : AACONV_E_UNSUPPORTED; }
+size_t out_bwd_patch_partial_floats(const Dims& d) { return (size_t)cdiv(d.B * d.L, 256) * d.dv * d.dv; }
+
+int out_bwd_patch(const Dims& d, const float* dy, const float* o, const float* lse, const float* wout, float* d_o, float* delta,
+                  void* qa, float* dw, float* partial, cudaStream_t st) {
+  if (out_bwd_patch_supported(d)) return fail(AACONV_E_UNSUPPORTED, "out_bwd_patch: nh = 8, dv/nh <= 2 only");
+  const AugLayout a = aug_layout(d);
+  const int grid = cdiv(d.B * d.L, 256);
+  float* wp = dw ? partial : nullptr;
+  if (d.dvh == 1)
+    out_bwd_patch_kernel<8, 1><<<grid, 256, 0, st>>>(dy, o, lse, wout, d_o, delta, static_cast<bf16*>(qa), wp, d.B, d.L, d.Cout, d.Cc,
+                                                     a.KD, a.C1, a.KP);
+  else
+    out_bwd_patch_kernel<8, 2><<<grid, 256, 0, st>>>(dy, o, lse, wout, d_o, delta, static_cast<bf16*>(qa), wp, d.B, d.L, d.Cout, d.Cc,
+                                                     a.KD, a.C1, a.KP);
+  AACONV_LAUNCH_OK("out_bwd_patch");
+  if (dw) {
+    out_w_reduce_kernel<<<cdiv(d.dv * d.dv, 64), 64, 0, st>>>(partial, grid, d.dv * d.dv, dw);
+    AACONV_LAUNCH_OK("out_w_reduce");
+  }
   return 0;
 }
 

@@ -22,7 +22,8 @@ struct Scratch {
     dq = c.take<float>(rows * d.dkh);
     dk = c.take<float>(rows * d.dkh);
     dv = c.take<float>(rows * d.dvh);
-    partial = c.take<float>(std::max(f32_partial_floats(d), tc_gemm_supported(d) == 0 ? tc_wgrad_partial_floats(d) : 0));
+    partial = c.take<float>(std::max(std::max(f32_partial_floats(d), tc_gemm_supported(d) == 0 ? tc_wgrad_partial_floats(d) : 0),
+                                     out_bwd_patch_partial_floats(d)));
     relpart = c.take<float>(rel_bwd_partial_floats(d));
     dqa = c.take<float>(rows * a.KD);
     gemm_ok = tc_gemm_supported(d) == 0;
@@ -105,11 +106,15 @@ int bf16_backward(const Dims& d, const float* x, const aaconv_params* p, const f
   const float* v = at<float>(saved, f32_saved_offset(d, "v"));
   const float* o = at<float>(saved, f32_saved_offset(d, "o"));
   const float* lse = at<float>(saved, f32_saved_offset(d, "lse"));
-  AACONV_TRY(f32_out_bwd(d, dy, o, p->out_w, w.d_o, g->out_w, w.partial, st));
   SavedAug sa(d, saved);
   // the backward-only columns of Qa (-lse, dO, -delta) are filled in place; idempotent, so a retained graph may
   // run backward again
-  AACONV_TRY(aug_patch_bwd(d, lse, w.d_o, o, sa.qa, w.delta, st));
+  if (out_bwd_patch_supported(d) == 0) {     // out_proj adjoint and the patch in one pass over the pixels
+    AACONV_TRY(out_bwd_patch(d, dy, o, lse, p->out_w, w.d_o, w.delta, sa.qa, g->out_w, w.partial, st));
+  } else {
+    AACONV_TRY(f32_out_bwd(d, dy, o, p->out_w, w.d_o, g->out_w, w.partial, st));
+    AACONV_TRY(aug_patch_bwd(d, lse, w.d_o, o, sa.qa, w.delta, st));
+  }
   // fast path: the attention-backward kernels write dq*scale, dk, dv as bf16 straight into the packed (B*L, KPq)
   // operand of the projection dgrad/wgrad GEMMs; its padding columns must be finite (they meet zero weights)
   const bool direct = w.gemm_ok && rel_bwd_supported(d) == 0 && tc_wgrad_supported(d) == 0;

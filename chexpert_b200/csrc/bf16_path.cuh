@@ -19,6 +19,11 @@ int aug_supported(const Dims& d);
 int aug_build_fwd(const Dims& d, const float* q, const float* k, const float* v, const float* krw, const float* krh,
                   void* qa, void* ka, cudaStream_t st);
 int aug_patch_bwd(const Dims& d, const float* lse, const float* d_o, const float* o, void* qa, float* delta, cudaStream_t st);
+// out_proj adjoint (dO, dWout) + the patch above in one pass (nh = 8, dv/nh <= 2); partial: out_bwd_patch_partial_floats
+int out_bwd_patch_supported(const Dims& d);
+size_t out_bwd_patch_partial_floats(const Dims& d);
+int out_bwd_patch(const Dims& d, const float* dy, const float* o, const float* lse, const float* wout, float* d_o, float* delta,
+                  void* qa, float* dw, float* partial, cudaStream_t st);
 int rel_bwd_supported(const Dims& d);
 size_t rel_bwd_partial_floats(const Dims& d);
 int rel_bwd(const Dims& d, const float* dqa, const float* q, const float* krw, const float* krh, float* dq, void* dqkvh,

@@ -48,7 +48,7 @@ struct __align__(1024) PGSmem {
 
 // Several independent jobs (accumulator-chunk groups, residue classes) share one launch: blockIdx.y selects the job, so
 // their CTAs fill one another's tail waves (long jobs first: blocks are dispatched in index order).
-constexpr int PG_MAX_JOBS = 4;
+constexpr int PG_MAX_JOBS = 8;
 struct PGJobs { PGParams job[PG_MAX_JOBS]; };
 
 __global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_tc_kernel(const __grid_constant__ PGJobs jobs) {
@@ -514,19 +514,24 @@ int tc_fprop(const Dims& d, const TcGemmBufs& t, const float* x, const float* co
   // then groups of projection chunks (short K) whose CTAs fill the tail of the long ones -- all in one launch.
   PGQueue qu;
   const int nc_conv = cdiv(d.Cc, 128), nc_qkv = cdiv(d.Nqkv, 128);
-  if (nc_conv + nc_qkv <= PG_MAX_CHUNKS) {
+  const int ncta = d.B * p.tiles_h;
+  // accumulator chunks per CTA: as many as TMEM holds (the A tiles are then read once), but never so many that the launch
+  // has fewer CTAs than SMs -- at Transition 3 (1600 pixels = 16 tiles) four chunks per CTA left 132 of 148 SMs idle
+  int per = PG_MAX_CHUNKS;
+  while (per > 1 && ncta * (cdiv(nc_conv, per) + cdiv(nc_qkv, per)) < 148) --per;
+  if (nc_conv + nc_qkv <= per) {
     p.nchunks = 0;
     for (int c = 0; c < nc_qkv; ++c) p.chunks[p.nchunks++] = PGChunk{c * 128, seg_qkv, seg_qkv + 1, 1};
     for (int c = 0; c < nc_conv; ++c) p.chunks[p.nchunks++] = PGChunk{c * 128, 0, T, 0};
     qu.add(p, d.B);
   } else {
-    for (int g0 = 0; g0 < d.Cc; g0 += 128 * PG_MAX_CHUNKS) {
-      p.nchunks = std::min(PG_MAX_CHUNKS, cdiv(d.Cc - g0, 128));
+    for (int g0 = 0; g0 < d.Cc; g0 += 128 * per) {
+      p.nchunks = std::min(per, cdiv(d.Cc - g0, 128));
       for (int c = 0; c < p.nchunks; ++c) p.chunks[c] = PGChunk{g0 + c * 128, 0, T, 0};
       qu.add(p, d.B);
     }
-    for (int g0 = 0; g0 < d.Nqkv; g0 += 128 * PG_MAX_CHUNKS) {
-      p.nchunks = std::min(PG_MAX_CHUNKS, cdiv(d.Nqkv - g0, 128));
+    for (int g0 = 0; g0 < d.Nqkv; g0 += 128 * per) {
+      p.nchunks = std::min(per, cdiv(d.Nqkv - g0, 128));
       for (int c = 0; c < p.nchunks; ++c) p.chunks[c] = PGChunk{g0 + c * 128, seg_qkv, seg_qkv + 1, 1};
       qu.add(p, d.B);
     }

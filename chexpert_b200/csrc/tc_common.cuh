@@ -47,19 +47,41 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (-> launch error at the next sync) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (-> launch error at the next sync) instead of hanging the GPU.  In "soft" mode
+// (aaconv_debug_set_mode bit 16; debugging only) a timed-out wait is logged to a device buffer and treated as satisfied, so
+// the kernel ends and the host can read WHICH barriers were stuck (aaconv_debug_read_mbar_log).
 #ifndef AACONV_MBAR_SPIN_LIMIT
 #define AACONV_MBAR_SPIN_LIMIT (1u << 26)
 #endif
+static __device__ unsigned long long* g_mbar_log = nullptr;   // mapped pinned host memory: [0] = count, [1..64] = records
+static __device__ unsigned g_mbar_soft = 0;                   // (survives a later fault of the kernel)
 static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  if (g_mbar_soft && g_mbar_log) {
+    const unsigned long long k = atomicAdd(g_mbar_log, 1ull);
+    if (k < 64) g_mbar_log[1 + k] = ((unsigned long long)bar << 32) | ((unsigned long long)parity << 31) | ((unsigned long long)blockIdx.x << 12) | threadIdx.x;
+    __threadfence_system();
+    return;
+  }
   printf("aaconv: mbarrier timeout block (%d,%d) thread %d bar 0x%x parity %u\n", blockIdx.x, blockIdx.y, threadIdx.x,
          bar, parity);
   __trap();
 }
+// debugging heartbeat (soft mode only): last position of a role of CTA 0, readable after a fault
+// (compiled in with -DAACONV_DEBUG_HB only: the flag test is a global load per call)
+__device__ __forceinline__ void hb(int slot, unsigned long long v) {
+#ifdef AACONV_DEBUG_HB
+  if (g_mbar_soft && g_mbar_log && blockIdx.x == 0) reinterpret_cast<volatile unsigned long long*>(g_mbar_log)[1 + slot] = v;
+#else
+  (void)slot; (void)v;
+#endif
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > AACONV_MBAR_SPIN_LIMIT) mbar_timeout(smem_u32(bar), parity);
+    if ((++spins & 0xFFFFFu) == 0 && (spins >= AACONV_MBAR_SPIN_LIMIT || g_mbar_soft)) {   // flag read once per 2^20 polls
+      mbar_timeout(smem_u32(bar), parity);
+      break;
+    }
   }
 }
 // Same, for waiters that are not on the critical path (math warpgroups, TMA producer): back off between polls so that
@@ -68,7 +90,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     __nanosleep(40);
-    if (++spins > (AACONV_MBAR_SPIN_LIMIT >> 4)) mbar_timeout(smem_u32(bar), parity);
+    if (++spins > (AACONV_MBAR_SPIN_LIMIT >> 4)) { mbar_timeout(smem_u32(bar), parity); break; }
   }
 }
 

@@ -128,6 +128,10 @@ long long aaconv_launch_count(void);
  *                              8 no math -- results are WRONG when non-zero; timing experiments only                */
 void aaconv_debug_set_timeline(void* device_buffer);
 void aaconv_debug_set_mode(int mode);
+/*   aaconv_debug_read_mbar_log  with mode bit 16 set, a timed-out mbarrier wait in the small-value-width attention kernels is
+ *                              logged instead of trapping; returns how many were logged, out[i] = smem barrier address << 32 |
+ *                              parity << 31 | block << 12 | thread                                                    */
+int aaconv_debug_read_mbar_log(unsigned long long* out, int max_entries);
 int aaconv_profile_begin(void* stream);
 int aaconv_profile_end(char* names_buf, size_t names_len, float* ms, int max_entries);
 
