@@ -42,7 +42,6 @@ extern "C" void aaconv_debug_set_mode(int m) {
 }
 // -> number of timed-out waits logged since the mode was set (readable even after the kernel faulted: the log lives in mapped
 // host memory); out[i] = smem barrier address << 32 | parity << 31 | block << 12 | thread
-extern "C" void* aaconv_debug_host_log(void) { return g_mbar_host_log; }
 extern "C" int aaconv_debug_read_mbar_log(unsigned long long* out, int max_entries) {
   if (!g_mbar_host_log) return 0;
   const int n = (int)g_mbar_host_log[0];

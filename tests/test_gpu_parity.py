@@ -223,6 +223,30 @@ def test_full_size_T1_properties_bf16():
     assert rel_err(m.key_rel_w.grad, 2.0 * gw) < 2e-2
 
 
+@pytest.mark.parametrize('B,H', [(3, 48), (9, 24), (2, 64)])
+def test_persistent_attention_kernels_many_items_per_cta(B, H):
+    """The small-value-width attention kernels are persistent: one CTA walks several (batch, head, tile) items and keeps
+    its barrier rings running across them.  Shapes with > 148 items and 1 / 2 / 3 operand atoms (H = 24 / 48 / 64),
+    bf16 against the fp32 kernels (themselves gated against the oracle above): an item-boundary protocol error shows up
+    as a launch failure or as garbage in the later items."""
+    shape = O.AAConvShape(64, 64, 3, 2, 160, 8, 8, True, (H, H))
+    p = O.init_params(shape, seed=3)
+    g0 = torch.Generator().manual_seed(9)
+    x = torch.relu(torch.randn(B, 64, 2 * H, 2 * H, generator=g0)).cuda()
+    dy = torch.randn(B, 64, H, H, generator=g0).cuda()
+    res = {}
+    for precision in ('fp32', 'bf16'):
+        m = _module(shape, p, precision)
+        xc = x.clone().requires_grad_(True)
+        y = m(xc)
+        y.backward(dy)
+        torch.cuda.synchronize()
+        res[precision] = [y.detach(), xc.grad] + [q.grad for q in m.parameters()]
+    for a, b in zip(res['bf16'], res['fp32']):
+        assert torch.isfinite(a).all()
+        assert rel_l2(a, b) < 3e-2, rel_l2(a, b)
+
+
 def test_tiny_densenet_matches_reference_fixture():
     """Whole-model anchor: the reference DenseNet(16,(2,2,2,2),32, k=v=0.5) forward/backward on one batch
     (fixture written by oracle/gen_golden.py), fp32 kernels, strict state_dict load."""
