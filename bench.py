@@ -147,7 +147,7 @@ def run_model(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     W, K, B = max(args.warmup, 3), args.steps, args.batch
-    ts = TrainStep(dev, size=args.size, precision=args.precision)
+    ts = TrainStep(dev, size=args.size, precision=args.precision, cuda_graph=args.cuda_graph)
     xh, th = synthetic_batch(B, size=args.size, seed=1000 + rank)
     xh, th = xh.pin_memory(), th.pin_memory()
     x, t = xh.to(dev), th.to(dev)
@@ -180,6 +180,8 @@ def run_model(args):
     l0 = _lib.launch_count()
     ms = timed(lambda: ts(x, t), K)
     launches = _lib.launch_count() - l0
+    if args.cuda_graph:          # replays do not pass through the host-side launch counter: count what one replay holds
+        launches = ts.graph_launches * K
     barrier()
     for _ in range(2):
         e2e_step()
@@ -198,6 +200,7 @@ def run_model(args):
                 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
                 'config': {'workload': 'aadensenet121 training step (configs[2])', 'batch_per_gpu': B, 'image': args.size,
                            'precision': args.precision, 'optimizer': 'SGD nesterov momentum 0.9', 'parallelism': f'dp{world}',
+                           'cuda_graph': bool(args.cuda_graph),
                            'l2': 'activations of one step (>> 126 MB) stream through L2; no explicit flush',
                            'dense_blocks': 'torchvision _DenseBlock under torch.autocast(bf16), as the reference wires them'},
                 'e2e': {'value': B * world / (ms_e2e * 1e-3), 'unit': 'images/s', 'ms_per_step': ms_e2e,
@@ -224,6 +227,7 @@ def main():
                     help="layer: AAConv2d fwd+bwd microbench (configs[1], the headline); model: aadensenet121 training step "
                          "(configs[2]: batch 16/GPU, 320x320, SGD-nesterov, gradient all-reduce), images/s")
     ap.add_argument('--size', type=int, default=320)
+    ap.add_argument('--cuda-graph', action='store_true', help='model workload: capture the whole training step in a CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

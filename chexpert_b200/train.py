@@ -10,6 +10,7 @@ path and not rebuilt; `TrainStep` is what bench.py times and what a user's own l
 import torch
 import torch.distributed as dist
 
+from . import _lib
 from .dataparallel import GradientBuckets
 from .densenet import aadensenet121
 from .loss import BCEWithLogitsLoss
@@ -37,7 +38,7 @@ class TrainStep:
     """Owns model, loss kernel, optimizer, scheduler and (when world > 1) the gradient buckets."""
 
     def __init__(self, device, size=320, precision='bf16', lr=1e-4, raw_labels=True, bucket_mb=25.0, seed=0,
-                 autocast=True, channels_last=False):
+                 autocast=True, channels_last=False, cuda_graph=False, graph_after=2):
         torch.manual_seed(seed)
         self.device = torch.device(device)
         self.model = aadensenet121(5, (size, size), precision=precision).to(self.device)
@@ -50,10 +51,19 @@ class TrainStep:
         self.buckets = GradientBuckets(self.model, bucket_mb=bucket_mb) if self.world > 1 else None
         # the dense blocks are torch/cuDNN (outside the hot path); bf16 autocast only decides THEIR arithmetic
         self.autocast = bool(autocast and precision == 'bf16' and self.device.type == 'cuda')
+        # cuda_graph: after `graph_after` eager steps (they create the momentum buffers and warm cuDNN up) the whole step --
+        # forward, loss, backward, bucket all-reduces, optimizer -- is captured once and replayed: the ~3000 small launches
+        # of the 120-layer dense blocks stop being bound by the Python / launch rate.  Re-captured when the lr changes.
+        self.cuda_graph = bool(cuda_graph and self.device.type == 'cuda' and self.world == 1)   # (NCCL work handles inside a
+        # capture hung at 2 GPUs: the multi-rank step stays eager)
+        self.graph_after = graph_after
+        self._calls = 0
+        self._graph = None
+        self._graph_lr = None
+        self.graph_launches = 0
         self.model.train()
 
-    def __call__(self, x, target):
-        """-> loss (0-dim device tensor; no host sync, unlike loss.item() at chexpert.py:167)."""
+    def _step(self, x, target):
         if self.buckets is not None:
             self.buckets.reset()
         else:
@@ -65,5 +75,31 @@ class TrainStep:
         if self.buckets is not None:
             self.buckets.finish()
         self.opt.step()
-        self.sched.step()
         return loss.detach()
+
+    def _capture(self, x, target):
+        self._sx, self._st = x.clone(), target.clone()
+        torch.cuda.synchronize(self.device)
+        self._graph = torch.cuda.CUDAGraph()
+        if self.buckets is None:
+            self.opt.zero_grad(set_to_none=True)
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self._graph):
+            self._sloss = self._step(self._sx, self._st)
+        self.graph_launches = _lib.launch_count() - n0      # kernels of libaaconv_b200 inside one replay
+        self._graph_lr = [g['lr'] for g in self.opt.param_groups]
+
+    def __call__(self, x, target):
+        """-> loss (0-dim device tensor; no host sync, unlike loss.item() at chexpert.py:167)."""
+        self._calls += 1
+        if not self.cuda_graph or self._calls <= self.graph_after:
+            loss = self._step(x, target)
+        else:
+            if self._graph is None or self._graph_lr != [g['lr'] for g in self.opt.param_groups]:
+                self._capture(x, target)
+            self._sx.copy_(x, non_blocking=True)
+            self._st.copy_(target, non_blocking=True)
+            self._graph.replay()
+            loss = self._sloss.clone()       # the static tensor is overwritten by the next replay
+        self.sched.step()
+        return loss

@@ -268,3 +268,22 @@ def test_tiny_densenet_matches_reference_fixture():
     for k, prm in m.named_parameters():
         if 'g.' + k in z.files:
             assert rel_err(prm.grad.cpu(), torch.from_numpy(z['g.' + k])) < 2e-3, k
+
+
+def test_train_step_cuda_graph_matches_eager():
+    """chexpert_b200.train.TrainStep(cuda_graph=True) replays the captured forward / loss / backward / SGD step: the loss
+    sequence must follow the eager one (same kernels, same order; cuDNN may pick another algorithm under capture)."""
+    from chexpert_b200.train import TrainStep, synthetic_batch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    x, t = synthetic_batch(4, size=64, seed=5, device='cuda')
+    losses = {}
+    for mode in (False, True):
+        ts = TrainStep('cuda', size=64, precision='fp32', lr=1e-3, cuda_graph=mode, seed=0)
+        losses[mode] = torch.stack([ts(x, t) for _ in range(6)]).cpu()
+        if mode:
+            assert ts._graph is not None and ts.graph_launches > 0
+    assert torch.isfinite(losses[True]).all()
+    # cuDNN's backward kernels are not run-to-run deterministic and training amplifies the difference step by step
+    assert torch.allclose(losses[True], losses[False], rtol=1e-2, atol=1e-3), (losses[True], losses[False])
+    assert float(losses[False][-1]) != float(losses[False][0])       # the steps really update the weights
