@@ -338,12 +338,30 @@ __global__ void __launch_bounds__(256) out_bwd_patch_kernel(const float* __restr
   }
 }
 
-__global__ void out_w_reduce_kernel(const float* __restrict__ wpartial, int nblocks, int n, float* __restrict__ dw) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// block = 32 outputs x 8 slices of the block partials; slices, then the 8 slice sums, are added in a fixed order
+__global__ void __launch_bounds__(256) out_w_reduce_kernel(const float* __restrict__ wpartial, int nblocks, int n,
+                                                           float* __restrict__ dw) {
+  __shared__ float red[8][33];
+  const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + o;
   float t = 0.f;
-  for (int k = 0; k < nblocks; ++k) t += wpartial[(size_t)k * n + i];
-  dw[i] = t;
+  if (i < n) {
+    int k = sl;
+    for (; k + 24 < nblocks; k += 32) {
+      const float a = wpartial[(size_t)k * n + i], b = wpartial[(size_t)(k + 8) * n + i], c = wpartial[(size_t)(k + 16) * n + i],
+                  d = wpartial[(size_t)(k + 24) * n + i];
+      t = (((t + a) + b) + c) + d;
+    }
+    for (; k < nblocks; k += 8) t += wpartial[(size_t)k * n + i];
+  }
+  red[sl][o] = t;
+  __syncthreads();
+  if (sl == 0 && i < n) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += red[k][o];
+    dw[i] = tot;
+  }
 }
 }  // namespace
 
@@ -406,7 +424,7 @@ int out_bwd_patch(const Dims& d, const float* dy, const float* o, const float* l
                                                      a.KD, a.C1, a.KP);
   AACONV_LAUNCH_OK("out_bwd_patch");
   if (dw) {
-    out_w_reduce_kernel<<<cdiv(d.dv * d.dv, 64), 64, 0, st>>>(partial, grid, d.dv * d.dv, dw);
+    out_w_reduce_kernel<<<cdiv(d.dv * d.dv, 32), 256, 0, st>>>(partial, grid, d.dv * d.dv, dw);
     AACONV_LAUNCH_OK("out_w_reduce");
   }
   return 0;
@@ -428,6 +446,7 @@ struct RelBwdP {
   int L, H, W, nh, dkh, KD, KPq, relative;
   int DK8, RW, RH, PBW, PBH, PTW, PTH, PA, RP;
   int tiles_per_bn, ntiles, tile_floats;
+  int pipelined;        // every tile can be fetched by bulk copies: tile i+1 is loaded while tile i is computed (two buffers)
   float qscale;
 };
 
@@ -446,12 +465,24 @@ __global__ void __launch_bounds__(256, (MT <= 5 ? 2 : 1)) rel_bwd_kernel(const R
   uint32_t* tabh = tabw + p.DK8 * p.PTW;                         // [DK8][PTH]
   // q and dQa tiles are contiguous copies of the global rows (one bulk copy each).  K/N padding of the q fragments
   // (columns dkh..8*NTE) reads the next row / the head of da: it only feeds output columns that are discarded.
-  float* qs = reinterpret_cast<float*>(tabh + p.DK8 * p.PTH);    // [TR][dkh]   q
-  float* da = qs + ((TR * p.dkh + 3) & ~3);                      // [TR][PA]    dQa rows of the tile (PA == KD)
+  const int QF = (TR * p.dkh + 3) & ~3, BUF = QF + p.tile_floats;   // one buffer = q tile + dQa tile
+  float* const buf0 = reinterpret_cast<float*>(tabh + p.DK8 * p.PTH);
+  float* qs = buf0;                                              // [TR][dkh]   q
+  float* da = qs + QF;                                           // [TR][PA]    dQa rows of the tile (PA == KD)
   const int PQ2 = p.dkh;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(da + p.tile_floats);
-  if (threadIdx.x == 0) { tc::mbar_init(bar, 1); tc::fence_barrier_init(); }
-  uint32_t phase = 0;
+  const int nbuf = p.pipelined ? 2 : 1;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(buf0 + nbuf * BUF);   // one barrier per buffer
+  if (threadIdx.x == 0) { tc::mbar_init(&bar[0], 1); tc::mbar_init(&bar[1], 1); tc::fence_barrier_init(); }
+  uint32_t phase = 0;                                            // bit b = phase of buffer b
+  auto fetch = [&](int tile, int b) {                            // thread 0: bulk copies of one tile into buffer b
+    const int bn = tile / p.tiles_per_bn, l0 = (tile - bn * p.tiles_per_bn) * TR;
+    const int nrows = min(TR, p.L - l0);
+    const size_t row0 = (size_t)bn * p.L + l0;
+    const uint32_t bq = nrows * p.dkh * 4, bd = nrows * p.KD * 4;
+    tc::mbar_arrive_expect_tx(&bar[b], bq + bd);
+    bulk_g2s(buf0 + b * BUF, p.q + row0 * p.dkh, bq, &bar[b]);
+    bulk_g2s(buf0 + b * BUF + QF, p.dqa + row0 * p.KD, bd, &bar[b]);
+  };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 
   for (int i = threadIdx.x; i < p.DK8 * p.PTW; i += blockDim.x) {
@@ -462,7 +493,7 @@ __global__ void __launch_bounds__(256, (MT <= 5 ? 2 : 1)) rel_bwd_kernel(const R
     const int e = i / p.PTH, r = i - e * p.PTH;
     tabh[i] = (e < p.dkh && r < p.RH) ? f2tf32(p.krh[e * p.RH + r]) : 0u;
   }
-  for (int i = threadIdx.x; i < ((TR * p.dkh + 3) & ~3) + TR * p.PA; i += blockDim.x) qs[i] = 0.f;
+  for (int i = threadIdx.x; i < nbuf * BUF; i += blockDim.x) buf0[i] = 0.f;
   float acc[MT][NTE][4];                                         // G role: dT^T[r][e] of this warp's axis / row half
 #pragma unroll
   for (int a = 0; a < MT; ++a)
@@ -471,24 +502,33 @@ __global__ void __launch_bounds__(256, (MT <= 5 ? 2 : 1)) rel_bwd_kernel(const R
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
 
-  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+  __syncthreads();                                     // zero-fill and barrier init before the first copy
+  if (p.pipelined && threadIdx.x == 0 && (int)blockIdx.x < p.ntiles) { tc::fence_proxy_async(); fetch(blockIdx.x, 0); }
+  int cur = 0;
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, cur ^= p.pipelined) {
     const int bn = tile / p.tiles_per_bn, l0 = (tile - bn * p.tiles_per_bn) * TR;
     const int nrows = min(TR, p.L - l0);
     const size_t row0 = (size_t)bn * p.L + l0;
-    __syncthreads();
+    qs = buf0 + cur * BUF;
+    da = qs + QF;
+    __syncthreads();                                   // everyone is done with the other buffer (tile - gridDim.x)
     if (nrows < TR) {                                  // last tile of an image: rows past the end must contribute zero
       for (int i = threadIdx.x + nrows * p.dkh; i < TR * p.dkh; i += blockDim.x) qs[i] = 0.f;
       for (int i = threadIdx.x + nrows * p.PA; i < TR * p.PA; i += blockDim.x) da[i] = 0.f;
     }
     const bool bulk = p.PA == p.KD && (((row0 * p.dkh) | (size_t)(nrows * p.dkh) | (row0 * p.KD) | (size_t)(nrows * p.KD)) & 3) == 0;
-    if (bulk) {
+    if (p.pipelined) {
+      if (threadIdx.x == 0 && tile + (int)gridDim.x < p.ntiles) { tc::fence_proxy_async(); fetch(tile + gridDim.x, cur ^ 1); }
+      tc::mbar_wait(&bar[cur], (phase >> cur) & 1);
+      phase ^= 1u << cur;
+    } else if (bulk) {
       if (threadIdx.x == 0) {
         const uint32_t bq = nrows * p.dkh * 4, bd = nrows * p.KD * 4;
-        tc::mbar_arrive_expect_tx(bar, bq + bd);
-        bulk_g2s(qs, p.q + row0 * p.dkh, bq, bar);
-        bulk_g2s(da, p.dqa + row0 * p.KD, bd, bar);
+        tc::mbar_arrive_expect_tx(&bar[0], bq + bd);
+        bulk_g2s(qs, p.q + row0 * p.dkh, bq, &bar[0]);
+        bulk_g2s(da, p.dqa + row0 * p.KD, bd, &bar[0]);
       }
-      tc::mbar_wait(bar, phase);
+      tc::mbar_wait(&bar[0], phase & 1);
       phase ^= 1;
     } else {
       for (int r = warp; r < nrows; r += 8) {
@@ -586,7 +626,7 @@ __global__ void __launch_bounds__(256, (MT <= 5 ? 2 : 1)) rel_bwd_kernel(const R
   }
   // ---- CTA partial of the key_rel gradients: sum the two row-half warps of each axis in a fixed order ----
   __syncthreads();
-  float* red = da;                                   // [4 warps][RP * DK8]  (fits: RP*DK8 <= 128*32 floats per warp ... checked on host)
+  float* red = buf0 + QF;                            // [4 warps][RP * DK8]: aliases buffer 0's dQa tile (sized for it on the host)
   if (warp >= 4) {
     float* mine = red + (warp - 4) * p.RP * p.DK8;
 #pragma unroll
@@ -622,8 +662,17 @@ __global__ void __launch_bounds__(256) rel_bwd_reduce_kernel(const float* __rest
   const int i = blockIdx.x * 32 + o;
   const int per_axis = RP * DK8;
   float s = 0.f;
-  if (i < 2 * per_axis)
-    for (int c = sl; c < nparts; c += 8) s += partial[(size_t)c * 2 * per_axis + i];
+  if (i < 2 * per_axis) {
+    const float* src = partial + i;
+    const size_t step = (size_t)2 * per_axis;
+    int c = sl;
+    for (; c + 24 < nparts; c += 32) {               // four loads in flight per add chain; order fixed
+      const float a = src[(size_t)c * step], b = src[(size_t)(c + 8) * step], d = src[(size_t)(c + 16) * step],
+                  e = src[(size_t)(c + 24) * step];
+      s = (((s + a) + b) + d) + e;
+    }
+    for (; c < nparts; c += 8) s += src[(size_t)c * step];
+  }
   red[sl][o] = s;
   __syncthreads();
   if (sl == 0 && i < 2 * per_axis) {
@@ -691,7 +740,16 @@ int rel_bwd(const Dims& d, const float* dqa, const float* q, const float* krw, c
   size_t tile_floats = (size_t)TR * p.PA;
   tile_floats = (std::max(tile_floats, (size_t)4 * p.RP * p.DK8) + 3) & ~size_t(3);       // the reduction buffer aliases the dQa tile
   p.tile_floats = (int)tile_floats;
-  const size_t smem = sizeof(uint32_t) * p.DK8 * (size_t)(p.PTW + p.PTH) + sizeof(float) * (((TR * d.dkh + 3) & ~3) + tile_floats) + 16;
+  // bulk copies need 16-byte aligned, 16-byte multiple row blocks for EVERY tile: then the next tile is prefetched
+  p.pipelined = (p.PA == p.KD && ((d.L * d.dkh) % 4) == 0 && ((d.L * a.KD) % 4) == 0 && ((TR * d.dkh) % 4) == 0 && ((TR * a.KD) % 4) == 0 &&
+                 ((std::min(TR, d.L - (p.tiles_per_bn - 1) * TR) * d.dkh) % 4) == 0 &&
+                 ((std::min(TR, d.L - (p.tiles_per_bn - 1) * TR) * a.KD) % 4) == 0) ? 1 : 0;
+  const size_t one_buf = sizeof(float) * (((TR * d.dkh + 3) & ~3) + tile_floats);
+  size_t smem = sizeof(uint32_t) * p.DK8 * (size_t)(p.PTW + p.PTH) + (p.pipelined ? 2 : 1) * one_buf + 32;
+  if (p.pipelined && smem > 100 * 1024) {              // keep two CTAs per SM
+    p.pipelined = 0;
+    smem -= one_buf;
+  }
   if (smem > 200 * 1024) return fail(AACONV_E_UNSUPPORTED, "rel_bwd: %zu B of shared memory needed", smem);
   const int grid = std::min(p.ntiles, REL_BWD_GRID);
   if (nte <= 3) AACONV_TRY(dispatch_rel_bwd<3>(mt, p, grid, smem, st));

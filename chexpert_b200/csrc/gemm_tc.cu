@@ -788,8 +788,18 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, WGShape s
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 128 * WG_N; i += gridDim.x * blockDim.x) {
     const int m = m0 + i / WG_N, nl = i % WG_N, n = n0 + nl;
     if (nl >= nn || n >= Cin || m >= (kind == 0 ? Cc : Nqkv)) continue;
+    // the partials are summed in split order (deterministic); loads are issued four at a time so that the chain is
+    // bound by the adds, not by one memory round trip per split
+    const float* src = partial + (size_t)task * 128 * WG_N + i;
+    const size_t step = (size_t)ntasks * 128 * WG_N;
     float s = 0.f;
-    for (int sp = 0; sp < splits; ++sp) s += partial[((size_t)(sp * ntasks + task) * 128) * WG_N + i];
+    int sp = 0;
+    for (; sp + 4 <= splits; sp += 4) {
+      const float a = src[(size_t)sp * step], b = src[(size_t)(sp + 1) * step], c = src[(size_t)(sp + 2) * step],
+                  d = src[(size_t)(sp + 3) * step];
+      s = (((s + a) + b) + c) + d;
+    }
+    for (; sp < splits; ++sp) s += src[(size_t)sp * step];
     if (kind == 0) dwc[((size_t)m * Cin + n) * shape.T + tap] = s;
     else dwq[(size_t)m * Cin + n] = s;
   }
@@ -848,7 +858,7 @@ int tc_wgrad(const Dims& d, const TcGemmBufs& t, float* dwc, float* dwq, float* 
   AACONV_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   wgrad_tc_kernel<<<dim3(nt, splits), WG_THREADS, smem, st>>>(p);
   AACONV_LAUNCH_OK("conv_qkv_wgrad_tc");
-  wgrad_reduce_kernel<<<dim3(16, nt), 256, 0, st>>>(partial, p.shape, splits, dwc, dwq, d.Cc, d.Cin, d.Nqkv);
+  wgrad_reduce_kernel<<<dim3(128, nt), 256, 0, st>>>(partial, p.shape, splits, dwc, dwq, d.Cc, d.Cin, d.Nqkv);
   AACONV_LAUNCH_OK("wgrad_reduce");
   return 0;
 }
