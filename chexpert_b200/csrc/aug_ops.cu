@@ -49,6 +49,10 @@ namespace {
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr int TR = 64;             // rows per tile (4 row groups of 16)
 
+// Round-to-nearest TF32 operand without the conversion unit: the MMA ignores the low 13 mantissa bits, so adding half an ulp
+// in the integer domain rounds (half away from zero).  cvt.rna.tf32.f32 runs on the XU pipe (16 lanes/clk/SM, shared with
+// MUFU); the ncu capture of rel_bwd showed that pipe 58 % busy with these conversions next to a 62 % busy HMMA pipe.
+__device__ __forceinline__ uint32_t f2tf32_alu(float x) { return __float_as_uint(x) + 0x1000u; }
 __device__ __forceinline__ uint32_t f2tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -193,10 +197,10 @@ __global__ void __launch_bounds__(256) aug_build_fwd_kernel(const BuildP p) {
 #pragma unroll
       for (int s = 0; s < 4; ++s)
         if (s < nks) {
-          af[s][0] = f2tf32(qs[ra * PQ + 8 * s + t] * LOG2E);
-          af[s][1] = f2tf32(qs[rb * PQ + 8 * s + t] * LOG2E);
-          af[s][2] = f2tf32(qs[ra * PQ + 8 * s + t + 4] * LOG2E);
-          af[s][3] = f2tf32(qs[rb * PQ + 8 * s + t + 4] * LOG2E);
+          af[s][0] = f2tf32_alu(qs[ra * PQ + 8 * s + t] * LOG2E);
+          af[s][1] = f2tf32_alu(qs[rb * PQ + 8 * s + t] * LOG2E);
+          af[s][2] = f2tf32_alu(qs[ra * PQ + 8 * s + t + 4] * LOG2E);
+          af[s][3] = f2tf32_alu(qs[rb * PQ + 8 * s + t + 4] * LOG2E);
         }
       const int NT = (R + 7) >> 3;
       for (int nt = 0; nt < NT; ++nt) {
@@ -557,10 +561,10 @@ __global__ void __launch_bounds__(256, (MT <= 5 ? 2 : 1)) rel_bwd_kernel(const R
         const int KS = (R + 7) >> 3;
         for (int ks = 0; ks < KS; ++ks) {
           const int r0 = 8 * ks + t, r1 = r0 + 4;
-          const uint32_t a0 = (unsigned)(r0 - lo_a) < (unsigned)N ? f2tf32(rowa[r0]) : 0u;
-          const uint32_t a1 = (unsigned)(r0 - lo_b) < (unsigned)N ? f2tf32(rowb[r0]) : 0u;
-          const uint32_t a2 = (unsigned)(r1 - lo_a) < (unsigned)N ? f2tf32(rowa[r1]) : 0u;
-          const uint32_t a3 = (unsigned)(r1 - lo_b) < (unsigned)N ? f2tf32(rowb[r1]) : 0u;
+          const uint32_t a0 = (unsigned)(r0 - lo_a) < (unsigned)N ? f2tf32_alu(rowa[r0]) : 0u;
+          const uint32_t a1 = (unsigned)(r0 - lo_b) < (unsigned)N ? f2tf32_alu(rowb[r0]) : 0u;
+          const uint32_t a2 = (unsigned)(r1 - lo_a) < (unsigned)N ? f2tf32_alu(rowa[r1]) : 0u;
+          const uint32_t a3 = (unsigned)(r1 - lo_b) < (unsigned)N ? f2tf32_alu(rowb[r1]) : 0u;
 #pragma unroll
           for (int nt = 0; nt < NTE; ++nt)
             mma_tf32(c[nt], a0, a1, a2, a3, tab[(8 * nt + g) * PT + r0], tab[(8 * nt + g) * PT + r1]);
@@ -606,17 +610,17 @@ __global__ void __launch_bounds__(256, (MT <= 5 ? 2 : 1)) rel_bwd_kernel(const R
         uint32_t b0[NTE], b1[NTE];
 #pragma unroll
         for (int nt = 0; nt < NTE; ++nt) {
-          b0[nt] = f2tf32(qs[k0 * PQ2 + 8 * nt + g]);
-          b1[nt] = f2tf32(qs[k1 * PQ2 + 8 * nt + g]);
+          b0[nt] = f2tf32_alu(qs[k0 * PQ2 + 8 * nt + g]);
+          b1[nt] = f2tf32_alu(qs[k1 * PQ2 + 8 * nt + g]);
         }
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           const int r_a = 16 * mt + g, r_b = r_a + 8;
           if (16 * mt < R) {
-            const uint32_t a0 = (unsigned)(r_a - lo0) < (unsigned)N ? f2tf32(row0p[r_a]) : 0u;
-            const uint32_t a1 = (unsigned)(r_b - lo0) < (unsigned)N ? f2tf32(row0p[r_b]) : 0u;
-            const uint32_t a2 = (unsigned)(r_a - lo1) < (unsigned)N ? f2tf32(row1p[r_a]) : 0u;
-            const uint32_t a3 = (unsigned)(r_b - lo1) < (unsigned)N ? f2tf32(row1p[r_b]) : 0u;
+            const uint32_t a0 = (unsigned)(r_a - lo0) < (unsigned)N ? f2tf32_alu(row0p[r_a]) : 0u;
+            const uint32_t a1 = (unsigned)(r_b - lo0) < (unsigned)N ? f2tf32_alu(row0p[r_b]) : 0u;
+            const uint32_t a2 = (unsigned)(r_a - lo1) < (unsigned)N ? f2tf32_alu(row1p[r_a]) : 0u;
+            const uint32_t a3 = (unsigned)(r_b - lo1) < (unsigned)N ? f2tf32_alu(row1p[r_b]) : 0u;
 #pragma unroll
             for (int nt = 0; nt < NTE; ++nt) mma_tf32(acc[mt][nt], a0, a1, a2, a3, b0[nt], b1[nt]);
           }
