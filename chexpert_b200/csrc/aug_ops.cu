@@ -218,24 +218,33 @@ __global__ void __launch_bounds__(256) aug_build_fwd_kernel(const BuildP p) {
       }
     }
     // ---- data columns: c*q into Qa, k and v into Ka (everything else in the tiles is constant or written above) ----
-    for (int i = threadIdx.x; i < TR * p.dkh; i += blockDim.x) {
-      const int r = i / p.dkh, e = i - r * p.dkh;
-      tq[r * PT + e] = __float2bfloat16(qs[i] * LOG2E);
-      tk[r * PT + e] = __float2bfloat16(ks[i]);
-    }
-    for (int i = threadIdx.x; i < TR * p.dvh; i += blockDim.x) {
-      const int r = i / p.dvh, e = i - r * p.dvh;
-      tk[r * PT + p.C1 + e] = __float2bfloat16(vs[i]);
+    // (row = warp-strided, column = lane: no integer division in the per-tile loops -- a runtime division is three XU-pipe
+    //  instructions, and the XU pipe was 98 % busy in the ncu capture of this kernel)
+    for (int r = warp; r < TR; r += 8) {
+      if (lane < p.dkh) {
+        tq[r * PT + lane] = __float2bfloat16(qs[r * p.dkh + lane] * LOG2E);
+        tk[r * PT + lane] = __float2bfloat16(ks[r * p.dkh + lane]);
+      }
+      if (lane < p.dvh) tk[r * PT + p.C1 + lane] = __float2bfloat16(vs[r * p.dvh + lane]);
     }
     __syncthreads();
     // ---- coalesced copy-out: rows of KP bf16 are contiguous in global memory ----
     const int vec_per_row = p.KP >> 3;                 // uint4 = 8 bf16
     uint4* gq = reinterpret_cast<uint4*>(p.qa + row0 * p.KP);
     uint4* gk = reinterpret_cast<uint4*>(p.ka + row0 * p.KP);
-    for (int i = threadIdx.x; i < nrows * vec_per_row; i += blockDim.x) {
-      const int r = i / vec_per_row, c = i - r * vec_per_row;
-      gq[i] = *reinterpret_cast<const uint4*>(tq + r * PT + c * 8);
-      gk[i] = *reinterpret_cast<const uint4*>(tk + r * PT + c * 8);
+    if ((vec_per_row & (vec_per_row - 1)) == 0) {       // 8 or 16 vectors per row: shifts instead of a division
+      const int sh = 31 - __clz(vec_per_row);
+      for (int i = threadIdx.x; i < nrows * vec_per_row; i += blockDim.x) {
+        const int r = i >> sh, c = i & (vec_per_row - 1);
+        gq[i] = *reinterpret_cast<const uint4*>(tq + r * PT + c * 8);
+        gk[i] = *reinterpret_cast<const uint4*>(tk + r * PT + c * 8);
+      }
+    } else {
+      for (int i = threadIdx.x; i < nrows * vec_per_row; i += blockDim.x) {
+        const int r = i / vec_per_row, c = i - r * vec_per_row;
+        gq[i] = *reinterpret_cast<const uint4*>(tq + r * PT + c * 8);
+        gk[i] = *reinterpret_cast<const uint4*>(tk + r * PT + c * 8);
+      }
     }
   }
 }
