@@ -389,9 +389,13 @@ constexpr int CB_NWG = 3, CB_W_TMA = 4 * CB_NWG, CB_W_S = CB_W_TMA + 1, CB_W_G =
               CB_THREADS = 32 * (CB_W_S2 + 1);
 // Streamed-tile stages.  A stage is held from its TMA issue until the tile's GRADIENT MMA has completed (~3.5 tiles of
 // pipeline), so the prefetch lead is ST - 4.5 tiles; with 6 stages the score issuer waited 400-900 cycles per tile for the
-// K tile to land (timeline).  The dQa kernel also holds a 56-88 KB staging tile, the dK/dV kernel does not.
-template <int KATOMS, bool HAS_OUT> struct CbStages {
-  static constexpr int value = HAS_OUT ? (KATOMS >= 3 ? 3 : KATOMS == 2 ? 7 : 10) : (KATOMS >= 3 ? 7 : 10);
+// K tile to land (timeline).  The dQa kernel also holds a 24-88 KB staging tile (sized by OUTW >= KD), the dK/dV kernel does not.
+template <int KATOMS, int OUT_FLOATS> struct CbStages {   // as many as fit beside the stationary tile and the staging tile
+  static constexpr int fixed = 1024 /*alignment slack*/ + 4096 /*side rows, barriers*/ + 2048 /*static dV exchange*/;
+  static constexpr int avail = 232448 - fixed - KATOMS * CB_BM * 128 - OUT_FLOATS * 4;
+  static constexpr int fit = avail / (KATOMS * CB_BN * 128);
+  static constexpr int value = fit > 10 ? 10 : fit;
+  static_assert(value >= 3, "not enough shared memory for three streamed stages");
 };
 
 // TMEM plan of a backward kernel whose accumulator needs ACC columns: QB stationary buffers, NS score slots of 64 columns
@@ -404,13 +408,19 @@ template <int KATOMS, bool HAS_OUT> struct CbStages {
 // slot wait (gradient MMA of tile t+2*ST-NS done) guarantees iff ST >= NS.  Hence NS <= ST for odd ST (an even ST keeps
 // every stage with one issuer).  The 512-pixel dQa kernel (3 stages) deadlocked with 4 slots before this rule.
 // Two score issuers when there are enough stages for both to have a tile in flight; one otherwise.
-__host__ __device__ constexpr int cb_issuers(int stages) { return stages >= 4 ? 2 : 1; }
+// (and an item of a single tile would leave one issuer without a commit on bar_s_done for that item)
+__host__ __device__ constexpr int cb_issuers(int stages, int ntiles) { return (stages >= 4 && ntiles >= 2) ? 2 : 1; }
 struct CbPlan { int QB, NS; uint32_t col_slot0, col_acc; };
-__device__ __forceinline__ CbPlan cb_plan(int katoms, int acc_cols, int stages) {
+__device__ __forceinline__ CbPlan cb_plan(int katoms, int acc_cols, int stages, int ntiles) {
   CbPlan p;
   p.QB = 1;
   p.NS = min(CB_MAXSLOTS, (512 - p.QB * katoms * 32 - acc_cols) / 64);
   if (stages & 1) p.NS = min(p.NS, stages);
+  // Math warpgroups: global tile t belongs to warpgroup t % 3, so before waiting for S'(t) on slot t % NS a warpgroup has
+  // seen S'(t-3) complete; the slot's previous phase is S'(t-NS).  With ONE issuer the score MMAs complete in order and
+  // NS >= 3 suffices; with TWO issuers (even / odd tiles) t-NS and t-3 must come from the same issuer, i.e. NS must be odd
+  // (3 or 5).  NS = 4 with two issuers (512-px dQa kernel with 4 stages) let a warpgroup run ahead of the lagging issuer.
+  if (cb_issuers(stages, ntiles) == 2 && !(p.NS & 1)) p.NS -= 1;
   p.col_slot0 = p.QB * katoms * 32;
   p.col_acc = p.col_slot0 + 64 * p.NS;
   return p;
@@ -418,7 +428,7 @@ __device__ __forceinline__ CbPlan cb_plan(int katoms, int acc_cols, int stages) 
 
 template <int KATOMS, int SIDE_FLOATS, int OUT_FLOATS, int ROW_FLOATS>
 struct __align__(1024) CbSmem {
-  static constexpr int ST = CbStages<KATOMS, (OUT_FLOATS > 0)>::value;
+  static constexpr int ST = CbStages<KATOMS, OUT_FLOATS>::value;
   bf16 stat[KATOMS][CB_BM * 64];
   bf16 strm[ST][KATOMS][CB_BN * 64];
   float side[ST][SIDE_FLOATS];                 // fp32 side tile: v (dq kernel) or dO | delta (dkv kernel)
@@ -450,7 +460,7 @@ __device__ __forceinline__ void cb_init(Smem& sm, int warp, int lane, const CUte
     tc::mbar_init(&sm.bar_stat, 1);
     tc::mbar_init(&sm.bar_stat_free, 128 * CB_NWG);   // every math thread has read its row data (WG0: and moved the tile to TMEM)
     tc::mbar_init(&sm.bar_a_ready, 128);
-    tc::mbar_init(&sm.bar_s_done, cb_issuers(Smem::ST));   // every score issuer has committed its last tile of the item
+    tc::mbar_init(&sm.bar_s_done, cb_issuers(Smem::ST, (L + CB_BN - 1) / CB_BN));   // every score issuer commits its last tile of the item
     tc::mbar_init(&sm.bar_final, 1);
     tc::mbar_init(&sm.bar_acc_free, 128);             // warpgroup 0 drains the accumulator
     tc::mbar_init(&sm.bar_dv, 128 * CB_NWG);
@@ -508,7 +518,7 @@ __device__ __forceinline__ void cb_producer(Smem& sm, const CUtensorMap* m_stat,
 
 template <int KATOMS, int NKS, class Smem>
 __device__ __forceinline__ void cb_score_loop(Smem& sm, uint32_t tmem, CbPlan pl, int ntiles, int my_items, int sidx, long long* tl) {
-  const int nstep = cb_issuers(Smem::ST);          // tiles sidx, sidx + nstep, ...
+  const int nstep = cb_issuers(Smem::ST, ntiles);  // tiles sidx, sidx + nstep, ...
   if (sidx >= nstep) return;
   constexpr uint32_t idesc_s = tc::idesc_bf16_f32(CB_BM, CB_BN);
   constexpr uint32_t STRM_ATOM = (CB_BN * 128) >> 4, STAGE = KATOMS * STRM_ATOM;
@@ -517,16 +527,9 @@ __device__ __forceinline__ void cb_score_loop(Smem& sm, uint32_t tmem, CbPlan pl
   Ring rst, rsl;
   for (int i = 0; i < sidx; ++i) { rst.next(Smem::ST); rsl.next(NS); }
   int it = 0, j = sidx, a_it = -1;
-  bool had_tile = false;                           // (ntiles == 1: an issuer sees only every other item and still owes bar_s_done)
   uint32_t a_tmem = tmem;
   for (int t = sidx; t < total; t += nstep) {
-    while (j >= ntiles) {
-      j -= ntiles;
-      if (!had_tile && lane_id() == 0) tc::mbar_arrive(&sm.bar_s_done);
-      had_tile = false;
-      ++it;
-    }
-    had_tile = true;
+    while (j >= ntiles) { j -= ntiles; ++it; }
     if (it != a_it) {                              // first tile of an item for this issuer: its stationary operand is in TMEM
       tc::mbar_wait(&sm.bar_a_ready, it & 1);
       a_it = it;
@@ -671,19 +674,19 @@ __device__ __forceinline__ void dkv_cc_tile(const uint32_t (&rs)[2][32], uint32_
 
 // ---- query-stationary: dQa ------------------------------------------------------------------------
 // TMEM: Qa buffers [0, QB*32K); slot s: S' at col_slot0 + 64 s (dS, bf16, over its first 32 columns); dQa behind the slots.
-template <int KATOMS, int DVH>
+template <int KATOMS, int DVH, int OUTW>
 __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dq_cc_kernel(
     const __grid_constant__ CUtensorMap tm_q_stat, const __grid_constant__ CUtensorMap tm_k_strm,
     const float* __restrict__ v, const float* __restrict__ d_o, const float* __restrict__ delta, float* __restrict__ dqa, int L,
     int KD, int NQ, int C1, int nqt, int nitems, int dbg, long long* __restrict__ tl_buf) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  typedef CbSmem<KATOMS, CB_BN * DVH, CB_BM * (KATOMS * 64 - 16), DVH + 1> Smem;
+  typedef CbSmem<KATOMS, CB_BN * DVH, CB_BM * OUTW, DVH + 1> Smem;
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int ST = Smem::ST;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = (L + CB_BN - 1) / CB_BN;
   const int my_items = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const CbPlan pl = cb_plan(KATOMS, NQ, ST);
+  const CbPlan pl = cb_plan(KATOMS, NQ, ST, ntiles);
   // clock timeline of one CTA (tools/attn_timeline.py): lane 0 of the issuing warps and of each warpgroup's first warp
   long long* const tl = (tl_buf != nullptr && blockIdx.x == TL_CTA && lane == 0) ? tl_buf : nullptr;
 
@@ -842,7 +845,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = (L + CB_BN - 1) / CB_BN;
   const int my_items = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const CbPlan pl = cb_plan(KATOMS, 32, ST);
+  const CbPlan pl = cb_plan(KATOMS, 32, ST, ntiles);
   __shared__ float dv_xch[2][CB_NWG][CB_BM][DVH];       // dV partial of every tile class (j % 3), by item parity
 
   cb_init<KATOMS>(sm, warp, lane, &tm_k_stat, &tm_q_strm, nqt, v, DVH, nullptr, 0, L);
@@ -996,6 +999,17 @@ int launch_fwd_cc(const Dims& d, const AugLayout& a, const void* qa, const void*
   return 0;
 }
 
+template <int KATOMS, int DVH, int OUTW>
+int launch_bwd_dq_cc(const Dims& d, const AugLayout& a, const CUtensorMap& tq_stat, const CUtensorMap& tk_strm, const float* v,
+                     const float* d_o, const float* delta, float* dqa, int nqt, int nitems, int grid, cudaStream_t st) {
+  const size_t smem = sizeof(CbSmem<KATOMS, CB_BN * DVH, CB_BM * OUTW, DVH + 1>) + 1024;
+  auto kern = attn_bwd_dq_cc_kernel<KATOMS, DVH, OUTW>;
+  AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, CB_THREADS, smem, st>>>(tq_stat, tk_strm, v, d_o, delta, dqa, d.L, a.KD, a.NQ, a.C1, nqt, nitems, g_attn_dbg_mode, g_attn_dbg);
+  AACONV_LAUNCH_OK("attn_bwd_dq_cc");
+  return 0;
+}
+
 template <int KATOMS, int DVH>
 int launch_bwd_cc(const Dims& d, const AugLayout& a, const void* qa, const void* ka, const float* v, const float* d_o,
                   const float* delta, float* dqa, float* dk, float* dv, void* dqkvh, int KPq, cudaStream_t st) {
@@ -1014,14 +1028,10 @@ int launch_bwd_cc(const Dims& d, const AugLayout& a, const void* qa, const void*
                                          nqt, nitems);
     AACONV_LAUNCH_OK("attn_bwd_dkv_cc");
   }
-  {
-    const size_t smem = sizeof(CbSmem<KATOMS, CB_BN * DVH, CB_BM * (KATOMS * 64 - 16), DVH + 1>) + 1024;
-    auto kern = attn_bwd_dq_cc_kernel<KATOMS, DVH>;
-    AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, CB_THREADS, smem, st>>>(tq_stat, tk_strm, v, d_o, delta, dqa, d.L, a.KD, a.NQ, a.C1, nqt, nitems, g_attn_dbg_mode, g_attn_dbg);
-    AACONV_LAUNCH_OK("attn_bwd_dq_cc");
-  }
-  return 0;
+  // the dQa staging tile is OUTW >= KD floats wide; a narrower one leaves room for one more streamed stage at 3 atoms
+  constexpr int OUTW_MAX = KATOMS * 64 - 16, OUTW_MID = KATOMS == 3 ? 152 : OUTW_MAX;
+  if (a.KD <= OUTW_MID) return launch_bwd_dq_cc<KATOMS, DVH, OUTW_MID>(d, a, tq_stat, tk_strm, v, d_o, delta, dqa, nqt, nitems, grid, st);
+  return launch_bwd_dq_cc<KATOMS, DVH, OUTW_MAX>(d, a, tq_stat, tk_strm, v, d_o, delta, dqa, nqt, nitems, grid, st);
 }
 
 }  // namespace

@@ -339,42 +339,43 @@ int pack_nhwc_bf16(const float* in, void* out, int B, int C, int Cp, int HW, cud
   return 0;
 }
 
-// fprop B operand: rows [t*NPc + n] = conv_w[n, :, t] (n < Cc, else 0), then rows [T*NPc + n] = qkv_w[n, :]; K = Cin
-__global__ void pack_wf_kernel(const float* __restrict__ conv_w, const float* __restrict__ qkv_w, bf16* __restrict__ out,
-                               int Cc, int Cin, int CinK, int T, int NPc, int Nqkv, int NPq) {
-  const size_t total = ((size_t)T * NPc + NPq) * CinK;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int cin = (int)(i % CinK);
-    const size_t row = i / CinK;
-    float val = 0.f;
-    if (cin >= Cin) {
-    } else if (row < (size_t)T * NPc) {
-      const int t = (int)(row / NPc), n = (int)(row - (size_t)t * NPc);
-      if (n < Cc) val = conv_w[((size_t)n * Cin + cin) * T + t];
-    } else {
-      const int n = (int)(row - (size_t)T * NPc);
-      if (n < Nqkv) val = qkv_w[(size_t)n * Cin + cin];
-    }
-    out[i] = __float2bfloat16(val);
+// fprop B operand: rows [t*NPc + n] = conv_w[n, :, t] (n < Cc, else 0), then rows [T*NPc + n] = qkv_w[n, :]; K = Cin.
+// One thread per (n, cin): it reads the T contiguous taps of its filter element (coalesced across cin) and writes one bf16
+// per tap row (coalesced across cin); no per-element index division.  grid = (ceil(CinK / 256), NPc + NPq).
+__global__ void __launch_bounds__(256) pack_wf_kernel(const float* __restrict__ conv_w, const float* __restrict__ qkv_w,
+                                                      bf16* __restrict__ out, int Cc, int Cin, int CinK, int T, int NPc, int Nqkv,
+                                                      int NPq) {
+  const int cin = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cin >= CinK) return;
+  const int n = blockIdx.y;
+  if (n < NPc) {
+    const bool live = n < Cc && cin < Cin;
+    const float* src = conv_w + ((size_t)n * Cin + cin) * T;
+    for (int t = 0; t < T; ++t) out[((size_t)t * NPc + n) * CinK + cin] = __float2bfloat16(live ? src[t] : 0.f);
+  } else {
+    const int m = n - NPc;
+    out[((size_t)T * NPc + m) * CinK + cin] = __float2bfloat16((m < Nqkv && cin < Cin) ? qkv_w[(size_t)m * Cin + cin] : 0.f);
   }
 }
 
 // dgrad B operands: wd rows [t*CinP + cin] = conv_w[:, cin, t] over K = co (KPc cols, zero padded);
 //                   wq rows [cin] = qkv_w[:, cin] over K = n (KPq cols, zero padded)
-__global__ void pack_wd_kernel(const float* __restrict__ conv_w, const float* __restrict__ qkv_w, bf16* __restrict__ wd,
-                               bf16* __restrict__ wq, int Cc, int Cin, int T, int CinP, int KPc, int Nqkv, int KPq) {
-  const size_t n1 = (size_t)T * CinP * KPc, n2 = (size_t)CinP * KPq;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += (size_t)gridDim.x * blockDim.x) {
-    if (i < n1) {
-      const int co = (int)(i % KPc);
-      const size_t row = i / KPc;
-      const int t = (int)(row / CinP), cin = (int)(row - (size_t)t * CinP);
-      wd[i] = __float2bfloat16((co < Cc && cin < Cin) ? conv_w[((size_t)co * Cin + cin) * T + t] : 0.f);
-    } else {
-      const size_t j = i - n1;
-      const int n = (int)(j % KPq), cin = (int)(j / KPq);
-      wq[j] = __float2bfloat16((n < Nqkv && cin < Cin) ? qkv_w[(size_t)n * Cin + cin] : 0.f);
-    }
+// One thread per (cin, co): it reads the T contiguous taps of its filter element and writes one bf16 per tap row, coalesced
+// along co; no per-element index division.  grid = (ceil(KPc / 128) + ceil(KPq / 128), CinP), 128 threads.
+__global__ void __launch_bounds__(128) pack_wd_kernel(const float* __restrict__ conv_w, const float* __restrict__ qkv_w,
+                                                      bf16* __restrict__ wd, bf16* __restrict__ wq, int Cc, int Cin, int T, int CinP,
+                                                      int KPc, int Nqkv, int KPq, int nbx_conv) {
+  const int cin = blockIdx.y;
+  if ((int)blockIdx.x < nbx_conv) {
+    const int co = blockIdx.x * 128 + threadIdx.x;
+    if (co >= KPc) return;
+    const bool live = co < Cc && cin < Cin;
+    const float* src = conv_w + ((size_t)co * Cin + cin) * T;
+    for (int t = 0; t < T; ++t) wd[((size_t)t * CinP + cin) * KPc + co] = __float2bfloat16(live ? src[t] : 0.f);
+  } else {
+    const int n = (blockIdx.x - nbx_conv) * 128 + threadIdx.x;
+    if (n >= KPq) return;
+    wq[(size_t)cin * KPq + n] = __float2bfloat16((n < Nqkv && cin < Cin) ? qkv_w[(size_t)n * Cin + cin] : 0.f);
   }
 }
 
@@ -484,8 +485,8 @@ int tc_fprop(const Dims& d, const TcGemmBufs& t, const float* x, const float* co
              float* q, float* k, float* v, cudaStream_t st) {
   const int T = d.ks * d.ks, s = d.stride;
   AACONV_TRY(pack_nhwc_bf16(x, t.xh, d.B, d.Cin, t.CinK, d.Hin * d.Win, st));
-  pack_wf_kernel<<<148 * 4, 256, 0, st>>>(conv_w, qkv_w, static_cast<bf16*>(t.wf), d.Cc, d.Cin, t.CinK, T, t.NPc, d.Nqkv,
-                                           t.NPq);
+  pack_wf_kernel<<<dim3(cdiv(t.CinK, 256), t.NPc + t.NPq), 256, 0, st>>>(conv_w, qkv_w, static_cast<bf16*>(t.wf), d.Cc, d.Cin,
+                                                                          t.CinK, T, t.NPc, d.Nqkv, t.NPq);
   AACONV_LAUNCH_OK("pack_wf");
 
   PGParams p;
@@ -553,8 +554,8 @@ int tc_pack_grads(const Dims& d, const TcGemmBufs& t, const float* dy, const flo
 // dx = conv dgrad + qkv dgrad (needs tc_pack_grads first).
 int tc_dgrad(const Dims& d, const TcGemmBufs& t, const float* conv_w, const float* qkv_w, float* dx, cudaStream_t st) {
   const int T = d.ks * d.ks, s = d.stride;
-  pack_wd_kernel<<<148 * 4, 256, 0, st>>>(conv_w, qkv_w, static_cast<bf16*>(t.wd), static_cast<bf16*>(t.wq), d.Cc, d.Cin, T,
-                                           t.CinP, t.KPc, d.Nqkv, t.KPq);
+  pack_wd_kernel<<<dim3(cdiv(t.KPc, 128) + cdiv(t.KPq, 128), t.CinP), 128, 0, st>>>(
+      conv_w, qkv_w, static_cast<bf16*>(t.wd), static_cast<bf16*>(t.wq), d.Cc, d.Cin, T, t.CinP, t.KPc, d.Nqkv, t.KPq, cdiv(t.KPc, 128));
   AACONV_LAUNCH_OK("pack_wd");
   // taps of the conv (and the 1x1 projection) that reach input-pixel class (rh, rw)
   auto class_segs = [&](int rh, int rw, PGSeg* out) {
@@ -858,7 +859,7 @@ int tc_wgrad(const Dims& d, const TcGemmBufs& t, float* dwc, float* dwq, float* 
   AACONV_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   wgrad_tc_kernel<<<dim3(nt, splits), WG_THREADS, smem, st>>>(p);
   AACONV_LAUNCH_OK("conv_qkv_wgrad_tc");
-  wgrad_reduce_kernel<<<dim3(128, nt), 256, 0, st>>>(partial, p.shape, splits, dwc, dwq, d.Cc, d.Cin, d.Nqkv);
+  wgrad_reduce_kernel<<<dim3(std::max(16, std::min(128, 2368 / nt)), nt), 256, 0, st>>>(partial, p.shape, splits, dwc, dwq, d.Cc, d.Cin, d.Nqkv);
   AACONV_LAUNCH_OK("wgrad_reduce");
   return 0;
 }

