@@ -18,9 +18,12 @@ using tc::smem_u32;
 typedef __nv_bfloat16 bf16;
 
 constexpr int PG_THREADS = 192;     // warps 0-3 epilogue, warp 4 TMA, warp 5 MMA
-constexpr int PG_STAGES = 6;
+// TWO CTAs per SM: 3 stages (96 KB) and 2 accumulator chunks (256 TMEM columns) each.  One CTA per SM with 6 stages and 4
+// chunks left the second of 1.5 (fprop) and the fourth of 3.03 (dgrad) waves almost empty and nothing to run under a CTA's
+// epilogue; with half-size CTAs the tail is half as long and one CTA's epilogue overlaps the other's main loop.
+constexpr int PG_STAGES = 3;
 constexpr int PG_MAX_SEGS = 16;
-constexpr int PG_MAX_CHUNKS = 4;    // 4 x 128 fp32 accumulator columns = all of TMEM
+constexpr int PG_MAX_CHUNKS = 2;    // 2 x 128 fp32 accumulator columns = half of TMEM
 
 struct PGSeg { int amap, dw, dh, katoms, bmap, brow; };       // one K-segment: a tap (or the qkv "tap")
 struct PGChunk { int n0, seg_begin, seg_end, kind; };          // one 128-wide accumulator
@@ -51,7 +54,7 @@ struct __align__(1024) PGSmem {
 constexpr int PG_MAX_JOBS = 8;
 struct PGJobs { PGParams job[PG_MAX_JOBS]; };
 
-__global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_tc_kernel(const __grid_constant__ PGJobs jobs) {
+__global__ void __launch_bounds__(PG_THREADS, 2) pixel_gemm_tc_kernel(const __grid_constant__ PGJobs jobs) {
   const PGParams& p = jobs.job[blockIdx.y];
   if ((int)blockIdx.x >= p.ncta) return;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -64,7 +67,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_tc_kernel(const __gr
     for (int c = 0; c < PG_MAX_CHUNKS; ++c) tc::mbar_init(&sm.bar_acc[c], 1);
     tc::fence_barrier_init();
   }
-  if (warp == 5) tc::tmem_alloc<512>(&sm.tmem_base);
+  if (warp == 5) tc::tmem_alloc<128 * PG_MAX_CHUNKS>(&sm.tmem_base);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pixel_gemm_tc_kernel(const __gr
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 5) tc::tmem_dealloc<512>(tmem);
+  if (warp == 5) tc::tmem_dealloc<128 * PG_MAX_CHUNKS>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------------
