@@ -42,9 +42,9 @@ def flops_fwd(B, cin, hin, cout, dk, dv, nh=8, ks=3):
 
 
 # dram bytes per launch of the dominant kernels at T1/B=16, copied from the ncu --set full captures under profiles/
-NCU_DRAM_BYTES_PER_LAUNCH = {   # profiles/r01_d_persistent.md (MB rd + MB wr columns)
-    'attn_fwd_cc': 110.5e6, 'attn_bwd_dkv_cc': 117.2e6, 'attn_bwd_dq_cc': 153.0e6, 'aug_build_fwd': 81.1e6, 'rel_bwd': 103.4e6,
-    'conv_qkv_fprop_tc': 62.4e6, 'conv_qkv_dgrad_tc': 81.5e6, 'conv_qkv_wgrad_tc': 83.0e6, 'pack_nhwc_bf16': 130.0e6,
+NCU_DRAM_BYTES_PER_LAUNCH = {   # profiles/r01_e_final.md (MB rd + MB wr columns)
+    'attn_fwd_cc': 111.2e6, 'attn_bwd_dkv_cc': 116.8e6, 'attn_bwd_dq_cc': 154.7e6, 'aug_build_fwd': 80.0e6, 'rel_bwd': 103.1e6,
+    'conv_qkv_fprop_tc': 60.9e6, 'conv_qkv_dgrad_tc': 83.4e6, 'conv_qkv_wgrad_tc': 82.4e6, 'pack_nhwc_bf16': 130.0e6,
 }
 
 
