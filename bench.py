@@ -145,6 +145,8 @@ def run_model(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        if args.cuda_graph:
+            os.environ.setdefault('TORCH_NCCL_ASYNC_ERROR_HANDLING', '0')   # no watchdog aborts while collectives are being captured
         dist.init_process_group('nccl', device_id=dev)
     W, K, B = max(args.warmup, 3), args.steps, args.batch
     ts = TrainStep(dev, size=args.size, precision=args.precision, cuda_graph=args.cuda_graph)
@@ -208,6 +210,11 @@ def run_model(args):
                 'gpu_launches': launches, 'clocks': sampler.summary(), 'roofline': None}
         print(json.dumps(line), flush=True)
     if world > 1:
+        ts.release()
+        barrier()
+        if args.cuda_graph:          # process-group teardown after captured NCCL work has been seen to hang: leave without it
+            sys.stdout.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 

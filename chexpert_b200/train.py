@@ -7,6 +7,8 @@ radiograph-shaped batches.
 The loop around it (tqdm, tensorboard, checkpoint tracker, periodic eval; chexpert.py:167-193) is outside the hot
 path and not rebuilt; `TrainStep` is what bench.py times and what a user's own loop would call per batch.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -54,8 +56,10 @@ class TrainStep:
         # cuda_graph: after `graph_after` eager steps (they create the momentum buffers and warm cuDNN up) the whole step --
         # forward, loss, backward, bucket all-reduces, optimizer -- is captured once and replayed: the ~3000 small launches
         # of the 120-layer dense blocks stop being bound by the Python / launch rate.  Re-captured when the lr changes.
-        self.cuda_graph = bool(cuda_graph and self.device.type == 'cuda' and self.world == 1)   # (NCCL work handles inside a
-        # capture hung at 2 GPUs: the multi-rank step stays eager)
+        # Multi-rank: the bucket all-reduces are captured too.  That needs the thread-local capture mode (NCCL's watchdog
+        # thread polls events during the capture; the default global mode hung at 2 GPUs) and, at exit, the graph has to go
+        # before the process group (release()).
+        self.cuda_graph = bool(cuda_graph and self.device.type == 'cuda')
         self.graph_after = graph_after
         self._calls = 0
         self._graph = None
@@ -84,10 +88,18 @@ class TrainStep:
         if self.buckets is None:
             self.opt.zero_grad(set_to_none=True)
         n0 = _lib.launch_count()
-        with torch.cuda.graph(self._graph):
+        mode = 'thread_local' if self.world > 1 else 'global'   # NCCL's watchdog thread polls events during the capture
+        with torch.cuda.graph(self._graph, capture_error_mode=mode):
             self._sloss = self._step(self._sx, self._st)
         self.graph_launches = _lib.launch_count() - n0      # kernels of libaaconv_b200 inside one replay
         self._graph_lr = [g['lr'] for g in self.opt.param_groups]
+
+    def release(self):
+        """Drop the captured graph (call before dist.destroy_process_group())."""
+        self._graph = None
+        self._sloss = self._sx = self._st = None
+        if self.device.type == 'cuda':
+            torch.cuda.synchronize(self.device)
 
     def __call__(self, x, target):
         """-> loss (0-dim device tensor; no host sync, unlike loss.item() at chexpert.py:167)."""
