@@ -7,8 +7,10 @@
 //
 // Why (measured): the value width is 1..2, so P.V / dO.v are 1-2 FMAs per score next to one MUFU.EX2;
 // doing them in registers halves the TMEM reads, removes two of the four barrier round trips per tile and shrinks a score
-// slot to the S' columns alone, so that four slots fit in TMEM and the issuing warps run far enough ahead of the math
+// slot to the S' columns alone, so that five slots fit in TMEM and the issuing warps run far enough ahead of the math
 // warpgroups to keep both busy.  v / dO / delta tiles come as fp32 through 1-D bulk copies on the K/Q tile's barrier.
+// All three kernels are PERSISTENT (one CTA per SM walks a list of (batch*head, stationary tile) items with its barrier
+// rings running on a global tile counter); the rules that keeps their mbarrier parity waits exact are next to cb_plan.
 // Reference rows a3-a8 (attn_aug_conv.py:75-91) and their adjoint; layouts as in attn_tc_bwd.cu.
 #include <algorithm>
 #include "tc_common.cuh"
@@ -20,7 +22,7 @@ using tc::smem_u32;
 typedef __nv_bfloat16 bf16;
 
 // ablation switches for tools/attn_ablate.py (0 in production): 1 no MUFU, 2 no global traffic after the first tiles,
-// 4 no gradient MMAs, 8 no math at all
+// 4 no gradient MMAs, 8 no math at all, 32 dQa drain by per-row stores; 16 = soft mbarrier timeouts (tools/dbg_shape.py)
 int g_attn_dbg_mode = 0;
 static unsigned long long* g_mbar_host_log = nullptr;
 extern long long* g_attn_dbg;      // attn_tc_bwd.cu: timeline buffer of TL_EVENTS x TL_COLS stamps (tools/attn_timeline.py)
