@@ -319,18 +319,70 @@ def main():
     y_host = torch.empty(B, cout, H, H).pin_memory()
     g_host = [torch.empty(p.shape).pin_memory() for p in params]
 
-    def e2e_step():
-        xd = x_host.to(dev, non_blocking=True).requires_grad_(True)
-        dyd = dy_host.to(dev, non_blocking=True)
-        y = step(xd, dyd)
-        y_host.copy_(y.detach(), non_blocking=True)
-        for gh, p in zip(g_host, params):
-            gh.copy_(p.grad, non_blocking=True)
+    # The way a training loop feeds a GPU: pinned host buffers, the uploads of step k+1 on a copy stream while step k
+    # computes, results read back on a third stream from double-buffered device staging.  Every step's H2D and D2H copies
+    # are inside the timed region; they overlap compute (a 118 MB upload takes 1.9 ms, the step 0.8 ms).
+    up, down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    xbuf = [torch.empty_like(x) for _ in range(2)]
+    dybuf = [torch.empty_like(dy) for _ in range(2)]
+    ystage = [torch.empty(B, cout, H, H, device=dev) for _ in range(2)]
+    gstage = [[torch.empty_like(p) for p in params] for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]       # upload into input buffer i finished
+    freed = [torch.cuda.Event() for _ in range(2)]       # compute on input buffer i finished
+    staged = [torch.cuda.Event() for _ in range(2)]      # results of a step are in staging buffer i
+    drained = [torch.cuda.Event() for _ in range(2)]     # staging buffer i has been read back
+    state = {'k': 0, 'n': 0}
 
-    for _ in range(2):
-        e2e_step()
+    def upload(i):
+        with torch.cuda.stream(up):
+            up.wait_event(freed[i])
+            xbuf[i].copy_(x_host, non_blocking=True)
+            dybuf[i].copy_(dy_host, non_blocking=True)
+            ready[i].record(up)
+
+    def e2e_step():
+        cur = torch.cuda.current_stream(dev)
+        k = state['k']
+        i = k & 1
+        if k == 0:
+            upload(i)
+        if k + 1 < state['n']:
+            upload(i ^ 1)                                # next step's inputs travel while this step computes
+        cur.wait_event(ready[i])
+        y = step(xbuf[i].detach().requires_grad_(True), dybuf[i])
+        freed[i].record(cur)
+        cur.wait_event(drained[i])
+        ystage[i].copy_(y.detach())
+        for gs, p in zip(gstage[i], params):
+            gs.copy_(p.grad)
+        staged[i].record(cur)
+        with torch.cuda.stream(down):
+            down.wait_event(staged[i])
+            y_host.copy_(ystage[i], non_blocking=True)
+            for gh, gs in zip(g_host, gstage[i]):
+                gh.copy_(gs, non_blocking=True)
+            drained[i].record(down)
+        state['k'] = k + 1
+
+    def e2e_timed(n):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        state['k'], state['n'] = 0, n
+        torch.cuda.synchronize()
+        cur = torch.cuda.current_stream(dev)
+        for ev in freed + drained:
+            ev.record(cur)
+        a.record()
+        for _ in range(n):
+            e2e_step()
+        cur.wait_stream(down)                            # the last read-back is part of the region
+        cur.wait_stream(up)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    e2e_timed(3)
     barrier()
-    ms_e2e = timed(e2e_step, max(3, K // 2))
+    ms_e2e = e2e_timed(max(6, K // 2))
     barrier()
     sampler.stop_flag = True
     sampler.join(timeout=2)
