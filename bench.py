@@ -459,7 +459,8 @@ def main():
                            'precision': args.precision, 'l2': 'flushed between timed steps (256 MiB memset)' if not args.no_flush else 'not flushed',
                            'gflop_per_step_per_gpu': f_tot / 1e9, 'wall_s_timed_region': t_wall},
                 'e2e': {'value': f_tot * world / (ms_e2e * 1e-3) / 1e12, 'unit': 'TFLOP/s', 'ms_per_step': ms_e2e,
-                        'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+                        'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                        'pipeline': 'pinned host buffers; upload of step k+1 and read-back of step k on side streams overlap compute'},
                 'gpu_launches': launches, 'clocks': sampler.summary(), 'roofline': roof, 'kernels': kern}
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
