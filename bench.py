@@ -149,7 +149,7 @@ def run_model(args):
             os.environ.setdefault('TORCH_NCCL_ASYNC_ERROR_HANDLING', '0')   # no watchdog aborts while collectives are being captured
         dist.init_process_group('nccl', device_id=dev)
     W, K, B = max(args.warmup, 3), args.steps, args.batch
-    ts = TrainStep(dev, size=args.size, precision=args.precision, cuda_graph=args.cuda_graph)
+    ts = TrainStep(dev, size=args.size, precision=args.precision, cuda_graph=args.cuda_graph, channels_last=args.channels_last)
     xh, th = synthetic_batch(B, size=args.size, seed=1000 + rank)
     xh, th = xh.pin_memory(), th.pin_memory()
     x, t = xh.to(dev), th.to(dev)
@@ -234,6 +234,7 @@ def main():
                     help="layer: AAConv2d fwd+bwd microbench (configs[1], the headline); model: aadensenet121 training step "
                          "(configs[2]: batch 16/GPU, 320x320, SGD-nesterov, gradient all-reduce), images/s")
     ap.add_argument('--size', type=int, default=320)
+    ap.add_argument('--channels-last', action='store_true', help='model workload: channels_last memory format for the dense blocks')
     ap.add_argument('--cuda-graph', action='store_true', help='model workload: capture the whole training step in a CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -28,6 +28,9 @@ static int validate(const aaconv_dims* dd, int precision) {
     if (Hc != H || Wc != W)
       return fail(AACONV_E_ARG, "conv branch map (%d,%d) != attention map (%d,%d): cannot concatenate", Hc, Wc, H, W);
   }
+  // bf16 mode has no fallback to the fp32 kernels: report WHY a shape is outside the tensor-core kernels here, before any
+  // buffer is sized (the *_bytes() queries return 0 for an invalid call)
+  if (precision == AACONV_BF16) AACONV_TRY(aug_supported(Dims(d)));
   return 0;
 }
 }  // namespace aaconv

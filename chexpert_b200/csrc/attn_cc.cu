@@ -996,7 +996,7 @@ int launch_fwd_cc(const Dims& d, const AugLayout& a, const void* qa, const void*
   auto kern = attn_fwd_cc_kernel<KATOMS, DVH>;
   AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nqt = cdiv(d.L, CF_BM), nitems = nqt * d.BN;
-  kern<<<std::min(nitems, sm_count()), CF_THREADS, smem, st>>>(tq, tk, v, o, lse, d.L, a.C1, nqt, nitems, g_attn_dbg_mode);
+  kern<<<std::min(nitems, sm_count()), CF_THREADS, smem, AACONV_ST(st)>>>(tq, tk, v, o, lse, d.L, a.C1, nqt, nitems, g_attn_dbg_mode);
   AACONV_LAUNCH_OK("attn_fwd_cc");
   return 0;
 }
@@ -1007,7 +1007,7 @@ int launch_bwd_dq_cc(const Dims& d, const AugLayout& a, const CUtensorMap& tq_st
   const size_t smem = sizeof(CbSmem<KATOMS, CB_BN * DVH, CB_BM * OUTW, DVH + 1>) + 1024;
   auto kern = attn_bwd_dq_cc_kernel<KATOMS, DVH, OUTW>;
   AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, CB_THREADS, smem, st>>>(tq_stat, tk_strm, v, d_o, delta, dqa, d.L, a.KD, a.NQ, a.C1, nqt, nitems, g_attn_dbg_mode, g_attn_dbg);
+  kern<<<grid, CB_THREADS, smem, AACONV_ST(st)>>>(tq_stat, tk_strm, v, d_o, delta, dqa, d.L, a.KD, a.NQ, a.C1, nqt, nitems, g_attn_dbg_mode, g_attn_dbg);
   AACONV_LAUNCH_OK("attn_bwd_dq_cc");
   return 0;
 }
@@ -1026,7 +1026,7 @@ int launch_bwd_cc(const Dims& d, const AugLayout& a, const void* qa, const void*
     const size_t smem = sizeof(CbSmem<KATOMS, CB_BN * (DVH + 1), 0, DVH>) + 1024;
     auto kern = attn_bwd_dkv_cc_kernel<KATOMS, DVH>;
     AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, CB_THREADS, smem, st>>>(tk_stat, tq_strm, v, d_o, delta, dk, dv, static_cast<bf16*>(dqkvh), KPq, d.nh, d.L, d.dkh, a.C1,
+    kern<<<grid, CB_THREADS, smem, AACONV_ST(st)>>>(tk_stat, tq_strm, v, d_o, delta, dk, dv, static_cast<bf16*>(dqkvh), KPq, d.nh, d.L, d.dkh, a.C1,
                                          nqt, nitems);
     AACONV_LAUNCH_OK("attn_bwd_dkv_cc");
   }

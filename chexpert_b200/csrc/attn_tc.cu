@@ -271,7 +271,7 @@ static int launch_fwd(const Dims& d, const AugLayout& a, const CUtensorMap& tq, 
   auto kern = attn_fwd_tc_kernel<KATOMS>;
   AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(d.L, FA_BM), d.BN);
-  kern<<<grid, FA_THREADS, smem, st>>>(tq, tk, o, lse, d.L, d.dvh, a.C1);
+  kern<<<grid, FA_THREADS, smem, AACONV_ST(st)>>>(tq, tk, o, lse, d.L, d.dvh, a.C1);
   AACONV_LAUNCH_OK("attn_fwd_tc");
   return 0;
 }

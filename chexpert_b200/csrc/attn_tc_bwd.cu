@@ -421,13 +421,13 @@ static int launch_bwd(const Dims& d, const AugLayout& a, const void* qa, const v
   {
     auto kern = attn_bwd_dkv_tc_kernel<KATOMS>;
     AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, PP_THREADS, smem, st>>>(tk_stat, tq_strm, dk, dv, static_cast<bf16*>(dqkvh), KPq, d.nh, d.L, d.dkh, d.dvh, a.C1);
+    kern<<<grid, PP_THREADS, smem, AACONV_ST(st)>>>(tk_stat, tq_strm, dk, dv, static_cast<bf16*>(dqkvh), KPq, d.nh, d.L, d.dkh, d.dvh, a.C1);
     AACONV_LAUNCH_OK("attn_bwd_dkv_tc");
   }
   {
     auto kern = attn_bwd_dq_tc_kernel<KATOMS>;
     AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, PP_THREADS, smem, st>>>(tq_stat, tk_strm, dqa, d.L, a.KD, a.NQ, a.C1, g_attn_dbg);
+    kern<<<grid, PP_THREADS, smem, AACONV_ST(st)>>>(tq_stat, tk_strm, dqa, d.L, a.KD, a.NQ, a.C1, g_attn_dbg);
     AACONV_LAUNCH_OK("attn_bwd_dq_tc");
   }
   return 0;
@@ -484,7 +484,7 @@ int aug_bwd_dq(const Dims& d, const float* dqa, const float* krw, const float* k
   const size_t smem = d.relative ? (size_t)d.dkh * (d.RW + d.RH) * sizeof(float) : 0;
   AACONV_CUDA_OK(cudaFuncSetAttribute(aug_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<size_t>((rows * d.dkh + 255) / 256, 148 * 16);
-  aug_bwd_dq_kernel<<<grid, 256, smem, st>>>(dqa, krw, krh, dq, rows, d.L, d.H, d.W, d.dkh, a.KD, d.relative);
+  aug_bwd_dq_kernel<<<grid, 256, smem, AACONV_ST(st)>>>(dqa, krw, krh, dq, rows, d.L, d.H, d.W, d.dkh, a.KD, d.relative);
   AACONV_LAUNCH_OK("aug_bwd_dq");
   return 0;
 }

@@ -405,7 +405,7 @@ int aug_build_fwd(const Dims& d, const float* q, const float* k, const float* v,
   AACONV_CUDA_OK(cudaFuncSetAttribute(aug_build_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = std::max(1, std::min(4, (int)(220 * 1024 / (smem + 1024))));
   const int grid = std::min(p.ntiles, 148 * per_sm);
-  aug_build_fwd_kernel<<<grid, 256, smem, st>>>(p);
+  aug_build_fwd_kernel<<<grid, 256, smem, AACONV_ST(st)>>>(p);
   AACONV_LAUNCH_OK("aug_build_fwd");
   return 0;
 }
@@ -414,11 +414,75 @@ int aug_patch_bwd(const Dims& d, const float* lse, const float* d_o, const float
   const AugLayout a = aug_layout(d);
   const size_t rows = (size_t)d.BN * d.L;
   const unsigned grid = (unsigned)((rows + 255) / 256);
-  aug_patch_bwd_kernel<<<grid, 256, 0, st>>>(lse, d_o, o, static_cast<bf16*>(qa), delta, rows, d.dvh, a.KD, a.C1, a.KP);
+  aug_patch_bwd_kernel<<<grid, 256, 0, AACONV_ST(st)>>>(lse, d_o, o, static_cast<bf16*>(qa), delta, rows, d.dvh, a.KD, a.C1, a.KP);
   AACONV_LAUNCH_OK("aug_patch_bwd");
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// attention map of the visualise path (opt-in; attn_aug_conv.py:87) from the bf16 kernels' OWN operands and statistics:
+//   P[q, k] = 2^( Qa[q, 0:KD] . Ka[k, 0:KD]  -  log2(e) * lse[q] )
+// Qa / Ka are the bf16 augmented operands the tcgen05 score MMAs consumed (log2(e) is folded into Qa), lse is what the
+// bf16 forward kernel's online softmax produced; the dot product is accumulated in fp32 like the tensor core does.  Not a
+// hot path (the map is (B, nh, L, L) fp32 and only the visualise path asks for it): plain shared-memory tiles, FFMA.
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int AW_T = 64, AW_KMAX = 160;
+__global__ void __launch_bounds__(256) aug_weights_kernel(const bf16* __restrict__ qa, const bf16* __restrict__ ka,
+                                                          const float* __restrict__ lse, float* __restrict__ w, int L, int KD, int KP) {
+  __shared__ __align__(16) bf16 qs[AW_T][AW_KMAX + 8];
+  __shared__ __align__(16) bf16 ks[AW_T][AW_KMAX + 8];
+  const int bn = blockIdx.z, q0 = blockIdx.y * AW_T, k0 = blockIdx.x * AW_T;
+  const int KD2 = (KD + 1) & ~1;
+  const size_t base = (size_t)bn * L;
+  for (int i = threadIdx.x; i < AW_T * (KD2 / 2); i += 256) {
+    const int r = i / (KD2 / 2), c = (i - r * (KD2 / 2)) * 2;
+    uint32_t vq = 0, vk = 0;
+    if (q0 + r < L) vq = *reinterpret_cast<const uint32_t*>(qa + (base + q0 + r) * KP + c);
+    if (k0 + r < L) vk = *reinterpret_cast<const uint32_t*>(ka + (base + k0 + r) * KP + c);
+    if (c + 1 >= KD) { vq &= 0xffffu; vk &= 0xffffu; }      // odd KD: column KD belongs to the statistics block
+    *reinterpret_cast<uint32_t*>(&qs[r][c]) = vq;
+    *reinterpret_cast<uint32_t*>(&ks[r][c]) = vk;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;     // 16 x 16 threads, 4 x 4 outputs each (rows ty + 16 i, cols tx + 16 j)
+  float acc[4][4] = {};
+  for (int c = 0; c < KD2; c += 2) {
+    float2 a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qs[ty + 16 * i][c]));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ks[tx + 16 * j][c]));
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i].y, b[j].y, fmaf(a[i].x, b[j].x, acc[i][j]));
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = q0 + ty + 16 * i;
+    if (q >= L) continue;
+    const float l2 = lse[base + q] * 1.4426950408889634f;
+    float* row = w + (base + q) * (size_t)L;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx + 16 * j;
+      if (k < L) row[k] = exp2f(acc[i][j] - l2);
+    }
+  }
+}
+}  // namespace
+
+int aug_weights(const Dims& d, const void* qa, const void* ka, const float* lse, float* weights, cudaStream_t st) {
+  const AugLayout a = aug_layout(d);
+  if (a.KD > AW_KMAX) return fail(AACONV_E_UNSUPPORTED, "aug_weights: %d logit columns > %d", a.KD, AW_KMAX);
+  dim3 grid(cdiv(d.L, AW_T), cdiv(d.L, AW_T), d.BN);
+  aug_weights_kernel<<<grid, 256, 0, AACONV_ST(st)>>>(static_cast<const bf16*>(qa), static_cast<const bf16*>(ka), lse, weights, d.L, a.KD,
+                                                      a.KP);
+  AACONV_LAUNCH_OK("aug_weights_bf16");
+  return 0;
+}
 
 int out_bwd_patch_supported(const Dims& d) { return (d.nh == 8 && (d.dvh == 1 || d.dvh == 2)) ? 0 : AACONV_E_UNSUPPORTED; }
 size_t out_bwd_patch_partial_floats(const Dims& d) { return (size_t)cdiv(d.B * d.L, 256) * d.dv * d.dv; }
@@ -430,14 +494,14 @@ int out_bwd_patch(const Dims& d, const float* dy, const float* o, const float* l
   const int grid = cdiv(d.B * d.L, 256);
   float* wp = dw ? partial : nullptr;
   if (d.dvh == 1)
-    out_bwd_patch_kernel<8, 1><<<grid, 256, 0, st>>>(dy, o, lse, wout, d_o, delta, static_cast<bf16*>(qa), wp, d.B, d.L, d.Cout, d.Cc,
+    out_bwd_patch_kernel<8, 1><<<grid, 256, 0, AACONV_ST(st)>>>(dy, o, lse, wout, d_o, delta, static_cast<bf16*>(qa), wp, d.B, d.L, d.Cout, d.Cc,
                                                      a.KD, a.C1, a.KP);
   else
-    out_bwd_patch_kernel<8, 2><<<grid, 256, 0, st>>>(dy, o, lse, wout, d_o, delta, static_cast<bf16*>(qa), wp, d.B, d.L, d.Cout, d.Cc,
+    out_bwd_patch_kernel<8, 2><<<grid, 256, 0, AACONV_ST(st)>>>(dy, o, lse, wout, d_o, delta, static_cast<bf16*>(qa), wp, d.B, d.L, d.Cout, d.Cc,
                                                      a.KD, a.C1, a.KP);
   AACONV_LAUNCH_OK("out_bwd_patch");
   if (dw) {
-    out_w_reduce_kernel<<<cdiv(d.dv * d.dv, 32), 256, 0, st>>>(partial, grid, d.dv * d.dv, dw);
+    out_w_reduce_kernel<<<cdiv(d.dv * d.dv, 32), 256, 0, AACONV_ST(st)>>>(partial, grid, d.dv * d.dv, dw);
     AACONV_LAUNCH_OK("out_w_reduce");
   }
   return 0;
@@ -703,7 +767,7 @@ template <int MT, int NTE>
 int launch_rel_bwd(const RelBwdP& p, int grid, size_t smem, cudaStream_t st) {
   auto kern = rel_bwd_kernel<MT, NTE>;
   AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, 256, smem, st>>>(p);
+  kern<<<grid, 256, smem, AACONV_ST(st)>>>(p);
   AACONV_LAUNCH_OK("rel_bwd");
   return 0;
 }
@@ -769,7 +833,7 @@ int rel_bwd(const Dims& d, const float* dqa, const float* q, const float* krw, c
   else AACONV_TRY(dispatch_rel_bwd<4>(mt, p, grid, smem, st));
   if (dkrw || dkrh) {
     const int n = 2 * p.RP * p.DK8;
-    rel_bwd_reduce_kernel<<<cdiv(n, 32), 256, 0, st>>>(partial, grid, p.RP, p.DK8, d.dkh, d.RW, d.RH, dkrw, dkrh);
+    rel_bwd_reduce_kernel<<<cdiv(n, 32), 256, 0, AACONV_ST(st)>>>(partial, grid, p.RP, p.DK8, d.dkh, d.RW, d.RH, dkrw, dkrh);
     AACONV_LAUNCH_OK("rel_bwd_reduce");
   }
   return 0;

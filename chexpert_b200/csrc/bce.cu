@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ z, c
 
 int bce_launch(const float* z, const float* targets, int ld, const int32_t* cols, int B, int C, float* el,
                float* loss, float* dz, const float* grad_scale, cudaStream_t st) {
-  bce_kernel<<<1, 256, 0, st>>>(z, targets, ld, cols, B, C, el, loss, dz, grad_scale);
+  bce_kernel<<<1, 256, 0, AACONV_ST(st)>>>(z, targets, ld, cols, B, C, el, loss, dz, grad_scale);
   AACONV_LAUNCH_OK("bce");
   return 0;
 }

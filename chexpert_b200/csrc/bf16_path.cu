@@ -9,7 +9,7 @@ namespace aaconv {
 
 namespace {
 struct Scratch {
-  float *d_o, *delta, *dq, *dk, *dv, *partial, *relpart, *dqa, *rw, *rh, *o_tmp, *lse_tmp;
+  float *d_o, *delta, *dq, *dk, *dv, *partial, *relpart, *dqa;
   TcGemmBufs gemm;
   bool gemm_ok;
   size_t bytes;
@@ -31,11 +31,7 @@ struct Scratch {
       char* gb = c.take<char>(gemm_ok ? tc_gemm_bufs(d, nullptr).bytes : 0);
       gemm = tc_gemm_bufs(d, gb);
     }
-    const bool w = want_weights && d.relative;
-    rw = c.take<float>(w ? rows * d.RW : 0);
-    rh = c.take<float>(w ? rows * d.RH : 0);
-    o_tmp = c.take<float>(want_weights ? rows * d.dvh : 0);
-    lse_tmp = c.take<float>(want_weights ? rows : 0);
+    (void)want_weights;   // the attention map is computed from the saved operands: no extra scratch
     bytes = c.off;
   }
 };
@@ -87,11 +83,8 @@ int bf16_forward(const Dims& d, const float* x, const aaconv_params* p, float* y
   AACONV_TRY(aug_build_fwd(d, q, k, v, p->key_rel_w, p->key_rel_h, sa.qa, sa.ka, st));
   if (cc_attn_supported(d) == 0) AACONV_TRY(cc_attn_fwd(d, sa.qa, sa.ka, v, o, lse, st));
   else AACONV_TRY(tc_attn_fwd(d, sa.qa, sa.ka, o, lse, st));
-  if (weights) {   // visualise path only: exact fp32 map (own fp32 statistics), independent of the bf16 kernel
-    AACONV_TRY(f32_rel_fwd(d, q, p->key_rel_w, p->key_rel_h, w.rw, w.rh, st));
-    AACONV_TRY(f32_attn_fwd(d, q, k, v, w.rw, w.rh, w.o_tmp, w.lse_tmp, st));
-    AACONV_TRY(f32_attn_weights(d, q, k, w.rw, w.rh, w.lse_tmp, weights, st));
-  }
+  // visualise path only: the bf16 kernels' own probabilities -- their bf16 operands, their lse (attn_aug_conv.py:87)
+  if (weights) AACONV_TRY(aug_weights(d, sa.qa, sa.ka, lse, weights, st));
   AACONV_TRY(f32_out_fwd(d, o, p->out_w, y, st));
   return 0;
 }

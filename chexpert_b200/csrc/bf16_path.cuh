@@ -11,13 +11,14 @@ struct AugLayout {
   int KP;   // padded row length (multiple of 64)
   int NQ;   // roundup16(KD): width of the dQa accumulator
 };
-constexpr float AUG_BIG = 64.f;   // log2-units shift of in-range logits in forward (out-of-range keys -> 2^-64)
 
 AugLayout aug_layout(const Dims& d);
 int aug_supported(const Dims& d);
 // aug_ops.cu
 int aug_build_fwd(const Dims& d, const float* q, const float* k, const float* v, const float* krw, const float* krh,
                   void* qa, void* ka, cudaStream_t st);
+// (B,nh,L,L) softmax map from the bf16 operands and the bf16 forward kernel's lse (visualise path)
+int aug_weights(const Dims& d, const void* qa, const void* ka, const float* lse, float* weights, cudaStream_t st);
 int aug_patch_bwd(const Dims& d, const float* lse, const float* d_o, const float* o, void* qa, float* delta, cudaStream_t st);
 // out_proj adjoint (dO, dWout) + the patch above in one pass (nh = 8, dv/nh <= 2); partial: out_bwd_patch_partial_floats
 int out_bwd_patch_supported(const Dims& d);

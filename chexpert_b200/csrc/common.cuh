@@ -26,6 +26,10 @@ int fail(int code, const char* fmt, ...);
 // Called right after every kernel launch of this library: error check + launch accounting (+ optional
 // per-launch CUDA-event profile, see aaconv_profile_begin/end).
 void note_launch(const char* name, cudaStream_t st);
+// Wraps the stream argument of every <<<...>>> launch: when the per-launch profile is on it records the launch's START event
+// (so host-side gaps between launches are not charged to the next kernel); returns `st` unchanged.
+cudaStream_t pre_launch(cudaStream_t st);
+#define AACONV_ST(stream__) ::aaconv::pre_launch(stream__)
 #define AACONV_LAUNCH_OK_ON(name, stream__)                                                        \
   do {                                                                                             \
     cudaError_t e__ = cudaGetLastError();                                                          \

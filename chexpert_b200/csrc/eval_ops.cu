@@ -58,7 +58,7 @@ __global__ void auroc_final_kernel(const unsigned long long* __restrict__ counte
 
 int ensemble_mean_launch(const float* logits, int M, size_t n, float* mean, cudaStream_t st) {
   const int blocks = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
-  ensemble_mean_kernel<<<blocks, 256, 0, st>>>(logits, M, n, mean);
+  ensemble_mean_kernel<<<blocks, 256, 0, AACONV_ST(st)>>>(logits, M, n, mean);
   AACONV_LAUNCH_OK("ensemble_mean");
   return 0;
 }
@@ -67,9 +67,9 @@ int auroc_launch(const float* z, const float* t, int N, int C, float* auroc, voi
   unsigned long long* counters = static_cast<unsigned long long*>(workspace);
   AACONV_CUDA_OK(cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * 3 * C, st));
   const int slices = (N + 255) / 256 < 64 ? (N + 255) / 256 : 64;
-  auroc_count_kernel<<<dim3(C, slices), 256, 0, st>>>(z, t, N, C, counters);
+  auroc_count_kernel<<<dim3(C, slices), 256, 0, AACONV_ST(st)>>>(z, t, N, C, counters);
   AACONV_LAUNCH_OK("auroc_count");
-  auroc_final_kernel<<<1, ((C + 31) / 32) * 32, 0, st>>>(counters, C, auroc);
+  auroc_final_kernel<<<1, ((C + 31) / 32) * 32, 0, AACONV_ST(st)>>>(counters, C, auroc);
   AACONV_LAUNCH_OK("auroc_final");
   return 0;
 }

@@ -57,7 +57,7 @@ int f32_rel_fwd(const Dims& d, const float* q, const float* krw, const float* kr
     if (smem > 200 * 1024) return fail(AACONV_E_UNSUPPORTED, "key_rel table too large for shared memory");
     AACONV_CUDA_OK(cudaFuncSetAttribute(f32_rel_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)std::min<size_t>((rows * R + 255) / 256, 148 * 16);
-    f32_rel_fwd_kernel<<<grid, 256, smem, st>>>(q, axis ? krh : krw, axis ? rh : rw, rows, d.dkh, R);
+    f32_rel_fwd_kernel<<<grid, 256, smem, AACONV_ST(st)>>>(q, axis ? krh : krw, axis ? rh : rw, rows, d.dkh, R);
     AACONV_LAUNCH_OK("rel_fwd_f32");
   }
   return 0;
@@ -289,7 +289,7 @@ __global__ void f32_delta_kernel(const float* __restrict__ d_o, const float* __r
 
 int f32_delta(const Dims& d, const float* d_o, const float* o, float* delta, cudaStream_t st) {
   const size_t rows = (size_t)d.BN * d.L;
-  f32_delta_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(d_o, o, delta, rows, d.dvh);
+  f32_delta_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, AACONV_ST(st)>>>(d_o, o, delta, rows, d.dvh);
   AACONV_LAUNCH_OK("delta_f32");
   return 0;
 }
@@ -323,7 +323,7 @@ int f32_rel_bwd_dq(const Dims& d, const float* krw, const float* krh, const floa
   if (smem > 200 * 1024) return fail(AACONV_E_UNSUPPORTED, "key_rel tables too large for shared memory");
   AACONV_CUDA_OK(cudaFuncSetAttribute(f32_rel_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<size_t>((rows * d.dkh + 255) / 256, 148 * 16);
-  f32_rel_bwd_dq_kernel<<<grid, 256, smem, st>>>(krw, krh, drw, drh, dq, rows, d.dkh, d.RW, d.RH);
+  f32_rel_bwd_dq_kernel<<<grid, 256, smem, AACONV_ST(st)>>>(krw, krh, drw, drh, dq, rows, d.dkh, d.RW, d.RH);
   AACONV_LAUNCH_OK("rel_bwd_dq_f32");
   return 0;
 }
@@ -359,7 +359,7 @@ int f32_attn_fwd(const Dims& d, const float* q, const float* k, const float* v, 
     const size_t smem = sizeof(float) * ((size_t)KT * (DK + DV) + (d.relative ? (size_t)d.RW * TQ : 0));
     auto kern = f32_attn_fwd_kernel<DK, DV, false>;
     AACONV_TRY(set_smem(kern, smem));
-    kern<<<grid, TQ, smem, st>>>(q, k, v, rw, rh, o, lse, nullptr, d.L, d.H, d.W, d.dkh, d.dvh, d.relative);
+    kern<<<grid, TQ, smem, AACONV_ST(st)>>>(q, k, v, rw, rh, o, lse, nullptr, d.L, d.H, d.W, d.dkh, d.dvh, d.relative);
   });
   AACONV_LAUNCH_OK("attn_fwd_f32");
   return 0;
@@ -372,7 +372,7 @@ int f32_attn_weights(const Dims& d, const float* q, const float* k, const float*
     const size_t smem = sizeof(float) * ((size_t)KT * (DK + DV) + (d.relative ? (size_t)d.RW * TQ : 0));
     auto kern = f32_attn_fwd_kernel<DK, DV, true>;
     AACONV_TRY(set_smem(kern, smem));
-    kern<<<grid, TQ, smem, st>>>(q, k, nullptr, rw, rh, nullptr, const_cast<float*>(lse), weights, d.L, d.H, d.W,
+    kern<<<grid, TQ, smem, AACONV_ST(st)>>>(q, k, nullptr, rw, rh, nullptr, const_cast<float*>(lse), weights, d.L, d.H, d.W,
                                  d.dkh, d.dvh, d.relative);
   });
   AACONV_LAUNCH_OK("attn_weights_f32");
@@ -387,7 +387,7 @@ int f32_attn_bwd(const Dims& d, const float* q, const float* k, const float* v, 
     const size_t smem = sizeof(float) * ((size_t)KT * (DK + DV) + (d.relative ? 2 * (size_t)d.RW * TQ : 0));
     auto kern = f32_attn_bwd_dq_kernel<DK, DV>;
     AACONV_TRY(set_smem(kern, smem));
-    kern<<<grid, TQ, smem, st>>>(q, k, v, rw, rh, lse, d_o, delta, dq, drw, drh, d.L, d.H, d.W, d.dkh, d.dvh,
+    kern<<<grid, TQ, smem, AACONV_ST(st)>>>(q, k, v, rw, rh, lse, d_o, delta, dq, drw, drh, d.L, d.H, d.W, d.dkh, d.dvh,
                                  d.relative);
   });
   AACONV_LAUNCH_OK("attn_bwd_dq_f32");
@@ -395,7 +395,7 @@ int f32_attn_bwd(const Dims& d, const float* q, const float* k, const float* v, 
     const size_t smem = sizeof(float) * ((size_t)QT * (DK + DV + 2) + (d.relative ? (size_t)QT * (d.RW + d.RH) : 0));
     auto kern = f32_attn_bwd_dkv_kernel<DK, DV>;
     AACONV_TRY(set_smem(kern, smem));
-    kern<<<grid, TQ, smem, st>>>(q, k, v, rw, rh, lse, d_o, delta, dk, dv, d.L, d.H, d.W, d.dkh, d.dvh, d.relative);
+    kern<<<grid, TQ, smem, AACONV_ST(st)>>>(q, k, v, rw, rh, lse, d_o, delta, dk, dv, d.L, d.H, d.W, d.dkh, d.dvh, d.relative);
   });
   AACONV_LAUNCH_OK("attn_bwd_dkv_f32");
   return 0;

@@ -16,7 +16,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* _
 }
 
 static int splitk_reduce(const float* partial, float* out, int count, int splits, cudaStream_t st) {
-  splitk_reduce_kernel<<<cdiv(count, 256), 256, 0, st>>>(partial, out, count, splits, 0);
+  splitk_reduce_kernel<<<cdiv(count, 256), 256, 0, AACONV_ST(st)>>>(partial, out, count, splits, 0);
   AACONV_LAUNCH_OK("splitk_reduce");
   return 0;
 }

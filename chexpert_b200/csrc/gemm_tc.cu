@@ -332,12 +332,12 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_v4_kernel(const float* 
 int pack_nhwc_bf16(const float* in, void* out, int B, int C, int Cp, int HW, cudaStream_t st) {
   if (HW % 4 == 0 && Cp % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
     dim3 grid(cdiv(HW, 64), cdiv(Cp, 64), B);
-    nchw_to_nhwc_bf16_v4_kernel<<<grid, 256, 0, st>>>(in, static_cast<bf16*>(out), C, Cp, HW);
+    nchw_to_nhwc_bf16_v4_kernel<<<grid, 256, 0, AACONV_ST(st)>>>(in, static_cast<bf16*>(out), C, Cp, HW);
     AACONV_LAUNCH_OK("pack_nhwc_bf16");
     return 0;
   }
   dim3 grid(cdiv(HW, 32), cdiv(Cp, 32), B), block(32, 8);
-  nchw_to_nhwc_bf16_kernel<<<grid, block, 0, st>>>(in, static_cast<bf16*>(out), C, Cp, HW);
+  nchw_to_nhwc_bf16_kernel<<<grid, block, 0, AACONV_ST(st)>>>(in, static_cast<bf16*>(out), C, Cp, HW);
   AACONV_LAUNCH_OK("pack_nhwc_bf16");
   return 0;
 }
@@ -455,7 +455,7 @@ struct PGQueue {
       const int n = (int)std::min<size_t>(PG_MAX_JOBS, jobs.size() - i);
       int ncta = 0;
       for (int k = 0; k < n; ++k) { j.job[k] = jobs[i + k]; ncta = std::max(ncta, j.job[k].ncta); }
-      pixel_gemm_tc_kernel<<<dim3(ncta, n), PG_THREADS, smem, st>>>(j);
+      pixel_gemm_tc_kernel<<<dim3(ncta, n), PG_THREADS, smem, AACONV_ST(st)>>>(j);
       AACONV_LAUNCH_OK(name);
     }
     jobs.clear();
@@ -488,7 +488,7 @@ int tc_fprop(const Dims& d, const TcGemmBufs& t, const float* x, const float* co
              float* q, float* k, float* v, cudaStream_t st) {
   const int T = d.ks * d.ks, s = d.stride;
   AACONV_TRY(pack_nhwc_bf16(x, t.xh, d.B, d.Cin, t.CinK, d.Hin * d.Win, st));
-  pack_wf_kernel<<<dim3(cdiv(t.CinK, 256), t.NPc + t.NPq), 256, 0, st>>>(conv_w, qkv_w, static_cast<bf16*>(t.wf), d.Cc, d.Cin,
+  pack_wf_kernel<<<dim3(cdiv(t.CinK, 256), t.NPc + t.NPq), 256, 0, AACONV_ST(st)>>>(conv_w, qkv_w, static_cast<bf16*>(t.wf), d.Cc, d.Cin,
                                                                           t.CinK, T, t.NPc, d.Nqkv, t.NPq);
   AACONV_LAUNCH_OK("pack_wf");
 
@@ -548,7 +548,7 @@ int tc_pack_grads(const Dims& d, const TcGemmBufs& t, const float* dy, const flo
                   cudaStream_t st) {
   AACONV_TRY(pack_nhwc_bf16(dy, t.dyh, d.B, d.Cout, t.KPc, d.L, st));
   if (!dq) return 0;
-  pack_dqkv_kernel<<<148 * 8, 256, 0, st>>>(dq, dk, dv, static_cast<bf16*>(t.dqkvh), (size_t)d.B * d.L, d.L, d.nh, d.dk,
+  pack_dqkv_kernel<<<148 * 8, 256, 0, AACONV_ST(st)>>>(dq, dk, dv, static_cast<bf16*>(t.dqkvh), (size_t)d.B * d.L, d.L, d.nh, d.dk,
                                              d.dkh, d.dvh, d.Nqkv, t.KPq, d.qscale);
   AACONV_LAUNCH_OK("pack_dqkv");
   return 0;
@@ -557,7 +557,7 @@ int tc_pack_grads(const Dims& d, const TcGemmBufs& t, const float* dy, const flo
 // dx = conv dgrad + qkv dgrad (needs tc_pack_grads first).
 int tc_dgrad(const Dims& d, const TcGemmBufs& t, const float* conv_w, const float* qkv_w, float* dx, cudaStream_t st) {
   const int T = d.ks * d.ks, s = d.stride;
-  pack_wd_kernel<<<dim3(cdiv(t.KPc, 128) + cdiv(t.KPq, 128), t.CinP), 128, 0, st>>>(
+  pack_wd_kernel<<<dim3(cdiv(t.KPc, 128) + cdiv(t.KPq, 128), t.CinP), 128, 0, AACONV_ST(st)>>>(
       conv_w, qkv_w, static_cast<bf16*>(t.wd), static_cast<bf16*>(t.wq), d.Cc, d.Cin, T, t.CinP, t.KPc, d.Nqkv, t.KPq, cdiv(t.KPc, 128));
   AACONV_LAUNCH_OK("pack_wd");
   // taps of the conv (and the 1x1 projection) that reach input-pixel class (rh, rw)
@@ -641,7 +641,7 @@ __global__ void zero_class_kernel(float* __restrict__ dx, size_t planes, int Hin
 }
 
 int tc_zero_class(const Dims& d, float* dx, int rh, int rw, cudaStream_t st) {
-  zero_class_kernel<<<148 * 4, 256, 0, st>>>(dx, (size_t)d.B * d.Cin, d.Hin, d.Win, d.stride, rh, rw);
+  zero_class_kernel<<<148 * 4, 256, 0, AACONV_ST(st)>>>(dx, (size_t)d.B * d.Cin, d.Hin, d.Win, d.stride, rh, rw);
   AACONV_LAUNCH_OK("zero_class");
   return 0;
 }
@@ -860,9 +860,9 @@ int tc_wgrad(const Dims& d, const TcGemmBufs& t, float* dwc, float* dwq, float* 
   p.partial = partial;
   const size_t smem = sizeof(WGSmem) + 1024;
   AACONV_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  wgrad_tc_kernel<<<dim3(nt, splits), WG_THREADS, smem, st>>>(p);
+  wgrad_tc_kernel<<<dim3(nt, splits), WG_THREADS, smem, AACONV_ST(st)>>>(p);
   AACONV_LAUNCH_OK("conv_qkv_wgrad_tc");
-  wgrad_reduce_kernel<<<dim3(std::max(16, std::min(128, 2368 / nt)), nt), 256, 0, st>>>(partial, p.shape, splits, dwc, dwq, d.Cc, d.Cin, d.Nqkv);
+  wgrad_reduce_kernel<<<dim3(std::max(16, std::min(128, 2368 / nt)), nt), 256, 0, AACONV_ST(st)>>>(partial, p.shape, splits, dwc, dwq, d.Cc, d.Cin, d.Nqkv);
   AACONV_LAUNCH_OK("wgrad_reduce");
   return 0;
 }

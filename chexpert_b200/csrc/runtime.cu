@@ -25,27 +25,33 @@ int fail(int code, const char* fmt, ...) {
 namespace {
 std::atomic<long long> g_launches{0};
 std::mutex g_prof_mu;
-bool g_prof_on = false;
-struct Mark { const char* name; cudaEvent_t ev; };
+std::atomic<bool> g_prof_on{false};
+struct Mark { const char* name; cudaEvent_t start, stop; };
 std::vector<Mark> g_marks;
-cudaEvent_t g_prof_start = nullptr;
-cudaStream_t g_prof_stream = nullptr;
+thread_local cudaEvent_t t_pending_start = nullptr;   // start event of the launch being issued by this thread
 }  // namespace
+
+cudaStream_t pre_launch(cudaStream_t st) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return st;
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return st;
+  cudaEventRecord(ev, st);
+  if (t_pending_start) cudaEventDestroy(t_pending_start);
+  t_pending_start = ev;
+  return st;
+}
 
 void note_launch(const char* name, cudaStream_t st) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  if (!g_prof_on) return;
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  cudaEvent_t start = t_pending_start;
+  t_pending_start = nullptr;
+  if (!start) return;                          // launch was issued before the profile began
+  cudaEvent_t stop;
+  if (cudaEventCreate(&stop) != cudaSuccess) { cudaEventDestroy(start); return; }
+  cudaEventRecord(stop, st);
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  if (!g_prof_on) return;
-  cudaEvent_t ev;
-  if (cudaEventCreate(&ev) != cudaSuccess) return;
-  if (g_marks.empty()) {                       // the first launch after begin(): its start mark
-    // start event was recorded at begin() on the default-captured stream; if the stream differs we
-    // cannot order against it, so re-record here (the first kernel's own time is then not measured).
-    if (st != g_prof_stream) { cudaEventRecord(g_prof_start, st); g_prof_stream = st; }
-  }
-  cudaEventRecord(ev, st);
-  g_marks.push_back({name, ev});
+  g_marks.push_back({name, start, stop});
 }
 
 }  // namespace aaconv
@@ -56,33 +62,30 @@ extern "C" {
 
 long long aaconv_launch_count(void) { return g_launches.load(); }
 
-// Start recording one CUDA event after every kernel launch this library makes (any thread) on `stream`.
+// Start recording a (start, stop) CUDA event pair around every kernel launch this library makes (any thread, any stream).
 int aaconv_profile_begin(void* stream) {
+  (void)stream;
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  for (auto& m : g_marks) cudaEventDestroy(m.ev);
+  for (auto& m : g_marks) { cudaEventDestroy(m.start); cudaEventDestroy(m.stop); }
   g_marks.clear();
-  if (!g_prof_start) AACONV_CUDA_OK(cudaEventCreate(&g_prof_start));
-  g_prof_stream = static_cast<cudaStream_t>(stream);
-  AACONV_CUDA_OK(cudaEventRecord(g_prof_start, g_prof_stream));
   g_prof_on = true;
   return 0;
 }
 
-// Stop recording; synchronises, then writes up to `max_entries` (name, ms) pairs: names '\n'-joined into
-// names_buf.  Each ms is the time between the previous mark and this launch's mark on the stream, i.e.
-// the kernel's duration when launches are back to back.  Returns the number of entries (or < 0).
+// Stop recording; synchronises, then writes up to `max_entries` (name, ms) pairs: names '\n'-joined into names_buf.
+// Each ms is the device time between the launch's own start and stop events (host gaps between launches are excluded).
+// Returns the number of entries (or < 0).
 int aaconv_profile_end(char* names_buf, size_t names_len, float* ms, int max_entries) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof_on = false;
   int n = 0;
   size_t off = 0;
   if (names_buf && names_len) names_buf[0] = 0;
-  cudaEvent_t prev = g_prof_start;
   for (auto& m : g_marks) {
-    if (cudaEventSynchronize(m.ev) != cudaSuccess) return fail(AACONV_E_CUDA, "profile: event sync failed");
+    if (cudaEventSynchronize(m.stop) != cudaSuccess) return fail(AACONV_E_CUDA, "profile: event sync failed");
     if (n < max_entries) {
       float t = 0.f;
-      cudaEventElapsedTime(&t, prev, m.ev);
+      cudaEventElapsedTime(&t, m.start, m.stop);
       ms[n] = t;
       const size_t len = strlen(m.name);
       if (names_buf && off + len + 2 < names_len) {
@@ -93,9 +96,8 @@ int aaconv_profile_end(char* names_buf, size_t names_len, float* ms, int max_ent
       }
       ++n;
     }
-    prev = m.ev;
   }
-  for (auto& m : g_marks) cudaEventDestroy(m.ev);
+  for (auto& m : g_marks) { cudaEventDestroy(m.start); cudaEventDestroy(m.stop); }
   g_marks.clear();
   return n;
 }

@@ -113,7 +113,7 @@ template <class P>
 int launch_simt_gemm(const P& p, int splits, cudaStream_t st, const char* name) {
   if (p.M <= 0 || p.N <= 0) return 0;
   dim3 grid(cdiv(p.M, SG_BM), cdiv(p.N, SG_BN), splits);
-  simt_gemm_kernel<P><<<grid, SG_THREADS, 0, st>>>(p);
+  simt_gemm_kernel<P><<<grid, SG_THREADS, 0, AACONV_ST(st)>>>(p);
   AACONV_LAUNCH_OK(name);
   return 0;
 }

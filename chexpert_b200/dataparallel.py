@@ -43,6 +43,9 @@ class GradientBuckets:
             self._seal(cur)
         self._pending = [0] * len(self.buckets)
         self._works = []
+        self._next = 0            # buckets [0, _next) have had their all-reduce issued this step
+        self._state = 'finished'  # 'armed' between reset() and finish()
+        self._sync = True
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
         self.reset()
 
@@ -59,11 +62,27 @@ class GradientBuckets:
         self.buckets.append((flat, params))
 
     def reset(self):
-        """Zero the buckets (replaces optimizer.zero_grad(); keeps the grad views alive)."""
+        """Zero the buckets (replaces optimizer.zero_grad(); keeps the grad views alive) and arm the step."""
         for flat, _ in self.buckets:
             flat.zero_()
         self._pending = [len(ps) for _, ps in self.buckets]
         self._works = []
+        self._next = 0
+        self._state = 'armed'
+
+    def no_sync(self):
+        """Context manager for gradient accumulation: backward passes inside it only accumulate locally into the buckets;
+        the exchange happens in the first backward outside it (then finish()).  reset() once per accumulation window."""
+        return _NoSync(self)
+
+    def _issue_ready(self, upto=None):
+        # collectives are ALWAYS issued in bucket order 0, 1, 2, ... on every rank, whatever order the hooks fired in (a rank on
+        # which some parameter got no gradient must not reorder its all-reduces relative to the other ranks)
+        n = len(self.buckets) if upto is None else upto
+        while self._next < n and (upto is not None or self._pending[self._next] == 0):
+            if self.world > 1:
+                self._works.append(dist.all_reduce(self.buckets[self._next][0], group=self.group, async_op=True))
+            self._next += 1
 
     def _on_grad(self, p):
         b = self._bucket_of[p]
@@ -71,21 +90,29 @@ class GradientBuckets:
         if p.grad.data_ptr() != view.data_ptr():     # someone replaced .grad (e.g. set_to_none): copy back in
             view.copy_(p.grad)
             p.grad = view
+        if not self._sync:
+            return
+        if self._state != 'armed':
+            raise RuntimeError('GradientBuckets: backward() after finish() without reset() -- the buckets hold reduced gradients; '
+                               'call reset() at the start of every step (use no_sync() for gradient accumulation)')
         self._pending[b] -= 1
-        if self._pending[b] == 0 and self.world > 1:
-            self._works.append(dist.all_reduce(self.buckets[b][0], group=self.group, async_op=True))
+        if self._pending[b] < 0:
+            raise RuntimeError('GradientBuckets: a parameter received a second gradient before finish(): its bucket has already '
+                               'been exchanged.  Wrap all but the last backward() of an accumulation window in no_sync().')
+        self._issue_ready()
 
     def finish(self):
-        """Wait for the exchange and turn sums into means.  Call after backward(), before optimizer.step()."""
+        """Wait for the exchange and turn sums into means.  Call once after backward(), before optimizer.step()."""
+        if self._state != 'armed':
+            raise RuntimeError('GradientBuckets: finish() called twice (or before reset())')
+        self._issue_ready(upto=len(self.buckets))     # buckets with parameters that received no gradient this step, in order
         if self.world > 1:
-            for b, n in enumerate(self._pending):     # parameters that received no gradient this step
-                if n > 0:
-                    self._works.append(dist.all_reduce(self.buckets[b][0], group=self.group, async_op=True))
             for w in self._works:
                 w.wait()
             for flat, _ in self.buckets:
                 flat.div_(self.world)
         self._works = []
+        self._state = 'finished'
 
     @property
     def nbytes(self):
@@ -94,3 +121,16 @@ class GradientBuckets:
     def remove(self):
         for h in self._hooks:
             h.remove()
+
+
+class _NoSync:
+    def __init__(self, gb):
+        self.gb = gb
+
+    def __enter__(self):
+        self.gb._sync = False
+        return self.gb
+
+    def __exit__(self, *exc):
+        self.gb._sync = True
+        return False

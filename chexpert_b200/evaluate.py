@@ -107,16 +107,19 @@ def auroc_per_class(logits, targets):
 @torch.no_grad()
 def evaluate_ensemble(model, state_dicts, images_u8, targets, batch_size=16, device='cuda'):
     """The reference's ensemble evaluation (chexpert.py:217-236): every checkpoint's state_dict is loaded strictly into
-    `model`, its logits over the whole set are kept, the ensemble output is their mean; metrics as compute_metrics
-    (chexpert.py:130-146) minus the plotting inputs.  -> dict(outputs, per_model, auroc, loss)."""
-    per_model = []
+    `model`, its logits and element losses over the whole set are kept, the ensemble output / loss are their means over the
+    checkpoints (chexpert.py:233-234; note mean-of-losses, not loss-of-mean); metrics as compute_metrics (chexpert.py:130-146)
+    minus the plotting inputs.  -> dict(outputs, per_model, auroc, loss)."""
+    t = targets.to(device)
+    loss_fn = BCEWithLogitsLoss('none').to(device)
+    per_model, losses = [], []
     for sd in state_dicts:
         model.load_state_dict(sd, strict=True)
         per_model.append(predict_logits(model, images_u8, batch_size, device))
+        losses.append(loss_fn(per_model[-1], t))       # element losses of THIS checkpoint (chexpert.py:205,229-231)
     stacked = torch.stack(per_model, 0)
-    outputs = ensemble_mean(stacked)
-    t = targets.to(device)
-    el = BCEWithLogitsLoss('none').to(device)(outputs, t)
+    outputs = ensemble_mean(stacked)                    # chexpert.py:233
+    el = ensemble_mean(torch.stack(losses, 0))          # chexpert.py:234: mean over checkpoints of the element losses
     return {'outputs': outputs, 'per_model': stacked, 'auroc': auroc_per_class(outputs, t), 'loss': el.mean(0)}
 
 

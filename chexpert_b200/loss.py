@@ -77,6 +77,13 @@ class BCEWithLogitsLoss(nn.Module):
         self.register_buffer('cols', torch.tensor(COMPETITION_INDEX, dtype=torch.int32), persistent=False)
 
     def forward(self, z, targets):
+        if self.raw_labels:
+            # the kernel reads targets[b, cols[c]] for c < C: check the shapes on the host (cols lives on the device)
+            if z.dim() != 2 or z.shape[1] != len(COMPETITION_INDEX):
+                raise RuntimeError(f'raw_labels=True needs (B, {len(COMPETITION_INDEX)}) logits (dataset.py:25), got {tuple(z.shape)}')
+            if targets.dim() != 2 or targets.shape[0] != z.shape[0] or targets.shape[1] <= max(COMPETITION_INDEX):
+                raise RuntimeError(f'raw_labels=True needs (B, >= {max(COMPETITION_INDEX) + 1}) label rows (dataset.py:20-23), '
+                                   f'got {tuple(targets.shape)}')
         cols = self.cols.to(z.device) if self.raw_labels else None
         fn = _BCETrainLoss if self.reduction == 'train' else _BCEElementLoss
         return fn.apply(z, targets, cols)

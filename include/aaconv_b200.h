@@ -118,8 +118,8 @@ int aaconv_auroc(const float* logits, const float* targets, int N, int C, float*
 
 /* Accounting / measurement helpers used by bench.py (no reference counterpart).
  *   aaconv_launch_count   kernels launched by this library since it was loaded (all threads).
- *   aaconv_profile_begin  start recording a CUDA event after every launch made on `stream`.
- *   aaconv_profile_end    stop; fills ms[i] = device time of launch i (gap to the previous mark) and the
+ *   aaconv_profile_begin  start recording a (start, stop) CUDA-event pair around every launch (`stream` is unused, kept for ABI).
+ *   aaconv_profile_end    stop; fills ms[i] = device time of launch i (its own start -> stop event) and the
  *                         '\n'-joined kernel names; returns the number of entries written (<= max_entries). */
 long long aaconv_launch_count(void);
 /* Debug hooks of the attention kernels (tools/attn_timeline.py, tools/attn_ablate.py); both default to off.

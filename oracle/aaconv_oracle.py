@@ -20,6 +20,7 @@ What each function follows (paths relative to /root/reference):
 * ``aaconv_forward_sequential``   models/attn_aug_conv.py:65-97 (same op order; used as the CPU timing port)
 * ``aaconv_forward_closed``       closed form of models/attn_aug_conv.py:75-86
 * ``aaconv_backward_closed``      hand-derived adjoint of :65-97 (the reference relies on autograd)
+* ``aaconv_backward_closed_by_head`` the same, one head at a time (bounded memory for L = 4096, BASELINE config 4)
 * ``bce_with_logits``             chexpert.py:530,160 (train) and :205,144 (eval)
 * ``uones_targets``               dataset.py:20-25,139,142
 * ``ensemble_mean`` / ``auroc``   chexpert.py:233 and :130-135
@@ -253,6 +254,67 @@ def aaconv_backward_closed(x, p, s: AAConvShape, dy):
                                              padding=s.pad, dilation=s.dilation)
     g['x'] = dx
     return y, g
+
+
+def aaconv_backward_closed_by_head(x, p, s: AAConvShape, dy, return_weights_head=None):
+    """Same adjoint as ``aaconv_backward_closed`` evaluated one head at a time, so that only one (B, L, L) block of
+    logits / probabilities / dS is alive at once: the L = 4096 case (512-px Transition 1, BASELINE config 4) then needs
+    ~1 GB per block in fp64 instead of 8 x that.  Returns (y, grads[, P of head `return_weights_head`])."""
+    xs, q, k, v, H, W = _project_qkv(x, p, s)
+    B, L = x.shape[0], H * W
+    nconv = s.out_channels - s.dv if 'conv.weight' in p else 0
+    Wo = p['out_proj.weight'][:, :, 0, 0]
+    dya = dy[:, nconv:]
+    dO_all = torch.einsum('oc,bohw->bchw', Wo, dya).reshape(B, s.nh, s.dvh, L)
+    O = torch.zeros(B, s.nh, s.dvh, L, dtype=x.dtype)
+    dq, dk, dV = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
+    g = {}
+    if s.relative:
+        g['key_rel_w'] = torch.zeros_like(p['key_rel_w'])
+        g['key_rel_h'] = torch.zeros_like(p['key_rel_h'])
+        ix, iy = _rel_index(W, x.device), _rel_index(H, x.device)
+    keep = None
+    one = AAConvShape(s.in_channels, s.out_channels, s.kernel_size, s.stride, s.dkh, s.dvh, 1, s.relative, s.input_dims,
+                      s.padding, s.dilation)
+    for n in range(s.nh):
+        qn, kn, vn, dOn = q[:, n:n + 1], k[:, n:n + 1], v[:, n:n + 1], dO_all[:, n:n + 1]
+        P = torch.softmax(closed_logits(qn, kn, p, one, H, W), dim=-1)
+        if return_weights_head == n:
+            keep = P[:, 0].clone()
+        O[:, n:n + 1] = torch.einsum('bnqk,bndk->bndq', P, vn)
+        dV[:, n:n + 1] = torch.einsum('bnqk,bndq->bndk', P, dOn)
+        dP = torch.einsum('bndq,bndk->bnqk', dOn, vn)
+        dS = P * (dP - (dP * P).sum(-1, keepdim=True))
+        del dP
+        dqn = torch.einsum('bnqk,bndk->bndq', dS, kn)
+        dk[:, n:n + 1] = torch.einsum('bnqk,bndq->bndk', dS, qn)
+        if s.relative:
+            dS6 = dS.reshape(B, 1, H, W, H, W)
+            dAw, dAh = dS6.sum(4), dS6.sum(5)
+            dRw = torch.zeros(B, 1, H, W, 2 * W - 1, dtype=x.dtype).scatter_add_(4, ix[None, None, None].expand(B, 1, H, W, W), dAw)
+            dRh = torch.zeros(B, 1, H, W, 2 * H - 1, dtype=x.dtype).scatter_add_(
+                4, iy[None, None, :, None, :].expand(B, 1, H, W, H), dAh)
+            dRw, dRh = dRw.reshape(B, 1, L, -1), dRh.reshape(B, 1, L, -1)
+            g['key_rel_w'] += torch.einsum('bndq,bnqr->dr', qn, dRw)
+            g['key_rel_h'] += torch.einsum('bndq,bnqr->dr', qn, dRh)
+            dqn = dqn + torch.einsum('dr,bnqr->bndq', p['key_rel_w'], dRw) + torch.einsum('dr,bnqr->bndq', p['key_rel_h'], dRh)
+        dq[:, n:n + 1] = dqn
+        del dS, P
+    a = torch.einsum('oc,bchw->bohw', Wo, O.reshape(B, s.dv, H, W))
+    g['out_proj.weight'] = torch.einsum('bohw,bchw->oc', dya, O.reshape(B, s.dv, H, W))[:, :, None, None]
+    dqkv = torch.cat([(dq * s.dkh ** -0.5).reshape(B, s.dk, H, W), dk.reshape(B, s.dk, H, W), dV.reshape(B, s.dv, H, W)], dim=1)
+    g['in_proj_qkv.weight'] = torch.einsum('bohw,bchw->oc', dqkv, xs)[:, :, None, None]
+    dx = torch.zeros_like(x)
+    dx[:, :, ::s.stride, ::s.stride] += torch.einsum('oc,bohw->bchw', p['in_proj_qkv.weight'][:, :, 0, 0], dqkv)
+    if nconv:
+        dyc = dy[:, :nconv]
+        c = F.conv2d(x, p['conv.weight'], stride=s.stride, padding=s.pad, dilation=s.dilation)
+        a = torch.cat([c, a], dim=1)
+        g['conv.weight'] = torch.nn.grad.conv2d_weight(x, p['conv.weight'].shape, dyc, stride=s.stride, padding=s.pad,
+                                                       dilation=s.dilation)
+        dx = dx + torch.nn.grad.conv2d_input(x.shape, p['conv.weight'], dyc, stride=s.stride, padding=s.pad, dilation=s.dilation)
+    g['x'] = dx
+    return (a, g, keep) if return_weights_head is not None else (a, g)
 
 
 def aaconv_autograd(x, p, s: AAConvShape, dy, fn=aaconv_forward_sequential):

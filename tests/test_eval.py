@@ -106,6 +106,10 @@ def test_ensemble_eval_fp32_matches_reference(gold, eval_set):
     assert err < 5e-4 * max(1.0, float(want.abs().max())) and err < 0.05 * spread, (err, spread)
     for i in range(n):
         np.testing.assert_allclose(E_auroc(got[i], eval_set[1]), gold['auroc_per_model'][i], rtol=0, atol=1e-3)
+    # 'loss' is the reference's: per-checkpoint element losses, mean over checkpoints, per-class mean (chexpert.py:229-234,144)
+    ref_loss = torch.nn.BCEWithLogitsLoss(reduction='none')
+    el = torch.stack([ref_loss(z, eval_set[1]) for z in want], 2).mean(2).mean(0)
+    np.testing.assert_allclose(res['loss'].cpu().numpy(), el.numpy(), rtol=2e-4, atol=2e-5)
 
 
 def E_auroc(z, t):
@@ -133,7 +137,10 @@ def test_ensemble_eval_bf16_auroc(gold, eval_set):
     dm = np.abs(np.stack([E_auroc(got[i], eval_set[1]) for i in range(n)]) - gold['auroc_per_model'])
     print('bf16 per-checkpoint AUROC |diff|: max', dm.max(), 'mean', dm.mean())
     assert dm.max() < 4e-3 and dm.mean() < 1e-3, dm
-    el = O.bce_with_logits(torch.from_numpy(gold['mean']), eval_set[1]).mean(0)
+    # chexpert.py:229-234,144: element losses per checkpoint, mean over checkpoints, then per-class mean -- the reference's own
+    # expression (nn.BCEWithLogitsLoss) on the reference's logits; NOT the loss of the mean logits
+    ref_loss = torch.nn.BCEWithLogitsLoss(reduction='none')
+    el = torch.stack([ref_loss(z, eval_set[1]) for z in want], 2).mean(2).mean(0)
     np.testing.assert_allclose(res['loss'].cpu().numpy(), el.numpy(), rtol=2e-2, atol=1e-2)
 
 

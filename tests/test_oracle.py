@@ -43,6 +43,18 @@ def test_backward_f64(name):
         assert rel_err(g_ad[n], g[n]) < 1e-11, n
 
 
+@pytest.mark.parametrize('name', golden_cases('f64'))
+def test_backward_by_head_f64(name):
+    """The bounded-memory (one head at a time) adjoint used for the L = 4096 GPU test is the same function."""
+    s, p, g, t = load_case(name, 'f64')
+    y, g_h, w0 = O.aaconv_backward_closed_by_head(t['x'], p, s, t['dy'], return_weights_head=s.nh - 1)
+    assert rel_err(y, t['y']) < 1e-12
+    assert rel_err(w0, t['weights'][:, s.nh - 1]) < 1e-12
+    assert set(g_h) == set(g)
+    for n in g:
+        assert rel_err(g_h[n], g[n]) < 1e-11, n
+
+
 @pytest.mark.parametrize('name', golden_cases('f32'))
 def test_forward_backward_f32(name):
     s, p, g, t = load_case(name, 'f32')
