@@ -19,6 +19,12 @@ class Dims(ctypes.Structure):
                  'relative')]
 
 
+class Io(ctypes.Structure):
+    """aaconv_io: element types of x / y, batch stride of y (feature-buffer destination), fused InstanceNorm + ReLU prologue."""
+    _fields_ = [('x_dtype', ctypes.c_int32), ('y_dtype', ctypes.c_int32), ('y_batch_stride', ctypes.c_int64),
+                ('fuse_in_relu', ctypes.c_int32), ('in_eps', ctypes.c_float)]
+
+
 class Params(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ('conv_w', 'qkv_w', 'out_w', 'key_rel_h', 'key_rel_w')]
 
@@ -30,12 +36,18 @@ class ParamGrads(ctypes.Structure):
 # every symbol the header declares: name -> (restype, argtypes)
 _P = ctypes.c_void_p
 _DP = ctypes.POINTER(Dims)
+_IOP = ctypes.POINTER(Io)
 SYMBOLS = {
     'aaconv_abi_version': (ctypes.c_int, []),
     'aaconv_last_error': (ctypes.c_char_p, []),
     'aaconv_validate': (ctypes.c_int, [_DP, ctypes.c_int]),
     'aaconv_saved_bytes': (ctypes.c_size_t, [_DP, ctypes.c_int]),
     'aaconv_scratch_bytes': (ctypes.c_size_t, [_DP, ctypes.c_int, ctypes.c_int]),
+    'aaconv_saved_bytes_io': (ctypes.c_size_t, [_DP, ctypes.c_int, _IOP]),
+    'aaconv_scratch_bytes_io': (ctypes.c_size_t, [_DP, ctypes.c_int, _IOP]),
+    'aaconv_forward_io': (ctypes.c_int, [_DP, ctypes.c_int, _IOP, _P, ctypes.POINTER(Params), _P, _P, _P, _P, _P]),
+    'aaconv_backward_io': (ctypes.c_int, [_DP, ctypes.c_int, _IOP, _P, ctypes.POINTER(Params), _P, _P, _P, _P,
+                                          ctypes.POINTER(ParamGrads), _P]),
     'aaconv_saved_offset': (ctypes.c_int64, [_DP, ctypes.c_int, ctypes.c_char_p]),
     'aaconv_forward': (ctypes.c_int, [_DP, ctypes.c_int, _P, ctypes.POINTER(Params), _P, _P, _P, _P, _P]),
     'aaconv_backward': (ctypes.c_int, [_DP, ctypes.c_int, _P, ctypes.POINTER(Params), _P, _P, _P, _P,
@@ -73,7 +85,7 @@ def load():
                 fn = getattr(lib, name)
                 fn.restype = res
                 fn.argtypes = args
-            if lib.aaconv_abi_version() != 1:
+            if lib.aaconv_abi_version() != 2:
                 raise RuntimeError('libaaconv_b200.so ABI version mismatch')
             _lib = lib
     return _lib

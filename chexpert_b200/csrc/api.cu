@@ -33,6 +33,15 @@ static int validate(const aaconv_dims* dd, int precision) {
   if (precision == AACONV_BF16) AACONV_TRY(aug_supported(Dims(d)));
   return 0;
 }
+static int validate_io(const aaconv_dims* d, const aaconv_io* io) {
+  if (!io) return 0;
+  if ((io->x_dtype != AACONV_FP32 && io->x_dtype != AACONV_BF16) || (io->y_dtype != AACONV_FP32 && io->y_dtype != AACONV_BF16))
+    return fail(AACONV_E_ARG, "aaconv_io: element types must be AACONV_FP32 or AACONV_BF16");
+  if (io->y_batch_stride != 0 && io->y_batch_stride < (int64_t)d->Cout * d->H * d->W)
+    return fail(AACONV_E_ARG, "aaconv_io: y_batch_stride %lld is smaller than one sample of y (%lld)", (long long)io->y_batch_stride,
+                (long long)d->Cout * d->H * d->W);
+  return 0;
+}
 }  // namespace aaconv
 
 using namespace aaconv;
@@ -43,37 +52,49 @@ int aaconv_abi_version(void) { return AACONV_ABI_VERSION; }
 const char* aaconv_last_error(void) { return last_error_ref().c_str(); }
 int aaconv_validate(const aaconv_dims* d, int precision) { return validate(d, precision); }
 
-size_t aaconv_saved_bytes(const aaconv_dims* d, int precision) {
-  if (validate(d, precision)) return 0;
-  return precision == AACONV_FP32 ? f32_saved_bytes(Dims(*d)) : bf16_saved_bytes(Dims(*d));
+size_t aaconv_saved_bytes_io(const aaconv_dims* d, int precision, const aaconv_io* io) {
+  if (validate(d, precision) || validate_io(d, io)) return 0;
+  return precision == AACONV_FP32 ? f32_saved_bytes_io(Dims(*d, io)) : bf16_saved_bytes(Dims(*d, io));
 }
-size_t aaconv_scratch_bytes(const aaconv_dims* d, int precision, int want_weights) {
-  if (validate(d, precision)) return 0;
-  return precision == AACONV_FP32 ? f32_scratch_bytes(Dims(*d)) : bf16_scratch_bytes(Dims(*d), want_weights);
+size_t aaconv_scratch_bytes_io(const aaconv_dims* d, int precision, const aaconv_io* io) {
+  if (validate(d, precision) || validate_io(d, io)) return 0;
+  return precision == AACONV_FP32 ? f32_scratch_bytes(Dims(*d, io)) : bf16_scratch_bytes(Dims(*d, io), 0);
 }
+size_t aaconv_saved_bytes(const aaconv_dims* d, int precision) { return aaconv_saved_bytes_io(d, precision, nullptr); }
+size_t aaconv_scratch_bytes(const aaconv_dims* d, int precision, int) { return aaconv_scratch_bytes_io(d, precision, nullptr); }
 int64_t aaconv_saved_offset(const aaconv_dims* d, int precision, const char* name) {
   if (validate(d, precision) || !name) return -1;
   return precision == AACONV_FP32 ? f32_saved_offset(Dims(*d), name) : bf16_saved_offset(Dims(*d), name);
 }
 
-int aaconv_forward(const aaconv_dims* d, int precision, const float* x, const aaconv_params* p, float* y,
-                   float* weights, void* saved, void* scratch, void* stream) {
+int aaconv_forward_io(const aaconv_dims* d, int precision, const aaconv_io* io, const void* x, const aaconv_params* p, void* y,
+                      float* weights, void* saved, void* scratch, void* stream) {
   AACONV_TRY(validate(d, precision));
+  AACONV_TRY(validate_io(d, io));
   if (!x || !p || !y || !saved || !scratch) return fail(AACONV_E_ARG, "NULL buffer");
   if (!p->qkv_w || !p->out_w || (d->Cout > d->dv && !p->conv_w) || (d->relative && (!p->key_rel_h || !p->key_rel_w)))
     return fail(AACONV_E_ARG, "NULL parameter");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return precision == AACONV_FP32 ? f32_forward(Dims(*d), x, p, y, weights, saved, scratch, st)
-                                  : bf16_forward(Dims(*d), x, p, y, weights, saved, scratch, st);
+  return precision == AACONV_FP32 ? f32_forward(Dims(*d, io), x, p, y, weights, saved, scratch, st)
+                                  : bf16_forward(Dims(*d, io), x, p, y, weights, saved, scratch, st);
+}
+int aaconv_forward(const aaconv_dims* d, int precision, const float* x, const aaconv_params* p, float* y,
+                   float* weights, void* saved, void* scratch, void* stream) {
+  return aaconv_forward_io(d, precision, nullptr, x, p, y, weights, saved, scratch, stream);
 }
 
-int aaconv_backward(const aaconv_dims* d, int precision, const float* x, const aaconv_params* p, const float* dy,
-                    void* saved, void* scratch, float* dx, const aaconv_param_grads* g, void* stream) {
+int aaconv_backward_io(const aaconv_dims* d, int precision, const aaconv_io* io, const void* x, const aaconv_params* p, const float* dy,
+                       void* saved, void* scratch, void* dx, const aaconv_param_grads* g, void* stream) {
   AACONV_TRY(validate(d, precision));
+  AACONV_TRY(validate_io(d, io));
   if (!x || !p || !dy || !saved || !scratch || !g) return fail(AACONV_E_ARG, "NULL buffer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return precision == AACONV_FP32 ? f32_backward(Dims(*d), x, p, dy, saved, scratch, dx, g, st)
-                                  : bf16_backward(Dims(*d), x, p, dy, saved, scratch, dx, g, st);
+  return precision == AACONV_FP32 ? f32_backward(Dims(*d, io), x, p, dy, saved, scratch, dx, g, st)
+                                  : bf16_backward(Dims(*d, io), x, p, dy, saved, scratch, dx, g, st);
+}
+int aaconv_backward(const aaconv_dims* d, int precision, const float* x, const aaconv_params* p, const float* dy,
+                    void* saved, void* scratch, float* dx, const aaconv_param_grads* g, void* stream) {
+  return aaconv_backward_io(d, precision, nullptr, x, p, dy, saved, scratch, dx, g, stream);
 }
 
 int aaconv_bce_forward_backward(const float* z, const float* targets, int ld, const int32_t* cols, int B, int C,

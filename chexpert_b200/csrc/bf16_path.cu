@@ -10,6 +10,9 @@ namespace aaconv {
 namespace {
 struct Scratch {
   float *d_o, *delta, *dq, *dk, *dv, *partial, *relpart, *dqa;
+  float* xn;        // fp32 NCHW relu((x-mean)*rstd) / fp32 copy of a bf16 x: only when an FFMA fallback needs x itself
+  void* dxraw;      // gradient wrt the AAConv2d input before the fused InstanceNorm + ReLU adjoint / type conversion
+  int dxraw_bf16;
   TcGemmBufs gemm;
   bool gemm_ok;
   size_t bytes;
@@ -32,6 +35,13 @@ struct Scratch {
       gemm = tc_gemm_bufs(d, gb);
     }
     (void)want_weights;   // the attention map is computed from the saved operands: no extra scratch
+    const size_t nx = (size_t)d.B * d.Cin * d.Hin * d.Win;
+    const bool typed = d.x_bf16 || d.fuse_in;
+    const bool ffma_x = !gemm_ok || tc_wgrad_supported(d) != 0;
+    xn = (typed && ffma_x) ? c.take<float>(nx) : nullptr;
+    // the tcgen05 dgrad writes the raw gradient in the type of x (bf16 under autocast); the FFMA fallback in fp32
+    dxraw_bf16 = (gemm_ok && d.x_bf16) ? 1 : 0;
+    dxraw = typed ? c.take<char>(nx * (dxraw_bf16 ? 2 : 4)) : nullptr;
     bytes = c.off;
   }
 };
@@ -41,6 +51,7 @@ T* at(const void* base, int64_t off) { return reinterpret_cast<T*>(static_cast<c
 // saved block = the fp32 block (q,k,v,o,lse; same offsets as the fp32 path) followed by the augmented operands
 struct SavedAug {
   void *qa, *ka, *xh;       // xh: channels-last bf16 copy of x (fprop operand, reused by wgrad)
+  float* stats;             // (B*Cin) x (mean, rstd) of the fused InstanceNorm prologue
   size_t bytes;
   SavedAug(const Dims& d, const void* base) {
     Carver c(const_cast<void*>(base));
@@ -50,6 +61,7 @@ struct SavedAug {
     qa = c.take<uint16_t>(rows * a.KP);
     ka = c.take<uint16_t>(rows * a.KP);
     xh = c.take<uint16_t>(tc_gemm_supported(d) == 0 ? (size_t)d.B * d.Hin * d.Win * (cdiv(d.Cin, 64) * 64) : 0);
+    stats = c.take<float>(d.fuse_in ? (size_t)d.B * d.Cin * 2 : 0);
     bytes = c.off;
   }
 };
@@ -62,7 +74,7 @@ size_t bf16_scratch_bytes(const Dims& d, int want_weights) {
 }
 int64_t bf16_saved_offset(const Dims& d, const char* name) { return f32_saved_offset(d, name); }
 
-int bf16_forward(const Dims& d, const float* x, const aaconv_params* p, float* y, float* weights, void* saved,
+int bf16_forward(const Dims& d, const void* xin, const aaconv_params* p, void* y, float* weights, void* saved,
                  void* scratch, cudaStream_t st) {
   AACONV_TRY(tc_attn_supported(d));
   AACONV_TRY(aug_supported(d));
@@ -73,9 +85,14 @@ int bf16_forward(const Dims& d, const float* x, const aaconv_params* p, float* y
   float* o = at<float>(saved, f32_saved_offset(d, "o"));
   float* lse = at<float>(saved, f32_saved_offset(d, "lse"));
   SavedAug sa(d, saved);
+  if (d.fuse_in) AACONV_TRY(in_stats(d, xin, sa.stats, st));     // InstanceNorm statistics (attn_aug_conv.py:438)
+  const float* x = static_cast<const float*>(xin);                // fp32 view of the (normalised) input for the FFMA fallbacks
+  if (w.xn && !w.gemm_ok) { AACONV_TRY(in_relu_apply(d, xin, sa.stats, w.xn, st)); x = w.xn; }
   if (w.gemm_ok) {
     w.gemm.xh = sa.xh;
-    AACONV_TRY(tc_fprop(d, w.gemm, x, p->conv_w, p->qkv_w, y, q, k, v, st));
+    // layout + precision pack of the GEMM operand, with relu((x-mean)*rstd) applied on the way (attn_aug_conv.py:438-439)
+    AACONV_TRY(pack_x(xin, d.x_bf16, d.fuse_in ? sa.stats : nullptr, sa.xh, d.B, d.Cin, w.gemm.CinK, d.Hin * d.Win, st));
+    AACONV_TRY(tc_fprop(d, w.gemm, p->conv_w, p->qkv_w, y, q, k, v, st));
   } else {   // geometry outside the TMA tiling (e.g. rows wider than 128 pixels): FFMA implicit GEMM
     AACONV_TRY(f32_conv_fwd(d, x, p->conv_w, y, st));
     AACONV_TRY(f32_qkv_fwd(d, x, p->qkv_w, q, k, v, st));
@@ -89,10 +106,17 @@ int bf16_forward(const Dims& d, const float* x, const aaconv_params* p, float* y
   return 0;
 }
 
-int bf16_backward(const Dims& d, const float* x, const aaconv_params* p, const float* dy, void* saved,
-                  void* scratch, float* dx, const aaconv_param_grads* g, cudaStream_t st) {
+int bf16_backward(const Dims& d, const void* xin, const aaconv_params* p, const float* dy, void* saved,
+                  void* scratch, void* dx_out, const aaconv_param_grads* g, cudaStream_t st) {
   AACONV_TRY(aug_supported(d));
   Scratch w(d, scratch, 0);
+  // typed boundary / fused prologue: the kernels below produce the gradient wrt the AAConv2d input in w.dxraw; the last step
+  // turns it into dx (InstanceNorm + ReLU adjoint, or a plain type conversion).  Otherwise they write dx directly.
+  const bool typed = d.x_bf16 || d.fuse_in;
+  void* const dxv = !dx_out ? nullptr : (typed ? w.dxraw : dx_out);
+  float* const dx = static_cast<float*>(dxv);                      // fp32 view for the FFMA fallbacks
+  const int dx_bf16 = typed ? w.dxraw_bf16 : 0;
+  const float* x = static_cast<const float*>(xin);
   const AugLayout a = aug_layout(d);
   const float* q = at<float>(saved, f32_saved_offset(d, "q"));
   const float* k = at<float>(saved, f32_saved_offset(d, "k"));
@@ -100,6 +124,7 @@ int bf16_backward(const Dims& d, const float* x, const aaconv_params* p, const f
   const float* o = at<float>(saved, f32_saved_offset(d, "o"));
   const float* lse = at<float>(saved, f32_saved_offset(d, "lse"));
   SavedAug sa(d, saved);
+  if (w.xn) { AACONV_TRY(in_relu_apply(d, xin, sa.stats, w.xn, st)); x = w.xn; }
   // the backward-only columns of Qa (-lse, dO, -delta) are filled in place; idempotent, so a retained graph may
   // run backward again
   if (out_bwd_patch_supported(d) == 0) {     // out_proj adjoint and the patch in one pass over the pixels
@@ -128,7 +153,7 @@ int bf16_backward(const Dims& d, const float* x, const aaconv_params* p, const f
   }
   if (w.gemm_ok) {
     AACONV_TRY(tc_pack_grads(d, w.gemm, dy, direct ? nullptr : w.dq, w.dk, w.dv, st));
-    if (dx) AACONV_TRY(tc_dgrad(d, w.gemm, p->conv_w, p->qkv_w, dx, st));
+    if (dxv) AACONV_TRY(tc_dgrad(d, w.gemm, p->conv_w, p->qkv_w, dxv, dx_bf16, st));
     if (g->conv_w || g->qkv_w) {
       if (tc_wgrad_supported(d) == 0) {
         w.gemm.xh = sa.xh;             // packed by forward
@@ -138,6 +163,7 @@ int bf16_backward(const Dims& d, const float* x, const aaconv_params* p, const f
         AACONV_TRY(f32_qkv_bwd(d, x, p->qkv_w, w.dq, w.dk, w.dv, g->qkv_w, nullptr, 0, w.partial, st));
       }
     }
+    if (typed && dx_out) AACONV_TRY(in_relu_bwd(d, xin, w.dxraw, w.dxraw_bf16, sa.stats, dx_out, st));
     return 0;
   }
   if (d.Cc) {
@@ -146,6 +172,7 @@ int bf16_backward(const Dims& d, const float* x, const aaconv_params* p, const f
     AACONV_CUDA_OK(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)d.B * d.Cin * d.Hin * d.Win, st));
   }
   AACONV_TRY(f32_qkv_bwd(d, x, p->qkv_w, w.dq, w.dk, w.dv, g->qkv_w, dx, /*accumulate=*/1, w.partial, st));
+  if (typed && dx_out) AACONV_TRY(in_relu_bwd(d, xin, w.dxraw, w.dxraw_bf16, sa.stats, dx_out, st));
   return 0;
 }
 

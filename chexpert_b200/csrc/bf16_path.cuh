@@ -53,15 +53,22 @@ struct TcGemmBufs {
 int tc_gemm_supported(const Dims& d);
 TcGemmBufs tc_gemm_bufs(const Dims& d, void* base);
 int pack_nhwc_bf16(const float* in, void* out, int B, int C, int Cp, int HW, cudaStream_t st);
-int tc_fprop(const Dims& d, const TcGemmBufs& t, const float* x, const float* conv_w, const float* qkv_w, float* y,
+// t.xh must hold the packed (optionally normalised) x of this call (pack_x); y: d.y_bf16 / d.y_bs
+int tc_fprop(const Dims& d, const TcGemmBufs& t, const float* conv_w, const float* qkv_w, void* y,
              float* q, float* k, float* v, cudaStream_t st);
 int tc_pack_grads(const Dims& d, const TcGemmBufs& t, const float* dy, const float* dq, const float* dk, const float* dv,
                   cudaStream_t st);   // dq == NULL: dqkvh was already written by the attention backward kernels
-int tc_dgrad(const Dims& d, const TcGemmBufs& t, const float* conv_w, const float* qkv_w, float* dx, cudaStream_t st);
-int tc_zero_class(const Dims& d, float* dx, int rh, int rw, cudaStream_t st);
+int tc_dgrad(const Dims& d, const TcGemmBufs& t, const float* conv_w, const float* qkv_w, void* dx, int dx_bf16, cudaStream_t st);
+int tc_zero_class(const Dims& d, void* dx, int dx_bf16, int rh, int rw, cudaStream_t st);
 int tc_wgrad_supported(const Dims& d);
 size_t tc_wgrad_partial_floats(const Dims& d);
 int tc_wgrad(const Dims& d, const TcGemmBufs& t, float* dwc, float* dwq, float* partial, cudaStream_t st);
+
+// prologue.cu: fused InstanceNorm + ReLU prologue of the Transition (attn_aug_conv.py:438-439) and the typed x / dx boundary
+int in_stats(const Dims& d, const void* x, float* stats, cudaStream_t st);                      // stats: (B*Cin) x (mean, rstd)
+int pack_x(const void* in, int in_bf16, const float* stats, void* out, int B, int C, int Cp, int HW, cudaStream_t st);
+int in_relu_apply(const Dims& d, const void* x, const float* stats, float* out, cudaStream_t st);
+int in_relu_bwd(const Dims& d, const void* x, const void* g, int g_bf16, const float* stats, void* dx, cudaStream_t st);
 
 // fp32_gemms.cu
 int aug_rel_weight_grad(const Dims& d, const float* q, const float* dqa, int KD, int axis, float* dkr, float* partial,
@@ -71,8 +78,8 @@ int aug_rel_weight_grad(const Dims& d, const float* q, const float* dqa, int KD,
 size_t bf16_saved_bytes(const Dims& d);
 size_t bf16_scratch_bytes(const Dims& d, int want_weights);
 int64_t bf16_saved_offset(const Dims& d, const char* name);
-int bf16_forward(const Dims& d, const float* x, const aaconv_params* p, float* y, float* weights, void* saved,
+int bf16_forward(const Dims& d, const void* x, const aaconv_params* p, void* y, float* weights, void* saved,
                  void* scratch, cudaStream_t st);
-int bf16_backward(const Dims& d, const float* x, const aaconv_params* p, const float* dy, void* saved,
-                  void* scratch, float* dx, const aaconv_param_grads* g, cudaStream_t st);
+int bf16_backward(const Dims& d, const void* x, const aaconv_params* p, const float* dy, void* saved,
+                  void* scratch, void* dx, const aaconv_param_grads* g, cudaStream_t st);
 }  // namespace aaconv

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
@@ -51,6 +52,19 @@ struct Dims {
   int B, Cin, Hin, Win, Cout, H, W, ks, stride, pad, dil, dk, dv, nh, relative;
   int dkh, dvh, L, Cc /*conv-branch channels*/, Nqkv, BN /*B*nh*/, RW, RH;
   float qscale;
+  // I/O description (aaconv_io): element types of x / y, batch stride of y, fused InstanceNorm + ReLU prologue
+  int x_bf16 = 0, y_bf16 = 0, fuse_in = 0;
+  long long y_bs = 0;
+  float in_eps = 1e-5f;
+  __host__ Dims(const aaconv_dims& d, const aaconv_io* io) : Dims(d) {
+    if (io) {
+      x_bf16 = io->x_dtype == AACONV_BF16;
+      y_bf16 = io->y_dtype == AACONV_BF16;
+      fuse_in = io->fuse_in_relu != 0;
+      in_eps = io->in_eps > 0.f ? io->in_eps : 1e-5f;
+      if (io->y_batch_stride > 0) y_bs = io->y_batch_stride;
+    }
+  }
   __host__ explicit Dims(const aaconv_dims& d)
       : B(d.B), Cin(d.Cin), Hin(d.Hin), Win(d.Win), Cout(d.Cout), H(d.H), W(d.W), ks(d.ksize),
         stride(d.stride), pad(d.pad), dil(d.dil), dk(d.dk), dv(d.dv), nh(d.nh), relative(d.relative) {
@@ -63,8 +77,17 @@ struct Dims {
     RW = 2 * W - 1;
     RH = 2 * H - 1;
     qscale = dkh > 0 ? 1.0f / sqrtf((float)dkh) : 0.f;
+    y_bs = (long long)Cout * L;
   }
 };
+
+// y element store: fp32 or bf16 destination selected at run time (the y tensor is small; the branch is uniform)
+#ifdef __CUDACC__
+__device__ __forceinline__ void store_y(void* y, size_t idx, float v, int bf16_out) {
+  if (bf16_out) static_cast<__nv_bfloat16*>(y)[idx] = __float2bfloat16(v);
+  else static_cast<float*>(y)[idx] = v;
+}
+#endif
 
 inline size_t align256(size_t n) { return (n + 255) & ~size_t(255); }
 

@@ -26,8 +26,8 @@ static int splitk_reduce(const float* partial, float* out, int count, int splits
 // ------------------------------------------------------------------------------------------------
 struct ConvFwdP {
   int M, N, K, k_chunk;
-  const float* x; const float* w; float* y;
-  int Cin, Hin, Win, Ho, Wo, ks, stride, pad, dil, Ctot, coff;
+  const float* x; const float* w; void* y;
+  int Cin, Hin, Win, Ho, Wo, ks, stride, pad, dil, coff, y_bf16; long long y_bs;
   static constexpr bool A_K_CONTIG = false, B_K_CONTIG = true;
   struct ARow { const float* xb; int h0, w0; };
   struct BCol { const float* wr; };
@@ -44,17 +44,17 @@ struct ConvFwdP {
   __device__ float b(const BCol& c, int k) const { return __ldg(c.wr + k); }
   __device__ void store(int m, int n, float v, int) const {
     const int j = m % Wo, t = m / Wo, i = t % Ho, b = t / Ho;
-    y[(((size_t)b * Ctot + coff + n) * Ho + i) * Wo + j] = v;
+    store_y(y, (size_t)b * y_bs + ((size_t)(coff + n) * Ho + i) * Wo + j, v, y_bf16);
   }
 };
 
-int f32_conv_fwd(const Dims& d, const float* x, const float* w, float* y, cudaStream_t st) {
+int f32_conv_fwd(const Dims& d, const float* x, const float* w, void* y, cudaStream_t st) {
   if (d.Cc == 0) return 0;
   ConvFwdP p;
   p.M = d.B * d.L; p.N = d.Cc; p.K = d.Cin * d.ks * d.ks; p.k_chunk = p.K;
   p.x = x; p.w = w; p.y = y;
   p.Cin = d.Cin; p.Hin = d.Hin; p.Win = d.Win; p.Ho = d.H; p.Wo = d.W;
-  p.ks = d.ks; p.stride = d.stride; p.pad = d.pad; p.dil = d.dil; p.Ctot = d.Cout; p.coff = 0;
+  p.ks = d.ks; p.stride = d.stride; p.pad = d.pad; p.dil = d.dil; p.coff = 0; p.y_bs = d.y_bs; p.y_bf16 = d.y_bf16;
   return launch_simt_gemm(p, 1, st, "conv_fwd_f32");
 }
 
@@ -105,8 +105,8 @@ int f32_qkv_fwd(const Dims& d, const float* x, const float* w, float* q, float* 
 // ------------------------------------------------------------------------------------------------
 struct OutFwdP {
   int M, N, K, k_chunk;
-  const float* o; const float* w; float* y;
-  int L, nh, dvh, Ctot, coff;
+  const float* o; const float* w; void* y;
+  int L, nh, dvh, coff, y_bf16; long long y_bs;
   static constexpr bool A_K_CONTIG = true, B_K_CONTIG = true;
   struct ARow { int b, l; };
   struct BCol { const float* wr; };
@@ -119,14 +119,14 @@ struct OutFwdP {
   __device__ float b(const BCol& c, int k) const { return __ldg(c.wr + k); }
   __device__ void store(int m, int n, float v, int) const {
     const int b = m / L, l = m - b * L;
-    y[((size_t)b * Ctot + coff + n) * L + l] = v;
+    store_y(y, (size_t)b * y_bs + (size_t)(coff + n) * L + l, v, y_bf16);
   }
 };
 
-int f32_out_fwd(const Dims& d, const float* o, const float* w, float* y, cudaStream_t st) {
+int f32_out_fwd(const Dims& d, const float* o, const float* w, void* y, cudaStream_t st) {
   OutFwdP p;
   p.M = d.B * d.L; p.N = d.dv; p.K = d.dv; p.k_chunk = p.K;
-  p.o = o; p.w = w; p.y = y; p.L = d.L; p.nh = d.nh; p.dvh = d.dvh; p.Ctot = d.Cout; p.coff = d.Cc;
+  p.o = o; p.w = w; p.y = y; p.L = d.L; p.nh = d.nh; p.dvh = d.dvh; p.coff = d.Cc; p.y_bs = d.y_bs; p.y_bf16 = d.y_bf16;
   return launch_simt_gemm(p, 1, st, "out_fwd_f32");
 }
 

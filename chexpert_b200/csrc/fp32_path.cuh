@@ -6,9 +6,9 @@
 namespace aaconv {
 
 // fp32_gemms.cu
-int f32_conv_fwd(const Dims& d, const float* x, const float* w, float* y, cudaStream_t st);
+int f32_conv_fwd(const Dims& d, const float* x, const float* w, void* y, cudaStream_t st);   // y: d.y_bf16 / d.y_bs
 int f32_qkv_fwd(const Dims& d, const float* x, const float* w, float* q, float* k, float* v, cudaStream_t st);
-int f32_out_fwd(const Dims& d, const float* o, const float* w, float* y, cudaStream_t st);
+int f32_out_fwd(const Dims& d, const float* o, const float* w, void* y, cudaStream_t st);
 int f32_out_bwd(const Dims& d, const float* dy, const float* o, const float* w, float* d_o, float* dw,
                 float* partial, cudaStream_t st);
 int f32_qkv_bwd(const Dims& d, const float* x, const float* w, const float* dq, const float* dk,
@@ -34,12 +34,13 @@ int f32_rel_bwd_dq(const Dims& d, const float* krw, const float* krh, const floa
                    float* dq, cudaStream_t st);
 
 // fp32_path.cu  (orchestration)
-size_t f32_saved_bytes(const Dims& d);
+size_t f32_saved_bytes(const Dims& d);           // q, k, v, o, lse (the block the bf16 path shares)
+size_t f32_saved_bytes_io(const Dims& d);        // + the InstanceNorm statistics of the fused prologue
 size_t f32_scratch_bytes(const Dims& d);
 int64_t f32_saved_offset(const Dims& d, const char* name);
-int f32_forward(const Dims& d, const float* x, const aaconv_params* p, float* y, float* weights, void* saved,
+int f32_forward(const Dims& d, const void* x, const aaconv_params* p, void* y, float* weights, void* saved,
                 void* scratch, cudaStream_t st);
-int f32_backward(const Dims& d, const float* x, const aaconv_params* p, const float* dy, void* saved,
-                 void* scratch, float* dx, const aaconv_param_grads* g, cudaStream_t st);
+int f32_backward(const Dims& d, const void* x, const aaconv_params* p, const float* dy, void* saved,
+                 void* scratch, void* dx, const aaconv_param_grads* g, cudaStream_t st);
 
 }  // namespace aaconv

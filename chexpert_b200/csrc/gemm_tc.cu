@@ -37,7 +37,8 @@ struct PGParams {
   int r, Wt, Ht, tiles_h, ncta;    // tile = r rows x Wt pixels of the (Ht x Wt) pixel grid this job covers; ncta = B * tiles_h
   // epilogue
   int mode;                        // 0 fprop, 1 dgrad
-  float* out0; float* q; float* k; float* v;
+  void* out0; float* q; float* k; float* v;
+  int out_bf16; long long y_bs;    // out0 = y (fprop: batch stride y_bs) or dx (dgrad, dense), fp32 or bf16
   int Cout, Cc, H, W, L, nh, dk, dkh, dvh, Nqkv; float qscale;           // fprop
   int Cin, Hin, Win, stride, rh, rw, pair;                                // dgrad
 };
@@ -138,7 +139,9 @@ __global__ void __launch_bounds__(PG_THREADS, 2) pixel_gemm_tc_kernel(const __gr
       const float qscale = p.qscale;
       const int l = hrow * p.W + ww;
       const bool vec = (dkh & 3) == 0;               // aligned groups of 4 columns never straddle a head
-      float* const ybase = p.out0 + (size_t)b * p.Cout * L + l;
+      const bool obf = p.out_bf16 != 0;
+      float* const ybase = static_cast<float*>(p.out0) + (size_t)b * p.y_bs + l;         // fp32 y
+      bf16* const ybase_h = static_cast<bf16*>(p.out0) + (size_t)b * p.y_bs + l;         // bf16 y (e.g. an autocast feature buffer)
       const size_t hs = (size_t)L * dkh;             // head stride of q / k
       float* const qbase = p.q + ((size_t)b * nh * L + l) * dkh;
       float* const kbase = p.k + ((size_t)b * nh * L + l) * dkh;
@@ -153,7 +156,12 @@ __global__ void __launch_bounds__(PG_THREADS, 2) pixel_gemm_tc_kernel(const __gr
           tc::tmem_ld_x32(tlane + c * 128 + cb * 32, rr);
           tc::tmem_ld_wait();
           if (!valid) continue;
-          if (ch.kind == 0) {                        // conv channels -> y NCHW (lanes = consecutive pixels: coalesced)
+          if (ch.kind == 0 && obf) {
+            bf16* dst = ybase_h + (size_t)nb * L;
+#pragma unroll
+            for (int e = 0; e < 32; ++e, dst += L)
+              if (nb + e < Cc) *dst = __float2bfloat16(__uint_as_float(rr[e]));
+          } else if (ch.kind == 0) {                 // conv channels -> y NCHW (lanes = consecutive pixels: coalesced)
             float* dst = ybase + (size_t)nb * L;
             if (nb + 32 <= Cc) {
 #pragma unroll
@@ -210,7 +218,9 @@ __global__ void __launch_bounds__(PG_THREADS, 2) pixel_gemm_tc_kernel(const __gr
         const int wi = ww * 2;
         const bool v1 = valid && hi < Hin && wi + 1 < Win;
         const bool vec2 = (Win & 1) == 0;
-        float* const base = p.out0 + (size_t)b * Cin * plane + (size_t)hi * Win + wi;
+        const bool obf = p.out_bf16 != 0;
+        float* const base = static_cast<float*>(p.out0) + (size_t)b * Cin * plane + (size_t)hi * Win + wi;
+        bf16* const base_h = static_cast<bf16*>(p.out0) + (size_t)b * Cin * plane + (size_t)hi * Win + wi;
         uint32_t r2[32];
         for (int c = 0; c < nchunks; c += 2) {
           const int n0 = p.chunks[c].n0;
@@ -224,6 +234,21 @@ __global__ void __launch_bounds__(PG_THREADS, 2) pixel_gemm_tc_kernel(const __gr
             tc::tmem_ld_x32(tlane + (c + 1) * 128 + cb * 32, r2);
             tc::tmem_ld_wait();
             if (!v0) continue;
+            if (obf) {                               // bf16 dx: one 4-byte store per channel (pixel pair)
+              bf16* dh = base_h + (size_t)nb * plane;
+#pragma unroll
+              for (int e = 0; e < 32; ++e, dh += plane) {
+                if (nb + e < Cin) {
+                  if (vec2) {
+                    *reinterpret_cast<uint32_t*>(dh) = tc::pack_bf16x2(__uint_as_float(rr[e]), __uint_as_float(r2[e]));
+                  } else {
+                    dh[0] = __float2bfloat16(__uint_as_float(rr[e]));
+                    if (v1) dh[1] = __float2bfloat16(__uint_as_float(r2[e]));
+                  }
+                }
+              }
+              continue;
+            }
             float* dst = base + (size_t)nb * plane;
             if (vec2 && nb + 32 <= Cin) {
 #pragma unroll
@@ -246,7 +271,9 @@ __global__ void __launch_bounds__(PG_THREADS, 2) pixel_gemm_tc_kernel(const __gr
         }
       } else {
         const int wi = ww * stride + p.rw;
-        float* const base = p.out0 + (size_t)b * Cin * plane + (size_t)hi * Win + wi;
+        const bool obf = p.out_bf16 != 0;
+        float* const base = static_cast<float*>(p.out0) + (size_t)b * Cin * plane + (size_t)hi * Win + wi;
+        bf16* const base_h = static_cast<bf16*>(p.out0) + (size_t)b * Cin * plane + (size_t)hi * Win + wi;
         for (int c = 0; c < nchunks; ++c) {
           const int n0 = p.chunks[c].n0;
           tc::mbar_wait(&sm.bar_acc[c], 0);
@@ -257,6 +284,13 @@ __global__ void __launch_bounds__(PG_THREADS, 2) pixel_gemm_tc_kernel(const __gr
             tc::tmem_ld_x32(tlane + c * 128 + cb * 32, rr);
             tc::tmem_ld_wait();
             if (!v0) continue;
+            if (obf) {
+              bf16* dh = base_h + (size_t)nb * plane;
+#pragma unroll
+              for (int e = 0; e < 32; ++e, dh += plane)
+                if (nb + e < Cin) *dh = __float2bfloat16(__uint_as_float(rr[e]));
+              continue;
+            }
             float* dst = base + (size_t)nb * plane;
 #pragma unroll
             for (int e = 0; e < 32; ++e, dst += plane)
@@ -274,74 +308,6 @@ __global__ void __launch_bounds__(PG_THREADS, 2) pixel_gemm_tc_kernel(const __gr
 // ------------------------------------------------------------------------------------------------
 // packing kernels
 // ------------------------------------------------------------------------------------------------
-// (B, C, HW) fp32 -> (B, HW, Cp) bf16, channels [C, Cp) zero
-__global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int C, int Cp, int HW) {
-  __shared__ float t[32][33];
-  const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
-  const float* src = in + (size_t)b * C * HW;
-  bf16* dst = out + (size_t)b * HW * Cp;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int c = c0 + i, px = p0 + threadIdx.x;
-    t[i][threadIdx.x] = (c < C && px < HW) ? src[(size_t)c * HW + px] : 0.f;
-  }
-  __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int px = p0 + i, c = c0 + threadIdx.x;
-    if (px < HW && c < Cp) dst[(size_t)px * Cp + c] = __float2bfloat16(t[threadIdx.x][i]);
-  }
-}
-
-// Fast path (HW % 4 == 0): tile = 64 channels x 64 pixels; 256 B coalesced reads along pixels (float4), 128 B
-// coalesced writes along channels (4 x bf16 per lane).
-__global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_v4_kernel(const float* __restrict__ in, bf16* __restrict__ out, int C,
-                                                                   int Cp, int HW) {
-  __shared__ float t[64][65];                                   // [pixel][channel]
-  const int b = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
-  const float* src = in + (size_t)b * C * HW;
-  bf16* dst = out + (size_t)b * HW * Cp;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  {
-    const int px = p0 + (lane & 15) * 4;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int cl = warp * 8 + i * 2 + (lane >> 4), c = c0 + cl;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c < C && px < HW) v = *reinterpret_cast<const float4*>(src + (size_t)c * HW + px);   // HW % 4 == 0: all-or-nothing
-      const int pl = (lane & 15) * 4;
-      t[pl][cl] = v.x; t[pl + 1][cl] = v.y; t[pl + 2][cl] = v.z; t[pl + 3][cl] = v.w;
-    }
-  }
-  __syncthreads();
-  {
-    const int cl = (lane & 15) * 4;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int pl = warp * 8 + i * 2 + (lane >> 4), px = p0 + pl;
-      if (px < HW && c0 + cl < Cp) {
-        const __nv_bfloat162 lo = __floats2bfloat162_rn(t[pl][cl], t[pl][cl + 1]);
-        const __nv_bfloat162 hi = __floats2bfloat162_rn(t[pl][cl + 2], t[pl][cl + 3]);
-        uint2 w;
-        w.x = *reinterpret_cast<const uint32_t*>(&lo);
-        w.y = *reinterpret_cast<const uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(dst + (size_t)px * Cp + c0 + cl) = w;
-      }
-    }
-  }
-}
-
-int pack_nhwc_bf16(const float* in, void* out, int B, int C, int Cp, int HW, cudaStream_t st) {
-  if (HW % 4 == 0 && Cp % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
-    dim3 grid(cdiv(HW, 64), cdiv(Cp, 64), B);
-    nchw_to_nhwc_bf16_v4_kernel<<<grid, 256, 0, AACONV_ST(st)>>>(in, static_cast<bf16*>(out), C, Cp, HW);
-    AACONV_LAUNCH_OK("pack_nhwc_bf16");
-    return 0;
-  }
-  dim3 grid(cdiv(HW, 32), cdiv(Cp, 32), B), block(32, 8);
-  nchw_to_nhwc_bf16_kernel<<<grid, block, 0, AACONV_ST(st)>>>(in, static_cast<bf16*>(out), C, Cp, HW);
-  AACONV_LAUNCH_OK("pack_nhwc_bf16");
-  return 0;
-}
-
 // fprop B operand: rows [t*NPc + n] = conv_w[n, :, t] (n < Cc, else 0), then rows [T*NPc + n] = qkv_w[n, :]; K = Cin.
 // One thread per (n, cin): it reads the T contiguous taps of its filter element (coalesced across cin) and writes one bf16
 // per tap row (coalesced across cin); no per-element index division.  grid = (ceil(CinK / 256), NPc + NPq).
@@ -484,10 +450,9 @@ static int make_2d_map(CUtensorMap* out, const void* base, int K, size_t rows) {
 static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 // conv fprop + qkv projection.  y: conv channels of (B,Cout,H,W); q,k,v head-split fp32.
-int tc_fprop(const Dims& d, const TcGemmBufs& t, const float* x, const float* conv_w, const float* qkv_w, float* y,
+int tc_fprop(const Dims& d, const TcGemmBufs& t, const float* conv_w, const float* qkv_w, void* y,
              float* q, float* k, float* v, cudaStream_t st) {
   const int T = d.ks * d.ks, s = d.stride;
-  AACONV_TRY(pack_nhwc_bf16(x, t.xh, d.B, d.Cin, t.CinK, d.Hin * d.Win, st));
   pack_wf_kernel<<<dim3(cdiv(t.CinK, 256), t.NPc + t.NPq), 256, 0, AACONV_ST(st)>>>(conv_w, qkv_w, static_cast<bf16*>(t.wf), d.Cc, d.Cin,
                                                                           t.CinK, T, t.NPc, d.Nqkv, t.NPq);
   AACONV_LAUNCH_OK("pack_wf");
@@ -509,7 +474,7 @@ int tc_fprop(const Dims& d, const TcGemmBufs& t, const float* x, const float* co
     }
   const int seg_qkv = ns;
   p.segs[ns++] = {0, 0, 0, katoms, 0, T * t.NPc};
-  p.mode = 0; p.out0 = y; p.q = q; p.k = k; p.v = v;
+  p.mode = 0; p.out0 = y; p.out_bf16 = d.y_bf16; p.y_bs = d.y_bs; p.q = q; p.k = k; p.v = v;
   p.Cout = d.Cout; p.Cc = d.Cc; p.H = d.H; p.W = d.W; p.L = d.L; p.nh = d.nh; p.dk = d.dk; p.dkh = d.dkh; p.dvh = d.dvh;
   p.Nqkv = d.Nqkv; p.qscale = d.qscale;
   // accumulator chunks, up to PG_MAX_CHUNKS per launch
@@ -555,7 +520,7 @@ int tc_pack_grads(const Dims& d, const TcGemmBufs& t, const float* dy, const flo
 }
 
 // dx = conv dgrad + qkv dgrad (needs tc_pack_grads first).
-int tc_dgrad(const Dims& d, const TcGemmBufs& t, const float* conv_w, const float* qkv_w, float* dx, cudaStream_t st) {
+int tc_dgrad(const Dims& d, const TcGemmBufs& t, const float* conv_w, const float* qkv_w, void* dx, int dx_bf16, cudaStream_t st) {
   const int T = d.ks * d.ks, s = d.stride;
   pack_wd_kernel<<<dim3(cdiv(t.KPc, 128) + cdiv(t.KPq, 128), t.CinP), 128, 0, AACONV_ST(st)>>>(
       conv_w, qkv_w, static_cast<bf16*>(t.wd), static_cast<bf16*>(t.wq), d.Cc, d.Cin, T, t.CinP, t.KPc, d.Nqkv, t.KPq, cdiv(t.KPc, 128));
@@ -591,7 +556,7 @@ int tc_dgrad(const Dims& d, const TcGemmBufs& t, const float* conv_w, const floa
       AACONV_TRY(make_2d_map(&p.bmaps[1], t.wq, t.KPq, (size_t)t.CinP));
       for (int i = 0; i < ns0; ++i) p.segs[i] = seg0[i];
       for (int i = 0; i < ns1; ++i) p.segs[ns0 + i] = seg1[i];
-      p.mode = 1; p.out0 = dx; p.Cin = d.Cin; p.Hin = d.Hin; p.Win = d.Win; p.stride = s; p.rh = rh; p.rw = 0; p.pair = 1;
+      p.mode = 1; p.out0 = dx; p.out_bf16 = dx_bf16; p.Cin = d.Cin; p.Hin = d.Hin; p.Win = d.Win; p.stride = s; p.rh = rh; p.rw = 0; p.pair = 1;
       for (int n0 = 0; n0 < d.Cin; n0 += 128 * (PG_MAX_CHUNKS / 2)) {
         const int nn = std::min(PG_MAX_CHUNKS / 2, cdiv(d.Cin - n0, 128));
         p.nchunks = 2 * nn;
@@ -613,9 +578,9 @@ int tc_dgrad(const Dims& d, const TcGemmBufs& t, const float* conv_w, const floa
       AACONV_TRY(make_2d_map(&p.bmaps[0], t.wd, t.KPc, (size_t)T * t.CinP));
       AACONV_TRY(make_2d_map(&p.bmaps[1], t.wq, t.KPq, (size_t)t.CinP));
       const int ns = class_segs(rh, rw, p.segs);
-      p.mode = 1; p.out0 = dx; p.Cin = d.Cin; p.Hin = d.Hin; p.Win = d.Win; p.stride = s; p.rh = rh; p.rw = rw; p.pair = 0;
+      p.mode = 1; p.out0 = dx; p.out_bf16 = dx_bf16; p.Cin = d.Cin; p.Hin = d.Hin; p.Win = d.Win; p.stride = s; p.rh = rh; p.rw = rw; p.pair = 0;
       if (ns == 0) {   // no tap reaches this class (e.g. 1x1 conv with stride 2): gradient is zero there
-        AACONV_TRY(tc_zero_class(d, dx, rh, rw, st));
+        AACONV_TRY(tc_zero_class(d, dx, dx_bf16, rh, rw, st));
         continue;
       }
       for (int n0 = 0; n0 < d.Cin; n0 += 128 * PG_MAX_CHUNKS) {
@@ -628,7 +593,7 @@ int tc_dgrad(const Dims& d, const TcGemmBufs& t, const float* conv_w, const floa
   return qu.flush(st, "conv_qkv_dgrad_tc");
 }
 
-__global__ void zero_class_kernel(float* __restrict__ dx, size_t planes, int Hin, int Win, int s, int rh, int rw) {
+__global__ void zero_class_kernel(void* __restrict__ dx, int dx_bf16, size_t planes, int Hin, int Win, int s, int rh, int rw) {
   const int Hc = (Hin - rh + s - 1) / s, Wc = (Win - rw + s - 1) / s;
   const size_t total = planes * Hc * Wc;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -636,12 +601,12 @@ __global__ void zero_class_kernel(float* __restrict__ dx, size_t planes, int Hin
     const size_t t = i / Wc;
     const int hc = (int)(t % Hc);
     const size_t pl = t / Hc;
-    dx[(pl * Hin + hc * s + rh) * Win + wc * s + rw] = 0.f;
+    store_y(dx, (pl * Hin + hc * s + rh) * Win + wc * s + rw, 0.f, dx_bf16);
   }
 }
 
-int tc_zero_class(const Dims& d, float* dx, int rh, int rw, cudaStream_t st) {
-  zero_class_kernel<<<148 * 4, 256, 0, AACONV_ST(st)>>>(dx, (size_t)d.B * d.Cin, d.Hin, d.Win, d.stride, rh, rw);
+int tc_zero_class(const Dims& d, void* dx, int dx_bf16, int rh, int rw, cudaStream_t st) {
+  zero_class_kernel<<<148 * 4, 256, 0, AACONV_ST(st)>>>(dx, dx_bf16, (size_t)d.B * d.Cin, d.Hin, d.Win, d.stride, rh, rw);
   AACONV_LAUNCH_OK("zero_class");
   return 0;
 }

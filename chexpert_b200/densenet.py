@@ -1,6 +1,6 @@
 """Host-side wiring of the attention-augmented DenseNet121 around the B200 AAConv2d.
 
-Only the wiring lives here: which dk/dv/input_dims each Transition gets, the
+The wiring lives here: which dk/dv/input_dims each Transition gets, the
 InstanceNorm -> ReLU -> AAConv2d(3x3, stride 2) sequence, and the weight initialisation, so that a checkpoint written
 by the reference (``features.transition{1,2,3}.conv.{conv,in_proj_qkv,out_proj}.weight``, ``...key_rel_h/w``;
 chexpert.py:90-123,504-518) loads strictly into this model and vice versa.  The dense blocks are torchvision's
@@ -13,9 +13,10 @@ chexpert.py:90-123,504-518) loads strictly into this model and vice versa.  The 
 """
 from collections import OrderedDict
 
+import torch
 import torch.nn as nn
 import torch.nn.functional as F
-from torchvision.models.densenet import _DenseBlock
+from torchvision.models.densenet import _DenseBlock, _DenseLayer
 
 from .aaconv import AAConv2d
 
@@ -29,7 +30,32 @@ def transition_attn_dims(num_output_features, attn_params):
     return dk, dv, dims
 
 
-def transition(num_input_features, num_output_features, attn_params=None, precision=None):
+class AATransition(nn.Sequential):
+    """InstanceNorm2d -> ReLU -> AAConv2d(3x3, stride 2) with the reference's child names ``norm`` / ``relu`` / ``conv``
+    (models/attn_aug_conv.py:436-440), so state_dicts are interchangeable.
+
+    ``fused_prologue=True``: on CUDA the InstanceNorm statistics, the normalisation and the ReLU
+    run inside the AAConv2d kernels (one statistics pass + the operand pack forward; one fused adjoint pass backward) instead
+    of as two separate torch modules; ``norm`` and ``relu`` stay as (parameter-free) children and define eps.
+    ``forward(x, out_total=C)`` makes the AAConv2d epilogues write into the first channels of the next dense block's
+    (B, C, H, W) feature buffer (row f3)."""
+
+    def __init__(self, num_input_features, num_output_features, attn_params, precision=None, fused_prologue=False):
+        super().__init__()
+        dk, dv, dims = transition_attn_dims(num_output_features, attn_params)
+        self.add_module('norm', nn.InstanceNorm2d(num_input_features))          # affine=False, no running stats (:438)
+        self.add_module('relu', nn.ReLU(inplace=True))
+        self.add_module('conv', AAConv2d(num_input_features, num_output_features, 3, 2, dk, dv, attn_params['nh'],
+                                         attn_params['relative'], dims, precision=precision))
+        self.fused_prologue = bool(fused_prologue)
+
+    def forward(self, x, out_total=None):
+        if self.fused_prologue and x.is_cuda and not self.norm.affine and not self.norm.track_running_stats:
+            return self.conv(x, out_total=out_total, fused_in=self.norm.eps)
+        return self.conv(self.relu(self.norm(x)), out_total=out_total)
+
+
+def transition(num_input_features, num_output_features, attn_params=None, precision=None, fused_prologue=False):
     """Sequential with the reference's child names: norm, relu, conv (+ pool for the plain variant)."""
     if attn_params is None:   # stock DenseNet transition (models/attn_aug_conv.py:429-434)
         return nn.Sequential(OrderedDict([
@@ -38,13 +64,82 @@ def transition(num_input_features, num_output_features, attn_params=None, precis
             ('conv', nn.Conv2d(num_input_features, num_output_features, kernel_size=1, stride=1, bias=False)),
             ('pool', nn.AvgPool2d(kernel_size=2, stride=2)),
         ]))
-    dk, dv, dims = transition_attn_dims(num_output_features, attn_params)
-    return nn.Sequential(OrderedDict([
-        ('norm', nn.InstanceNorm2d(num_input_features)),          # affine=False, no running stats (:438)
-        ('relu', nn.ReLU(inplace=True)),
-        ('conv', AAConv2d(num_input_features, num_output_features, 3, 2, dk, dv, attn_params['nh'],
-                          attn_params['relative'], dims, precision=precision)),
-    ]))
+    return AATransition(num_input_features, num_output_features, attn_params, precision, fused_prologue)
+
+
+# ------------------------------------------------------------------------------------------------
+# pre-allocated DenseBlock feature buffer
+# ------------------------------------------------------------------------------------------------
+def _alias(buf, c0, c1):
+    """Tensor over channels [c0, c1) of the (B, C, H, W) buffer that shares its storage but NOT its autograd identity / version
+    counter: later layers write channels >= c1 of the same storage, which must not invalidate what earlier layers saved."""
+    B, C, H, W = buf.shape
+    return torch.empty(0, dtype=buf.dtype, device=buf.device).set_(
+        buf.untyped_storage(), buf.storage_offset() + c0 * H * W, (B, c1 - c0, H, W), (C * H * W, H * W, W, 1))
+
+
+class _Adopt(torch.autograd.Function):
+    """init_features -> the first channels of the block's buffer (copied unless they were produced there)."""
+
+    @staticmethod
+    def forward(ctx, init, buf):
+        c0 = init.shape[1]
+        view = _alias(buf, 0, c0)
+        if init.data_ptr() != view.data_ptr() or init.stride() != view.stride():
+            view.copy_(init)
+        return view
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+class _Append(torch.autograd.Function):
+    """[features so far | new_features]: the concatenation of torchvision's block (densenet.py:48,120-124) without the copy of
+    everything that came before -- only the layer's own `growth_rate` channels are written, next to the rest."""
+
+    @staticmethod
+    def forward(ctx, prev, new, buf):
+        c = prev.shape[1]
+        ctx.c = c
+        _alias(buf, c, c + new.shape[1]).copy_(new)
+        return _alias(buf, 0, c + new.shape[1])
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[:, :ctx.c], g[:, ctx.c:], None
+
+
+class BufferedDenseBlock(nn.ModuleDict):
+    """torchvision's ``_DenseBlock`` (same ``denselayer%d`` children, parameters and arithmetic; the reference uses it at
+    models/attn_aug_conv.py:479-482) over ONE pre-allocated (B, C_in + n * growth, H, W) feature buffer: layer i reads channels
+    [0, c_i) of the buffer and writes its output behind them, so the per-layer ``torch.cat`` (O(layers^2) copy traffic and
+    saved activations) disappears.  If ``init_features`` already lives in such a buffer (an AAConv2d called with ``out_total``),
+    it is adopted without a copy.  The gradient of the concatenated features is accumulated along the chain
+    (one add per layer over contiguous tensors) instead of per (producer, consumer) pair."""
+
+    def __init__(self, num_layers, num_input_features, bn_size, growth_rate, drop_rate):
+        super().__init__()
+        for i in range(num_layers):
+            self.add_module('denselayer%d' % (i + 1),
+                            _DenseLayer(num_input_features + i * growth_rate, growth_rate=growth_rate, bn_size=bn_size,
+                                        drop_rate=drop_rate))
+        self.num_input_features, self.growth_rate, self.num_layers = num_input_features, growth_rate, num_layers
+        self.out_channels = num_input_features + num_layers * growth_rate
+
+    def forward(self, init_features):
+        B, C0, H, W = init_features.shape
+        buf = getattr(init_features, 'feature_buffer', None)
+        if (buf is None or tuple(buf.shape) != (B, self.out_channels, H, W) or buf.dtype != init_features.dtype
+                or not buf.is_contiguous() or buf.data_ptr() != init_features.data_ptr()):
+            buf = torch.empty(B, self.out_channels, H, W, dtype=init_features.dtype, device=init_features.device)
+        feats = _Adopt.apply(init_features, buf)
+        for layer in self.values():
+            new = layer.conv2(layer.relu2(layer.norm2(layer.conv1(layer.relu1(layer.norm1(feats))))))
+            if layer.drop_rate > 0:
+                new = F.dropout(new, p=layer.drop_rate, training=self.training)
+            feats = _Append.apply(feats, new.to(buf.dtype), buf)
+        return feats
 
 
 class DenseNet(nn.Module):
@@ -52,8 +147,9 @@ class DenseNet(nn.Module):
     ``precision`` ('fp32' | 'bf16') for the AAConv2d kernels.  Unlike the reference, ``attn_params`` is not mutated."""
 
     def __init__(self, growth_rate=32, block_config=(6, 12, 24, 16), num_init_features=64, bn_size=4, drop_rate=0,
-                 num_classes=1000, attn_params=None, precision=None):
+                 num_classes=1000, attn_params=None, precision=None, feature_buffer=False, fused_prologue=False):
         super().__init__()
+        self.feature_buffer = bool(feature_buffer)
         attn = dict(attn_params) if attn_params is not None else None
         if len(block_config) == 4:    # ImageNet stem: /4 before the first block (:460-468)
             stem = [('conv0', nn.Conv2d(3, num_init_features, kernel_size=7, stride=2, padding=3, bias=False)),
@@ -69,12 +165,13 @@ class DenseNet(nn.Module):
         self.features = nn.Sequential(OrderedDict(stem))
         width = num_init_features
         for i, num_layers in enumerate(block_config):
-            self.features.add_module(f'denseblock{i + 1}', _DenseBlock(num_layers=num_layers, num_input_features=width,
-                                                                        bn_size=bn_size, growth_rate=growth_rate,
-                                                                        drop_rate=drop_rate))
+            block = (BufferedDenseBlock(num_layers, width, bn_size, growth_rate, drop_rate) if feature_buffer else
+                     _DenseBlock(num_layers=num_layers, num_input_features=width, bn_size=bn_size, growth_rate=growth_rate,
+                                 drop_rate=drop_rate))
+            self.features.add_module(f'denseblock{i + 1}', block)
             width += num_layers * growth_rate
             if i != len(block_config) - 1:
-                self.features.add_module(f'transition{i + 1}', transition(width, width // 2, attn, precision))
+                self.features.add_module(f'transition{i + 1}', transition(width, width // 2, attn, precision, fused_prologue))
                 width //= 2
             if attn is not None:      # every stage halves the map the next transition's attention sees (:491-493)
                 attn['input_dims'] = attn['input_dims'][0] // 2, attn['input_dims'][1] // 2
@@ -89,8 +186,20 @@ class DenseNet(nn.Module):
             elif isinstance(m, nn.Linear):
                 nn.init.constant_(m.bias, 0)
 
+    def _features(self, x):
+        if not self.feature_buffer:
+            return self.features(x)
+        mods = list(self.features.children())
+        for i, m in enumerate(mods):
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            if isinstance(m, AATransition) and isinstance(nxt, BufferedDenseBlock):
+                x = m(x, out_total=nxt.out_channels)      # the AAConv2d epilogues write into the next block's buffer
+            else:
+                x = m(x)
+        return x
+
     def forward(self, x):
-        f = F.relu(self.features(x), inplace=True)
+        f = F.relu(self._features(x), inplace=True)
         return self.classifier(F.adaptive_avg_pool2d(f, (1, 1)).flatten(1))
 
     def attn_layers(self):
@@ -98,8 +207,9 @@ class DenseNet(nn.Module):
         return [m for m in self.modules() if isinstance(m, AAConv2d)]
 
 
-def aadensenet121(num_classes=5, input_dims=(320, 320), precision=None):
-    """The model behind ``--model aadensenet121`` (chexpert.py:474-476); ``input_dims`` is the image size."""
+def aadensenet121(num_classes=5, input_dims=(320, 320), precision=None, feature_buffer=False, fused_prologue=False):
+    """The model behind ``--model aadensenet121`` (chexpert.py:474-476); ``input_dims`` is the image size.
+    ``feature_buffer`` / ``fused_prologue``: the B200 execution options of rows f3 / f1 (same parameters, same state_dict)."""
     return DenseNet(32, (6, 12, 24, 16), 64, num_classes=num_classes,
                     attn_params={'k': 0.2, 'v': 0.1, 'nh': 8, 'relative': True, 'input_dims': tuple(input_dims)},
-                    precision=precision)
+                    precision=precision, feature_buffer=feature_buffer, fused_prologue=fused_prologue)

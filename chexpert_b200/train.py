@@ -40,10 +40,11 @@ class TrainStep:
     """Owns model, loss kernel, optimizer, scheduler and (when world > 1) the gradient buckets."""
 
     def __init__(self, device, size=320, precision='bf16', lr=1e-4, raw_labels=True, bucket_mb=25.0, seed=0,
-                 autocast=True, channels_last=False, cuda_graph=False, graph_after=2):
+                 autocast=True, channels_last=False, cuda_graph=False, graph_after=2, buffered=False, fused_prologue=False):
         torch.manual_seed(seed)
         self.device = torch.device(device)
-        self.model = aadensenet121(5, (size, size), precision=precision).to(self.device)
+        self.model = aadensenet121(5, (size, size), precision=precision, feature_buffer=buffered,
+                                   fused_prologue=fused_prologue).to(self.device)
         if channels_last:
             self.model = self.model.to(memory_format=torch.channels_last)
         self.loss_fn = BCEWithLogitsLoss('train', raw_labels=raw_labels).to(self.device)

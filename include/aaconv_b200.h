@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define AACONV_ABI_VERSION 1
+#define AACONV_ABI_VERSION 2
 
 enum { AACONV_FP32 = 0, AACONV_BF16 = 1 };
 
@@ -66,6 +66,23 @@ typedef struct aaconv_param_grads {   /* any member may be NULL: that gradient i
   float* key_rel_w;
 } aaconv_param_grads;
 
+/* Optional I/O description of one call (NULL = the defaults: fp32 x / y, dense y, no fused prologue).  It lets the module sit
+ * inside the DenseNet the way north_star (4) and SURVEY.md section 8 rows f1 / f3 ask:
+ *   x_dtype / y_dtype   element type of x (and dx) / of y: AACONV_FP32 or AACONV_BF16 (bf16 activations under autocast);
+ *                        dy and the parameters stay fp32.
+ *   y_batch_stride      elements between consecutive samples of y; 0 = Cout*H*W.  With Ctot*H*W the call writes the first Cout
+ *                        channels of a wider (B,Ctot,H,W) feature buffer -- the pre-allocated DenseBlock buffer that replaces
+ *                        torch.cat (torchvision densenet.py:48,120-124; attn_aug_conv.py:479-482) -- straight from the epilogues.
+ *   fuse_in_relu        1: x is the INPUT of the Transition's InstanceNorm2d (affine=False, eps) + ReLU (attn_aug_conv.py:438-439);
+ *                        forward computes the per-(b,c) mean / rstd and applies relu((x-mean)*rstd) while packing the GEMM operand,
+ *                        backward returns the gradient with respect to that raw x (ReLU mask + InstanceNorm adjoint fused). */
+typedef struct aaconv_io {
+  int32_t x_dtype, y_dtype;
+  int64_t y_batch_stride;
+  int32_t fuse_in_relu;
+  float in_eps;
+} aaconv_io;
+
 int aaconv_abi_version(void);
 const char* aaconv_last_error(void);          /* thread-local text of the last failing call */
 int aaconv_validate(const aaconv_dims* d, int precision);
@@ -74,6 +91,8 @@ int aaconv_validate(const aaconv_dims* d, int precision);
 size_t aaconv_saved_bytes(const aaconv_dims* d, int precision);     /* forward -> backward state       */
 size_t aaconv_scratch_bytes(const aaconv_dims* d, int precision, int want_weights);  /* transient, either direction;
                                                            want_weights: forward will also fill `weights` */
+size_t aaconv_saved_bytes_io(const aaconv_dims* d, int precision, const aaconv_io* io);
+size_t aaconv_scratch_bytes_io(const aaconv_dims* d, int precision, const aaconv_io* io);
 
 /* Byte offsets of the named blocks inside the saved buffer (for tests and the visualise path).
  * names: "q","k","v","o","lse" (fp32 path: q,k (B,nh,L,dkh) with q pre-scaled; v,o (B,nh,L,dvh);
@@ -94,6 +113,13 @@ int aaconv_forward(const aaconv_dims* d, int precision, const float* x, const aa
 int aaconv_backward(const aaconv_dims* d, int precision, const float* x, const aaconv_params* p,
                     const float* dy, void* saved, void* scratch,
                     float* dx, const aaconv_param_grads* g, void* stream);
+
+/* The same two calls with an I/O description (see aaconv_io): x / dx in io->x_dtype, y in io->y_dtype at io->y_batch_stride,
+ * optional fused InstanceNorm + ReLU prologue.  dy stays fp32 dense (B,Cout,H,W).  Buffers sized by the *_bytes_io() queries. */
+int aaconv_forward_io(const aaconv_dims* d, int precision, const aaconv_io* io, const void* x, const aaconv_params* p,
+                      void* y, float* weights, void* saved, void* scratch, void* stream);
+int aaconv_backward_io(const aaconv_dims* d, int precision, const aaconv_io* io, const void* x, const aaconv_params* p,
+                       const float* dy, void* saved, void* scratch, void* dx, const aaconv_param_grads* g, void* stream);
 
 /* Loss: replaces nn.BCEWithLogitsLoss(reduction='none')(z,t) [.sum(1).mean(0)]  (chexpert.py:530,160,205).
  *   z (B,C) logits.  Targets are either

@@ -3,7 +3,7 @@ import sys, torch
 sys.path.insert(0, '/root/repo')
 from chexpert_b200.train import TrainStep, synthetic_batch
 cl = '--cl' in sys.argv
-ts = TrainStep('cuda', precision='bf16', channels_last=cl)
+ts = TrainStep('cuda', precision='bf16', channels_last=cl, buffered='--buf' in sys.argv, fused_prologue='--fused' in sys.argv)
 x, t = synthetic_batch(16, device='cuda')
 if cl: x = x.contiguous(memory_format=torch.channels_last)
 for _ in range(3): ts(x, t)
@@ -12,4 +12,4 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(2): ts(x, t)
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=45, max_name_column_width=70))
+print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=60, max_name_column_width=90))
