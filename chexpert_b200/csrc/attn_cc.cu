@@ -13,6 +13,7 @@
 // rings running on a global tile counter); the rules that keeps their mbarrier parity waits exact are next to cb_plan.
 // Reference rows a3-a8 (attn_aug_conv.py:75-91) and their adjoint; layouts as in attn_tc_bwd.cu.
 #include <algorithm>
+#include <cstdlib>
 #include "tc_common.cuh"
 #include "bf16_path.cuh"
 
@@ -165,12 +166,17 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 // ================================================================================================
 // forward
 // ================================================================================================
+// Measured A/B on B200 (T1, B = 16; profiles/r02_attn_ab.md): 128-key tiles with three 128-column score slots and two
+// tcgen05.ld in flight per half tile (this configuration) 132 us; 64-key tiles with six 64-column slots (two per warpgroup)
+// 142 us; four warpgroups (96 registers) 140 us; S' read in four software-pipelined 32-column chunks 136 us.  The kernel is
+// bound by the per-warp dependent-issue rate (ncu: issue slots 61 % busy, MUFU pipe 67 %, 7.7 instructions per exponential),
+// not by TMEM latency, slot count or the number of MMA k-steps (2 k-steps instead of 7: 127 us).
 constexpr int CF_BM = 128, CF_BN = 128, CF_SLOTS = 3;
 // three softmax warpgroups (global tile t -> warpgroup t % 3), one TMA warp, one score-MMA issuer (+TMEM alloc)
 constexpr int CF_NWG = 3, CF_W_TMA = 4 * CF_NWG, CF_W_S = CF_W_TMA + 1, CF_THREADS = 32 * (CF_W_S + 1);
 template <int KATOMS> struct CfStages { static constexpr int value = KATOMS >= 3 ? 3 : 4; };
-// Qa buffers in TMEM: two when they fit next to the three 128-column score slots
-template <int KATOMS> struct CfQBuf { static constexpr int value = (2 * KATOMS * 32 + CF_SLOTS * 128 <= 512) ? 2 : 1; };
+// Qa buffers in TMEM: two when they fit next to the score slots
+template <int KATOMS> struct CfQBuf { static constexpr int value = (2 * KATOMS * 32 + CF_SLOTS * CF_BN <= 512) ? 2 : 1; };
 
 template <int KATOMS, int DVH>
 struct __align__(1024) CfSmem {
@@ -612,66 +618,63 @@ __device__ __forceinline__ void cb_grad_issuer(Smem& sm, uint32_t tmem, CbPlan p
   }
 }
 
-// one key tile of the dQa kernel: dS = 2^S' (dO.v[k] - delta) for this thread's query row, packed to bf16
-template <int DVH, bool TAIL>
-__device__ __forceinline__ void dq_cc_tile(const uint32_t (&rs)[2][32], uint32_t (&pd)[32], uint32_t vt, int nvalid,
-                                           const float (&go)[DVH], float ndelta) {
+// 32 keys (chunk C of a 64-key tile) of the dQa kernel: dS = 2^S' (dO.v[k] - delta) for this thread's query row, packed to bf16
+template <int DVH, bool TAIL, int C>
+__device__ __forceinline__ void dq_cc_chunk(const uint32_t (&rs)[32], uint32_t (&pd)[32], uint32_t vt, int nvalid,
+                                            const float (&go)[DVH], float ndelta) {
 #pragma unroll
-  for (int c = 0; c < 2; ++c)
+  for (int i = 0; i < 32; i += 4) {
+    float vv[4 * DVH];
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      float vv[4 * DVH];
-#pragma unroll
-      for (int u = 0; u < DVH; ++u) {
-        const float4 t4 = lds128(vt + ((c * 32 + i) * DVH + 4 * u) * 4);
-        vv[4 * u] = t4.x; vv[4 * u + 1] = t4.y; vv[4 * u + 2] = t4.z; vv[4 * u + 3] = t4.w;
-      }
-      float ds[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float dp = ndelta;
-#pragma unroll
-        for (int e = 0; e < DVH; ++e) dp = fmaf(go[e], vv[u * DVH + e], dp);
-        ds[u] = tc::ex2_mixed(__uint_as_float(rs[c][i + u]), u) * dp;
-        if (TAIL && c * 32 + i + u >= nvalid) ds[u] = 0.f;     // zero-filled keys past L
-      }
-      pd[c * 16 + (i >> 1)] = tc::pack_bf16x2(ds[0], ds[1]);
-      pd[c * 16 + (i >> 1) + 1] = tc::pack_bf16x2(ds[2], ds[3]);
+    for (int u = 0; u < DVH; ++u) {
+      const float4 t4 = lds128(vt + ((C * 32 + i) * DVH + 4 * u) * 4);
+      vv[4 * u] = t4.x; vv[4 * u + 1] = t4.y; vv[4 * u + 2] = t4.z; vv[4 * u + 3] = t4.w;
     }
+    float ds[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float dp = ndelta;
+#pragma unroll
+      for (int e = 0; e < DVH; ++e) dp = fmaf(go[e], vv[u * DVH + e], dp);
+      ds[u] = tc::ex2_mixed(__uint_as_float(rs[i + u]), u) * dp;
+      if (TAIL && C * 32 + i + u >= nvalid) ds[u] = 0.f;     // zero-filled keys past L
+    }
+    pd[C * 16 + (i >> 1)] = tc::pack_bf16x2(ds[0], ds[1]);
+    pd[C * 16 + (i >> 1) + 1] = tc::pack_bf16x2(ds[2], ds[3]);
+  }
 }
 
-// one query tile of the dK/dV kernel for this thread's key row: p = 2^S'^T, dV += p dO[q] (registers), dS^T = p (dO[q].v - delta[q])
-template <int DVH, bool TAIL>
-__device__ __forceinline__ void dkv_cc_tile(const uint32_t (&rs)[2][32], uint32_t (&pd)[32], uint32_t dot, uint32_t dlt, int nvalid,
-                                            const float (&vk)[DVH], float (&dvacc)[DVH]) {
+// 32 queries (chunk C of a 64-query tile) of the dK/dV kernel for this thread's key row: p = 2^S'^T, dV += p dO[q] (registers),
+// dS^T = p (dO[q].v - delta[q])
+template <int DVH, bool TAIL, int C>
+__device__ __forceinline__ void dkv_cc_chunk(const uint32_t (&rs)[32], uint32_t (&pd)[32], uint32_t dot, uint32_t dlt, int nvalid,
+                                             const float (&vk)[DVH], float (&dvacc)[DVH]) {
 #pragma unroll
-  for (int c = 0; c < 2; ++c)
+  for (int i = 0; i < 32; i += 4) {
+    float gg[4 * DVH];
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      float gg[4 * DVH];
-#pragma unroll
-      for (int u = 0; u < DVH; ++u) {
-        const float4 t4 = lds128(dot + ((c * 32 + i) * DVH + 4 * u) * 4);
-        gg[4 * u] = t4.x; gg[4 * u + 1] = t4.y; gg[4 * u + 2] = t4.z; gg[4 * u + 3] = t4.w;
-      }
-      const float4 dl = lds128(dlt + (c * 32 + i) * 4);
-      const float dls[4] = {dl.x, dl.y, dl.z, dl.w};
-      float ds[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float dp = -dls[u];
-#pragma unroll
-        for (int e = 0; e < DVH; ++e) dp = fmaf(gg[u * DVH + e], vk[e], dp);
-        float p = tc::ex2_mixed(__uint_as_float(rs[c][i + u]), u);
-        const bool dead = TAIL && c * 32 + i + u >= nvalid;    // zero-filled queries past L: the side tile holds stale data there
-        if (dead) { p = 0.f; dp = 0.f; }
-#pragma unroll
-        for (int e = 0; e < DVH; ++e) dvacc[e] = fmaf(p, dead ? 0.f : gg[u * DVH + e], dvacc[e]);
-        ds[u] = p * dp;
-      }
-      pd[c * 16 + (i >> 1)] = tc::pack_bf16x2(ds[0], ds[1]);
-      pd[c * 16 + (i >> 1) + 1] = tc::pack_bf16x2(ds[2], ds[3]);
+    for (int u = 0; u < DVH; ++u) {
+      const float4 t4 = lds128(dot + ((C * 32 + i) * DVH + 4 * u) * 4);
+      gg[4 * u] = t4.x; gg[4 * u + 1] = t4.y; gg[4 * u + 2] = t4.z; gg[4 * u + 3] = t4.w;
     }
+    const float4 dl = lds128(dlt + (C * 32 + i) * 4);
+    const float dls[4] = {dl.x, dl.y, dl.z, dl.w};
+    float ds[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float dp = -dls[u];
+#pragma unroll
+      for (int e = 0; e < DVH; ++e) dp = fmaf(gg[u * DVH + e], vk[e], dp);
+      float p = tc::ex2_mixed(__uint_as_float(rs[i + u]), u);
+      const bool dead = TAIL && C * 32 + i + u >= nvalid;    // zero-filled queries past L: the side tile holds stale data there
+      if (dead) { p = 0.f; dp = 0.f; }
+#pragma unroll
+      for (int e = 0; e < DVH; ++e) dvacc[e] = fmaf(p, dead ? 0.f : gg[u * DVH + e], dvacc[e]);
+      ds[u] = p * dp;
+    }
+    pd[C * 16 + (i >> 1)] = tc::pack_bf16x2(ds[0], ds[1]);
+    pd[C * 16 + (i >> 1) + 1] = tc::pack_bf16x2(ds[2], ds[3]);
+  }
 }
 
 // ---- query-stationary: dQa ------------------------------------------------------------------------
@@ -748,19 +751,31 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dq_cc_kernel(
         tc::mbar_wait(&sm.bar_s_full[slot], rsl.ph);
         tc::tc_fence_after();
         TL_STAMP(tw, 8, it * ntiles + j);
+        // S' leaves TMEM in two 32-column chunks: the second load is in flight while the first chunk is exponentiated
         tc::tmem_ld_x32(tslot, rs[0]);
-        tc::tmem_ld_x32(tslot + 32, rs[1]);
         tc::tmem_ld_wait();
+        tc::tmem_ld_landed(rs[0]);
+        tc::tmem_ld_x32(tslot + 32, rs[1]);
         TL_STAMP(tw, 9, it * ntiles + j);
         const uint32_t vt = smem_u32(sm.side[st]);
-        if (dbg & 8) {
+        if (dbg & 9) {
+          tc::tmem_ld_wait();
+          tc::tmem_ld_landed(rs[1]);
+          if (dbg & 8) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) pd[i] = rs[0][i];
-        } else if (dbg & 1) {
+            for (int i = 0; i < 32; ++i) pd[i] = rs[0][i];
+          } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) pd[i] = tc::pack_bf16x2(__uint_as_float(rs[0][i]) * ndelta, __uint_as_float(rs[1][i]) * go[0]);
-        } else if (tail) dq_cc_tile<DVH, true>(rs, pd, vt, nvalid, go, ndelta);
-        else dq_cc_tile<DVH, false>(rs, pd, vt, nvalid, go, ndelta);
+            for (int i = 0; i < 32; ++i) pd[i] = tc::pack_bf16x2(__uint_as_float(rs[0][i]) * ndelta, __uint_as_float(rs[1][i]) * go[0]);
+          }
+        } else {
+          if (tail) dq_cc_chunk<DVH, true, 0>(rs[0], pd, vt, nvalid, go, ndelta);
+          else dq_cc_chunk<DVH, false, 0>(rs[0], pd, vt, nvalid, go, ndelta);
+          tc::tmem_ld_wait();
+          tc::tmem_ld_landed(rs[1]);
+          if (tail) dq_cc_chunk<DVH, true, 1>(rs[1], pd, vt, nvalid, go, ndelta);
+          else dq_cc_chunk<DVH, false, 1>(rs[1], pd, vt, nvalid, go, ndelta);
+        }
         TL_STAMP(tw, 10, it * ntiles + j);
         tc::tmem_st_x32(tslot, pd);                    // dS (bf16) over S'[0,32): all of S' is in registers
         tc::tmem_st_wait();
@@ -901,11 +916,16 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
         tc::mbar_wait(&sm.bar_s_full[slot], rsl.ph);
         tc::tc_fence_after();
         tc::tmem_ld_x32(tslot, rs[0]);
-        tc::tmem_ld_x32(tslot + 32, rs[1]);
         tc::tmem_ld_wait();
+        tc::tmem_ld_landed(rs[0]);
+        tc::tmem_ld_x32(tslot + 32, rs[1]);           // in flight under the first chunk's math
         const uint32_t dot = smem_u32(sm.side[st]), dlt = dot + CB_BN * DVH * 4;
-        if (tail) dkv_cc_tile<DVH, true>(rs, pd, dot, dlt, nvalid, vk, dvacc);
-        else dkv_cc_tile<DVH, false>(rs, pd, dot, dlt, nvalid, vk, dvacc);
+        if (tail) dkv_cc_chunk<DVH, true, 0>(rs[0], pd, dot, dlt, nvalid, vk, dvacc);
+        else dkv_cc_chunk<DVH, false, 0>(rs[0], pd, dot, dlt, nvalid, vk, dvacc);
+        tc::tmem_ld_wait();
+        tc::tmem_ld_landed(rs[1]);
+        if (tail) dkv_cc_chunk<DVH, true, 1>(rs[1], pd, dot, dlt, nvalid, vk, dvacc);
+        else dkv_cc_chunk<DVH, false, 1>(rs[1], pd, dot, dlt, nvalid, vk, dvacc);
         tc::tmem_st_x32(tslot, pd);                    // dS^T (bf16) over S'^T[0,32): all of S'^T is in registers
         tc::tmem_st_wait();
         tc::tc_fence_before();
@@ -1045,9 +1065,16 @@ int cc_attn_supported(const Dims& d) {
   return 0;
 }
 
+// ablation (tools/attn_ablate.py; results are WRONG): AACONV_ABL_NKS = score k-steps, AACONV_ABL_NQ = width of the dQa accumulator
+static AugLayout ablated(AugLayout a) {
+  if (const char* e = getenv("AACONV_ABL_NKS")) a.C1 = 16 * atoi(e);
+  if (const char* e = getenv("AACONV_ABL_NQ")) a.NQ = atoi(e);
+  return a;
+}
+
 int cc_attn_fwd(const Dims& d, const void* qa, const void* ka, const float* v, float* o, float* lse, cudaStream_t st) {
   AACONV_TRY(cc_attn_supported(d));
-  const AugLayout a = aug_layout(d);
+  const AugLayout a = ablated(aug_layout(d));
   const int K = a.KP / 64;
   if (d.dvh == 1) {
     if (K == 1) return launch_fwd_cc<1, 1>(d, a, qa, ka, v, o, lse, st);
@@ -1062,7 +1089,7 @@ int cc_attn_fwd(const Dims& d, const void* qa, const void* ka, const float* v, f
 int cc_attn_bwd(const Dims& d, const void* qa, const void* ka, const float* v, const float* d_o, const float* delta, float* dqa,
                 float* dk, float* dv, void* dqkvh, int KPq, cudaStream_t st) {
   AACONV_TRY(cc_attn_supported(d));
-  const AugLayout a = aug_layout(d);
+  const AugLayout a = ablated(aug_layout(d));
   const int K = a.KP / 64;
   if (d.dvh == 1) {
     if (K == 1) return launch_bwd_cc<1, 1>(d, a, qa, ka, v, d_o, delta, dqa, dk, dv, dqkvh, KPq, st);

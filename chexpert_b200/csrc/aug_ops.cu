@@ -274,6 +274,7 @@ __global__ void aug_patch_bwd_kernel(const float* __restrict__ lse, const float*
   delta_out[row] = delta;
 }
 
+constexpr int OBP_THREADS = 128;   // 25600 pixels at Transition 1 -> 200 CTAs (256 threads left 48 of 148 SMs idle)
 // ------------------------------------------------------------------------------------------------
 // out_proj adjoint + backward patch of Qa in ONE pass over the pixels (small value widths: dv = NH * DVH <= 16)
 //   dO[b,n,l,e] = sum_c Wout[c, n*dvh+e] dy[b, Cc+c, l]        (attn_aug_conv.py:92 adjoint, data)
@@ -284,14 +285,14 @@ __global__ void aug_patch_bwd_kernel(const float* __restrict__ lse, const float*
 // work is 25600 pixels x 8 channels.
 // ------------------------------------------------------------------------------------------------
 template <int NH, int DVH>
-__global__ void __launch_bounds__(256) out_bwd_patch_kernel(const float* __restrict__ dy, const float* __restrict__ o,
+__global__ void __launch_bounds__(OBP_THREADS) out_bwd_patch_kernel(const float* __restrict__ dy, const float* __restrict__ o,
                                                             const float* __restrict__ lse, const float* __restrict__ wout,
                                                             float* __restrict__ d_o, float* __restrict__ delta_out,
                                                             bf16* __restrict__ qa, float* __restrict__ wpartial, int B, int L,
                                                             int Ctot, int coff, int KD, int C1, int KP) {
   constexpr int DV = NH * DVH;
   __shared__ float ws[DV * DV];
-  __shared__ float red[8][DV * DV];
+  __shared__ float red[OBP_THREADS / 32][DV * DV];
   for (int i = threadIdx.x; i < DV * DV; i += blockDim.x) ws[i] = wout[i];
   __syncthreads();
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -345,10 +346,87 @@ __global__ void __launch_bounds__(256) out_bwd_patch_kernel(const float* __restr
     for (int i = threadIdx.x; i < DV * DV; i += blockDim.x) {
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) t += red[w][i];
+      for (int w = 0; w < OBP_THREADS / 32; ++w) t += red[w][i];
       wpartial[(size_t)blockIdx.x * DV * DV + i] = t;
     }
   }
+}
+
+// head combine + out_proj + concat write (attn_aug_conv.py:89-95): y[b, Cc + n, l] = sum_k Wout[n, k] o[b, k / dvh, l, k % dvh].
+// One thread per (output channel, pixel), consecutive threads = consecutive pixels: coalesced o reads and y writes, the Wout row
+// is a shared-memory broadcast.  (The generic 64 x 64-tiled FFMA GEMM spent 10.6 us on these 25600 x 8 x 8 MACs.)
+__global__ void __launch_bounds__(256) out_proj_fwd_kernel(const float* __restrict__ o, const float* __restrict__ wout, void* __restrict__ y,
+                                                           int BL, int L, int nh, int dvh, int coff, long long y_bs, int y_bf16) {
+  extern __shared__ float ws[];
+  const int dv = nh * dvh;
+  for (int i = threadIdx.x; i < dv * dv; i += blockDim.x) ws[i] = wout[i];
+  __syncthreads();
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)BL * dv) return;
+  const int n = (int)(t / BL), pix = (int)(t - (size_t)n * BL);
+  const int b = pix / L, l = pix - b * L;
+  const float* wr = ws + n * dv;
+  float acc = 0.f;
+  for (int h = 0; h < nh; ++h) {
+    const float* op = o + ((size_t)(b * nh + h) * L + l) * dvh;
+    for (int e = 0; e < dvh; ++e) acc = fmaf(wr[h * dvh + e], __ldg(op + e), acc);
+  }
+  store_y(y, (size_t)b * y_bs + (size_t)(coff + n) * L + l, acc, y_bf16);
+}
+
+// Any value width (dv/nh <= 14; Transition 2 / 3: dvh = 3 / 6): out_proj adjoint (data part) + the Qa patch, one thread per
+// (batch, head, pixel) row.  Replaces out_bwd_data_f32 (a 64 x 64-tiled FFMA GEMM whose M x N = pixels x dv output gave it
+// 25-100 CTAs with strided gathers: 76 / 171 us at Transition 2 / 3) and aug_patch_bwd.  dWout stays a split-K GEMM.
+__global__ void __launch_bounds__(256) out_bwd_data_patch_kernel(const float* __restrict__ dy, const float* __restrict__ o,
+                                                                 const float* __restrict__ lse, const float* __restrict__ wout,
+                                                                 float* __restrict__ d_o, float* __restrict__ delta_out,
+                                                                 bf16* __restrict__ qa, int B, int L, int nh, int dvh, int Ctot, int coff,
+                                                                 int KD, int C1, int KP) {
+  // block = 32 consecutive pixels x nh heads (warp = one head: coalesced row writes); dy of the 32 pixels is staged in shared
+  // memory once (coalesced along the pixels) instead of dv dependent global loads per thread
+  extern __shared__ float ws[];                     // Wout (dv x dv), row c = output channel of out_proj; then dys[dv][33]
+  const int dv = nh * dvh;
+  float* dys = ws + dv * dv;
+  const int pix0 = blockIdx.x * 32, npix = B * L;
+  for (int i = threadIdx.x; i < dv * dv; i += blockDim.x) ws[i] = wout[i];
+  for (int i = threadIdx.x; i < dv * 32; i += blockDim.x) {
+    const int c = i >> 5, pp = i & 31, pix = pix0 + pp;
+    float v = 0.f;
+    if (pix < npix) { const int b = pix / L, l = pix - b * L; v = __ldg(dy + ((size_t)b * Ctot + coff + c) * L + l); }
+    dys[c * 33 + pp] = v;
+  }
+  __syncthreads();
+  const int pp = threadIdx.x & 31, h = threadIdx.x >> 5, pix = pix0 + pp;
+  if (pix >= npix || h >= nh) return;
+  const int b = pix / L, l = pix - b * L;
+  const size_t row = (size_t)(b * nh + h) * L + l;
+  float g[14];
+#pragma unroll
+  for (int e = 0; e < 14; ++e) g[e] = 0.f;
+  for (int c = 0; c < dv; ++c) {
+    const float v = dys[c * 33 + pp];
+    const float* wr = ws + c * dv + h * dvh;
+#pragma unroll
+    for (int e = 0; e < 14; ++e)
+      if (e < dvh) g[e] = fmaf(wr[e], v, g[e]);
+  }
+  bf16* dst = qa + row * KP;
+  bf16 hi, lo;
+  split_bf16(-lse[row] * LOG2E, hi, lo);
+  dst[KD] = hi;
+  dst[KD + 1] = lo;
+  float delta = 0.f;
+#pragma unroll
+  for (int e = 0; e < 14; ++e)
+    if (e < dvh) {
+      d_o[row * dvh + e] = g[e];
+      delta = fmaf(g[e], o[row * dvh + e], delta);
+      dst[C1 + e] = __float2bfloat16(g[e]);
+    }
+  split_bf16(-delta, hi, lo);
+  dst[C1 + dvh] = hi;
+  dst[C1 + dvh + 1] = lo;
+  delta_out[row] = delta;
 }
 
 // block = 32 outputs x 8 slices of the block partials; slices, then the 8 slice sums, are added in a fixed order
@@ -484,20 +562,40 @@ int aug_weights(const Dims& d, const void* qa, const void* ka, const float* lse,
   return 0;
 }
 
+int out_bwd_data_patch(const Dims& d, const float* dy, const float* o, const float* lse, const float* wout, float* d_o, float* delta,
+                       void* qa, cudaStream_t st) {
+  if (d.dvh > 14 || d.nh > 8) return fail(AACONV_E_UNSUPPORTED, "out_bwd_data_patch: dv/nh <= 14, nh <= 8");
+  const AugLayout a = aug_layout(d);
+  const size_t smem = sizeof(float) * ((size_t)d.dv * d.dv + (size_t)d.dv * 33);
+  if (smem > 48 * 1024) AACONV_CUDA_OK(cudaFuncSetAttribute(out_bwd_data_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  out_bwd_data_patch_kernel<<<cdiv(d.B * d.L, 32), 32 * d.nh, smem, AACONV_ST(st)>>>(dy, o, lse, wout, d_o, delta, static_cast<bf16*>(qa), d.B, d.L,
+                                                                            d.nh, d.dvh, d.Cout, d.Cc, a.KD, a.C1, a.KP);
+  AACONV_LAUNCH_OK("out_bwd_data_patch");
+  return 0;
+}
+
+int out_proj_fwd(const Dims& d, const float* o, const float* wout, void* y, cudaStream_t st) {
+  const size_t n = (size_t)d.B * d.L * d.dv, smem = sizeof(float) * d.dv * d.dv;
+  if (smem > 48 * 1024) AACONV_CUDA_OK(cudaFuncSetAttribute(out_proj_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  out_proj_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, smem, AACONV_ST(st)>>>(o, wout, y, d.B * d.L, d.L, d.nh, d.dvh, d.Cc, d.y_bs, d.y_bf16);
+  AACONV_LAUNCH_OK("out_proj_fwd");
+  return 0;
+}
+
 int out_bwd_patch_supported(const Dims& d) { return (d.nh == 8 && (d.dvh == 1 || d.dvh == 2)) ? 0 : AACONV_E_UNSUPPORTED; }
-size_t out_bwd_patch_partial_floats(const Dims& d) { return (size_t)cdiv(d.B * d.L, 256) * d.dv * d.dv; }
+size_t out_bwd_patch_partial_floats(const Dims& d) { return (size_t)cdiv(d.B * d.L, OBP_THREADS) * d.dv * d.dv; }
 
 int out_bwd_patch(const Dims& d, const float* dy, const float* o, const float* lse, const float* wout, float* d_o, float* delta,
                   void* qa, float* dw, float* partial, cudaStream_t st) {
   if (out_bwd_patch_supported(d)) return fail(AACONV_E_UNSUPPORTED, "out_bwd_patch: nh = 8, dv/nh <= 2 only");
   const AugLayout a = aug_layout(d);
-  const int grid = cdiv(d.B * d.L, 256);
+  const int grid = cdiv(d.B * d.L, OBP_THREADS);
   float* wp = dw ? partial : nullptr;
   if (d.dvh == 1)
-    out_bwd_patch_kernel<8, 1><<<grid, 256, 0, AACONV_ST(st)>>>(dy, o, lse, wout, d_o, delta, static_cast<bf16*>(qa), wp, d.B, d.L, d.Cout, d.Cc,
+    out_bwd_patch_kernel<8, 1><<<grid, OBP_THREADS, 0, AACONV_ST(st)>>>(dy, o, lse, wout, d_o, delta, static_cast<bf16*>(qa), wp, d.B, d.L, d.Cout, d.Cc,
                                                      a.KD, a.C1, a.KP);
   else
-    out_bwd_patch_kernel<8, 2><<<grid, 256, 0, AACONV_ST(st)>>>(dy, o, lse, wout, d_o, delta, static_cast<bf16*>(qa), wp, d.B, d.L, d.Cout, d.Cc,
+    out_bwd_patch_kernel<8, 2><<<grid, OBP_THREADS, 0, AACONV_ST(st)>>>(dy, o, lse, wout, d_o, delta, static_cast<bf16*>(qa), wp, d.B, d.L, d.Cout, d.Cc,
                                                      a.KD, a.C1, a.KP);
   AACONV_LAUNCH_OK("out_bwd_patch");
   if (dw) {

@@ -102,7 +102,7 @@ int bf16_forward(const Dims& d, const void* xin, const aaconv_params* p, void* y
   else AACONV_TRY(tc_attn_fwd(d, sa.qa, sa.ka, o, lse, st));
   // visualise path only: the bf16 kernels' own probabilities -- their bf16 operands, their lse (attn_aug_conv.py:87)
   if (weights) AACONV_TRY(aug_weights(d, sa.qa, sa.ka, lse, weights, st));
-  AACONV_TRY(f32_out_fwd(d, o, p->out_w, y, st));
+  AACONV_TRY(out_proj_fwd(d, o, p->out_w, y, st));
   return 0;
 }
 
@@ -129,9 +129,9 @@ int bf16_backward(const Dims& d, const void* xin, const aaconv_params* p, const 
   // run backward again
   if (out_bwd_patch_supported(d) == 0) {     // out_proj adjoint and the patch in one pass over the pixels
     AACONV_TRY(out_bwd_patch(d, dy, o, lse, p->out_w, w.d_o, w.delta, sa.qa, g->out_w, w.partial, st));
-  } else {
-    AACONV_TRY(f32_out_bwd(d, dy, o, p->out_w, w.d_o, g->out_w, w.partial, st));
-    AACONV_TRY(aug_patch_bwd(d, lse, w.d_o, o, sa.qa, w.delta, st));
+  } else {                                   // wider values (Transition 2 / 3): data part + patch fused, dWout as a split-K GEMM
+    AACONV_TRY(out_bwd_data_patch(d, dy, o, lse, p->out_w, w.d_o, w.delta, sa.qa, st));
+    AACONV_TRY(f32_out_bwd_weight(d, dy, o, g->out_w, w.partial, st));
   }
   // fast path: the attention-backward kernels write dq*scale, dk, dv as bf16 straight into the packed (B*L, KPq)
   // operand of the projection dgrad/wgrad GEMMs; its padding columns must be finite (they meet zero weights)

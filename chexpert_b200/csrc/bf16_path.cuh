@@ -25,6 +25,10 @@ int out_bwd_patch_supported(const Dims& d);
 size_t out_bwd_patch_partial_floats(const Dims& d);
 int out_bwd_patch(const Dims& d, const float* dy, const float* o, const float* lse, const float* wout, float* d_o, float* delta,
                   void* qa, float* dw, float* partial, cudaStream_t st);
+int out_proj_fwd(const Dims& d, const float* o, const float* wout, void* y, cudaStream_t st);   // attention channels of y
+// any value width: data part of the out_proj adjoint + the patch (dWout: f32_out_bwd_weight)
+int out_bwd_data_patch(const Dims& d, const float* dy, const float* o, const float* lse, const float* wout, float* d_o, float* delta,
+                       void* qa, cudaStream_t st);
 int rel_bwd_supported(const Dims& d);
 size_t rel_bwd_partial_floats(const Dims& d);
 int rel_bwd(const Dims& d, const float* dqa, const float* q, const float* krw, const float* krh, float* dq, void* dqkvh,

@@ -12,7 +12,8 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ['api.cu', 'runtime.cu', 'prologue.cu', 'fp32_gemms.cu', 'fp32_attn.cu', 'fp32_path.cu', 'bce.cu', 'eval_ops.cu', 'bf16_path.cu', 'tc_host.cu', 'aug_ops.cu', 'attn_tc.cu', 'attn_cc.cu', 'attn_tc_bwd.cu', 'gemm_tc.cu']
-LIB = os.path.join(HERE, 'libaaconv_b200.so')
+LIB = os.path.join(HERE, os.environ.get('AACONV_BUILD_NAME', 'libaaconv_b200.so'))
+EXTRA = os.environ.get('AACONV_BUILD_FLAGS', '').split()     # experiment variants: AACONV_BUILD_NAME=libx.so AACONV_BUILD_FLAGS='-DAACONV_CF_NWG=4'
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC', '--use_fast_math=false', '-Xptxas', '-v']
@@ -30,17 +31,18 @@ def _digest():
 
 
 def build(force=False, verbose=True):
-    stamp = os.path.join(HERE, 'build', 'stamp')
+    bdir = 'build' if not EXTRA else 'build_' + os.path.basename(LIB)
+    stamp = os.path.join(HERE, bdir, 'stamp')
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
-    os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
+    os.makedirs(os.path.join(HERE, bdir), exist_ok=True)
 
     def cc(src):
-        obj = os.path.join(HERE, 'build', src.replace('.cu', '.o'))
-        cmd = [NVCC, *FLAGS, '-c', os.path.join(HERE, src), '-o', obj]
+        obj = os.path.join(HERE, bdir, src.replace('.cu', '.o'))
+        cmd = [NVCC, *FLAGS, *EXTRA, '-c', os.path.join(HERE, src), '-o', obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        log = os.path.join(HERE, 'build', src + '.log')
+        log = os.path.join(HERE, bdir, src + '.log')
         open(log, 'w').write(r.stdout + r.stderr)
         if r.returncode:
             raise RuntimeError(f'nvcc failed for {src}:\n{r.stdout}\n{r.stderr}')

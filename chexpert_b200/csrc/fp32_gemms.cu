@@ -180,6 +180,10 @@ int f32_out_bwd(const Dims& d, const float* dy, const float* o, const float* w, 
   p.M = d.B * d.L; p.N = d.dv; p.K = d.dv; p.k_chunk = p.K;
   p.dy = dy; p.w = w; p.d_o = d_o; p.L = d.L; p.nh = d.nh; p.dvh = d.dvh; p.Ctot = d.Cout; p.coff = d.Cc;
   AACONV_TRY(launch_simt_gemm(p, 1, st, "out_bwd_data_f32"));
+  return f32_out_bwd_weight(d, dy, o, dw, partial, st);
+}
+
+int f32_out_bwd_weight(const Dims& d, const float* dy, const float* o, float* dw, float* partial, cudaStream_t st) {
   if (dw) {
     OutBwdWeightP q;
     q.M = d.dv; q.N = d.dv; q.K = d.B * d.L;

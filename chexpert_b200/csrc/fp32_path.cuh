@@ -11,6 +11,7 @@ int f32_qkv_fwd(const Dims& d, const float* x, const float* w, float* q, float* 
 int f32_out_fwd(const Dims& d, const float* o, const float* w, void* y, cudaStream_t st);
 int f32_out_bwd(const Dims& d, const float* dy, const float* o, const float* w, float* d_o, float* dw,
                 float* partial, cudaStream_t st);
+int f32_out_bwd_weight(const Dims& d, const float* dy, const float* o, float* dw, float* partial, cudaStream_t st);
 int f32_qkv_bwd(const Dims& d, const float* x, const float* w, const float* dq, const float* dk,
                 const float* dv, float* dw, float* dx, int dx_accumulate, float* partial, cudaStream_t st);
 int f32_conv_bwd(const Dims& d, const float* x, const float* w, const float* dy, float* dx, float* dw,
