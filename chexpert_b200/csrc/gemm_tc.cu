@@ -21,7 +21,8 @@ constexpr int PG_THREADS = 192;     // warps 0-3 epilogue, warp 4 TMA, warp 5 MM
 // TWO CTAs per SM: 3 stages (96 KB) and 2 accumulator chunks (256 TMEM columns) each.  One CTA per SM with 6 stages and 4
 // chunks left the second of 1.5 (fprop) and the fourth of 3.03 (dgrad) waves almost empty and nothing to run under a CTA's
 // epilogue; with half-size CTAs the tail is half as long and one CTA's epilogue overlaps the other's main loop.
-constexpr int PG_STAGES = 3;
+// When the whole launch fits one CTA per SM (Transition 3: 112 CTAs) the same kernel runs with 6 stages instead: with 3 a CTA
+// alone on its SM waited ~830 cycles per 64-channel k-atom for TMA round trips (53 us for a 6.6 us GEMM).
 constexpr int PG_MAX_SEGS = 16;
 constexpr int PG_MAX_CHUNKS = 2;    // 2 x 128 fp32 accumulator columns = half of TMEM
 
@@ -43,6 +44,7 @@ struct PGParams {
   int Cin, Hin, Win, stride, rh, rw, pair;                                // dgrad
 };
 
+template <int PG_STAGES>
 struct __align__(1024) PGSmem {
   bf16 a[PG_STAGES][128 * 64];
   bf16 b[PG_STAGES][128 * 64];
@@ -55,11 +57,12 @@ struct __align__(1024) PGSmem {
 constexpr int PG_MAX_JOBS = 8;
 struct PGJobs { PGParams job[PG_MAX_JOBS]; };
 
-__global__ void __launch_bounds__(PG_THREADS, 2) pixel_gemm_tc_kernel(const __grid_constant__ PGJobs jobs) {
+template <int PG_STAGES>
+__global__ void __launch_bounds__(PG_THREADS, PG_STAGES <= 3 ? 2 : 1) pixel_gemm_tc_kernel(const __grid_constant__ PGJobs jobs) {
   const PGParams& p = jobs.job[blockIdx.y];
   if ((int)blockIdx.x >= p.ncta) return;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  PGSmem& sm = *reinterpret_cast<PGSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  PGSmem<PG_STAGES>& sm = *reinterpret_cast<PGSmem<PG_STAGES>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / p.tiles_h, h0 = (blockIdx.x % p.tiles_h) * p.r;
 
@@ -412,17 +415,23 @@ TcGemmBufs tc_gemm_bufs(const Dims& d, void* base) {
 struct PGQueue {
   std::vector<PGParams> jobs;
   void add(PGParams p, int B) { p.ncta = B * p.tiles_h; jobs.push_back(p); }
+  template <int STAGES>
+  int launch(const PGJobs& j, int ncta, int n, cudaStream_t st, const char* name) {
+    const size_t smem = sizeof(PGSmem<STAGES>) + 1024;
+    AACONV_CUDA_OK(cudaFuncSetAttribute(pixel_gemm_tc_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pixel_gemm_tc_kernel<STAGES><<<dim3(ncta, n), PG_THREADS, smem, AACONV_ST(st)>>>(j);
+    AACONV_LAUNCH_OK(name);
+    return 0;
+  }
   int flush(cudaStream_t st, const char* name) {
-    const size_t smem = sizeof(PGSmem) + 1024;
-    AACONV_CUDA_OK(cudaFuncSetAttribute(pixel_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (size_t i = 0; i < jobs.size(); i += PG_MAX_JOBS) {
       PGJobs j;
       memset(&j, 0, sizeof j);
       const int n = (int)std::min<size_t>(PG_MAX_JOBS, jobs.size() - i);
-      int ncta = 0;
-      for (int k = 0; k < n; ++k) { j.job[k] = jobs[i + k]; ncta = std::max(ncta, j.job[k].ncta); }
-      pixel_gemm_tc_kernel<<<dim3(ncta, n), PG_THREADS, smem, AACONV_ST(st)>>>(j);
-      AACONV_LAUNCH_OK(name);
+      int ncta = 0, total = 0;
+      for (int k = 0; k < n; ++k) { j.job[k] = jobs[i + k]; ncta = std::max(ncta, j.job[k].ncta); total += j.job[k].ncta; }
+      if (total <= 148) AACONV_TRY(launch<6>(j, ncta, n, st, name));      // one CTA per SM: deep TMA pipeline
+      else AACONV_TRY(launch<3>(j, ncta, n, st, name));                   // two CTAs per SM share the tensor pipe
     }
     jobs.clear();
     return 0;
@@ -486,8 +495,10 @@ int tc_fprop(const Dims& d, const TcGemmBufs& t, const float* conv_w, const floa
   const int ncta = d.B * p.tiles_h;
   // accumulator chunks per CTA: as many as TMEM holds (the A tiles are then read once), but never so many that the launch
   // has fewer CTAs than SMs -- at Transition 3 (1600 pixels = 16 tiles) four chunks per CTA left 132 of 148 SMs idle
+  // ... nor so many that the long conv CTAs (per x 9 taps x Cin / 64 k-atoms each) cannot be balanced over the SMs: aim for at
+  // least two CTAs per SM (Transition 2 with two chunks per CTA: 64 CTAs of 144 k-atoms next to 128 of 8 -> 52 us)
   int per = PG_MAX_CHUNKS;
-  while (per > 1 && ncta * (cdiv(nc_conv, per) + cdiv(nc_qkv, per)) < 148) --per;
+  while (per > 1 && ncta * (cdiv(nc_conv, per) + cdiv(nc_qkv, per)) < 2 * 148) --per;
   if (nc_conv + nc_qkv <= per) {
     p.nchunks = 0;
     for (int c = 0; c < nc_qkv; ++c) p.chunks[p.nchunks++] = PGChunk{c * 128, seg_qkv, seg_qkv + 1, 1};
@@ -787,10 +798,17 @@ int tc_wgrad_supported(const Dims& d) {
   return 0;
 }
 
+// split-K over pixel chunks only while the tasks alone leave SMs idle.  (Measured at Transition 3, 156 tasks: splitting 4-8 ways
+// to even out the 1.05 waves made wgrad 62 -> 87 us and its reduction 27 -> 54 us: the kernel is bound by its partial-tile
+// traffic, not by the tail wave.)
+static int wgrad_splits(int nt, int nchunks_total) { return std::max(1, std::min(148 / nt, nchunks_total)); }
+
 size_t tc_wgrad_partial_floats(const Dims& d) {
   const int T = d.ks * d.ks, nch = cdiv(d.Cin, WG_N);
   const int ntasks = (cdiv(d.Cc, 128) * T + cdiv(d.Nqkv, 128)) * nch;
-  return (size_t)std::max(ntasks, 148) * 128 * WG_N;
+  const int kr = wgrad_kr(d.W);
+  const int nchunks_total = kr ? d.B * cdiv(d.H, kr) : 1;
+  return (size_t)ntasks * wgrad_splits(ntasks, nchunks_total) * 128 * WG_N;
 }
 
 // xh, dyh (and dqkvh when dwq != NULL) must already hold the packed operands of this step.
@@ -819,7 +837,8 @@ int tc_wgrad(const Dims& d, const TcGemmBufs& t, float* dwc, float* dwq, float* 
   p.shape.CinK = t.CinK;
   const int nt = p.shape.ntasks();
   if (nt == 0) return 0;
-  int splits = std::max(1, 148 / nt);
+  int splits = wgrad_splits(nt, p.nchunks_total);
+  while (splits > 1 && (size_t)nt * splits * 128 * WG_N > tc_wgrad_partial_floats(d)) --splits;   // the caller sized `partial` for all tasks
   p.chunks_per_split = cdiv(p.nchunks_total, splits);
   splits = cdiv(p.nchunks_total, p.chunks_per_split);
   p.partial = partial;
