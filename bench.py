@@ -469,7 +469,9 @@ def main():
     ap.add_argument('--no-model', action='store_true', help='skip the whole-model training measurement (`model` field)')
     ap.add_argument('--no-shapes', action='store_true', help='skip the T2 / T3 / T1_512 rows (`shapes` field; N = 1 only)')
     ap.add_argument('--model-eager', action='store_true', help='`model` field: eager step instead of the CUDA-graph replay')
-    ap.add_argument('--no-feature-buffer', action='store_true', help='model: torchvision dense blocks (torch.cat) instead of the buffer')
+    ap.add_argument('--no-feature-buffer', action='store_true',
+                    help='model: torchvision dense blocks (torch.cat, torch BatchNorm) instead of the pre-allocated feature buffer with '
+                         'fused strided BN + ReLU')
     ap.add_argument('--no-fused-prologue', action='store_true', help='model: nn.InstanceNorm2d + ReLU instead of the fused prologue')
     ap.add_argument('--workload', default='layer', choices=['layer', 'model'],
                     help="layer: AAConv2d fwd+bwd microbench (configs[1], the headline) plus `shapes` and `model` fields; model: the "

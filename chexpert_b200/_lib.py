@@ -57,6 +57,11 @@ SYMBOLS = {
     'aaconv_ensemble_mean': (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, _P]),
     'aaconv_auroc_workspace_bytes': (ctypes.c_size_t, [ctypes.c_int]),
     'aaconv_auroc': (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, _P, _P, _P]),
+    'aaconv_bn_relu_workspace_bytes': (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    'aaconv_bn_relu_forward': (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, _P, _P, _P, _P,
+                                              ctypes.c_float, ctypes.c_float, _P, _P, _P, _P]),
+    'aaconv_bn_relu_backward': (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, _P, _P, _P, _P,
+                                               _P, _P, _P, _P, _P]),
     'aaconv_launch_count': (ctypes.c_longlong, []),
     'aaconv_debug_set_timeline': (None, [_P]),
     'aaconv_debug_set_mode': (None, [ctypes.c_int]),

@@ -19,6 +19,7 @@ import torch.nn.functional as F
 from torchvision.models.densenet import _DenseBlock, _DenseLayer
 
 from .aaconv import AAConv2d
+from .fused_bn import bn_relu
 
 
 def transition_attn_dims(num_output_features, attn_params):
@@ -135,7 +136,8 @@ class BufferedDenseBlock(nn.ModuleDict):
             buf = torch.empty(B, self.out_channels, H, W, dtype=init_features.dtype, device=init_features.device)
         feats = _Adopt.apply(init_features, buf)
         for layer in self.values():
-            new = layer.conv2(layer.relu2(layer.norm2(layer.conv1(layer.relu1(layer.norm1(feats))))))
+            # norm -> relu pairs: fused strided kernels in training on CUDA (chexpert_b200.fused_bn), the torch modules otherwise
+            new = layer.conv2(bn_relu(layer.norm2, layer.conv1(bn_relu(layer.norm1, feats))))
             if layer.drop_rate > 0:
                 new = F.dropout(new, p=layer.drop_rate, training=self.training)
             feats = _Append.apply(feats, new.to(buf.dtype), buf)

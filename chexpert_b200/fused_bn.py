@@ -1,0 +1,65 @@
+"""BatchNorm2d (training mode) + ReLU as one op that reads its input through a batch stride -- the normalisation of a channel
+slice of the pre-allocated DenseBlock feature buffer (torchvision densenet.py:36-41 under
+models/attn_aug_conv.py:479-482).  Parameters, buffers and the arithmetic are nn.BatchNorm2d's (same state_dict, same running
+statistics update); eval mode and CPU tensors go through the module's own forward.
+"""
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .aaconv import _ptr, _stream
+
+_DT = {torch.float32: _lib.FP32, torch.bfloat16: _lib.BF16}
+
+
+def _strided_ok(x):
+    """(B, C, H, W) with dense (C, H, W) inside every sample: a contiguous tensor or a channel slice of the feature buffer."""
+    B, C, H, W = x.shape
+    return x.stride(3) == 1 and x.stride(2) == W and x.stride(1) == H * W and x.stride(0) >= C * H * W
+
+
+class _BNReLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps):
+        lib = _lib.load()
+        B, C, H, W = x.shape
+        xs = x.detach()
+        w, b = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        with torch.cuda.device(x.device):
+            y = torch.empty(B, C, H, W, device=x.device, dtype=x.dtype)
+            saved = torch.empty(C, 2, device=x.device, dtype=torch.float32)
+            ws = torch.empty(lib.aaconv_bn_relu_workspace_bytes(B, C), device=x.device, dtype=torch.uint8)
+            _lib.check(lib.aaconv_bn_relu_forward(_ptr(xs), _DT[x.dtype], B, C, H * W, xs.stride(0), _ptr(w), _ptr(b),
+                                                  _ptr(running_mean), _ptr(running_var), float(momentum), float(eps), _ptr(y),
+                                                  _ptr(saved), _ptr(ws), _stream()), 'aaconv_bn_relu_forward')
+        ctx.save_for_backward(xs, saved, w, b)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        xs, saved, w, b = ctx.saved_tensors
+        B, C, H, W = xs.shape
+        g = dy.detach().to(xs.dtype).contiguous()
+        need = ctx.needs_input_grad
+        with torch.cuda.device(xs.device):
+            dx = torch.empty(B, C, H, W, device=xs.device, dtype=xs.dtype) if need[0] else None
+            dw = torch.empty(C, device=xs.device, dtype=torch.float32) if need[1] else None
+            db = torch.empty(C, device=xs.device, dtype=torch.float32) if need[2] else None
+            ws = torch.empty(lib.aaconv_bn_relu_workspace_bytes(B, C), device=xs.device, dtype=torch.uint8)
+            _lib.check(lib.aaconv_bn_relu_backward(_ptr(xs), _DT[xs.dtype], B, C, H * W, xs.stride(0), _ptr(g), _ptr(saved), _ptr(w),
+                                                   _ptr(b), _ptr(dx), _ptr(dw), _ptr(db), _ptr(ws), _stream()), 'aaconv_bn_relu_backward')
+        return dx, dw, db, None, None, None, None
+
+
+def bn_relu(bn, x):
+    """relu(bn(x)) for an nn.BatchNorm2d `bn`; the fused strided kernels when it is training on CUDA, the modules otherwise."""
+    fused = (bn.training and x.is_cuda and x.dim() == 4 and x.dtype in _DT and bn.affine and bn.track_running_stats
+             and bn.momentum is not None and _strided_ok(x) and x.shape[0] <= 65535)
+    if not fused:
+        return F.relu(bn(x), inplace=True)
+    if bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return _BNReLU.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps)

@@ -142,6 +142,21 @@ int aaconv_ensemble_mean(const float* logits, int n_models, int N, int C, float*
 size_t aaconv_auroc_workspace_bytes(int C);
 int aaconv_auroc(const float* logits, const float* targets, int N, int C, float* auroc, void* workspace, void* stream);
 
+/* Dense-block side of the feature buffer: BatchNorm2d in TRAINING mode (batch statistics, as
+ * nn.BatchNorm2d does under model.train(): torchvision densenet.py:36,40 inside models/attn_aug_conv.py:479-482) fused with the
+ * ReLU that follows it, reading its input THROUGH a batch stride -- layer i of a block normalises channels [0, c_i) of the
+ * (B, C_total, H, W) feature buffer in place of torch.cat's copy.  x: (B, C, HW) elements of `dtype` (AACONV_FP32 | AACONV_BF16)
+ * with x_batch_stride >= C*HW elements between samples; y, dy, dx dense (B, C, HW) of the same dtype; weight, bias,
+ * running_mean, running_var (C) fp32 (running_* may both be NULL; updated with `momentum`, unbiased variance);
+ * saved: (C) x (mean, rstd) fp32 written by forward for backward; workspace: aaconv_bn_relu_workspace_bytes(B, C) bytes.
+ * backward: dx may be NULL; dweight / dbias (C) are WRITTEN (may be NULL).  All reductions run in a fixed order. */
+size_t aaconv_bn_relu_workspace_bytes(int B, int C);
+int aaconv_bn_relu_forward(const void* x, int dtype, int B, int C, int HW, int64_t x_batch_stride, const float* weight, const float* bias,
+                           float* running_mean, float* running_var, float momentum, float eps, void* y, float* saved, void* workspace,
+                           void* stream);
+int aaconv_bn_relu_backward(const void* x, int dtype, int B, int C, int HW, int64_t x_batch_stride, const void* dy, const float* saved,
+                            const float* weight, const float* bias, void* dx, float* dweight, float* dbias, void* workspace, void* stream);
+
 /* Accounting / measurement helpers used by bench.py (no reference counterpart).
  *   aaconv_launch_count   kernels launched by this library since it was loaded (all threads).
  *   aaconv_profile_begin  start recording a (start, stop) CUDA-event pair around every launch (`stream` is unused, kept for ABI).

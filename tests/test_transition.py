@@ -186,3 +186,37 @@ def test_train_step_options_follow_the_plain_step():
         losses[opt] = torch.stack([ts(x, t) for _ in range(5)]).cpu()
     assert torch.isfinite(losses[True]).all()
     assert torch.allclose(losses[True], losses[False], rtol=5e-2, atol=5e-3), (losses[True], losses[False])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dt,tol', [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+def test_fused_bn_relu_on_a_buffer_slice_matches_torch(dt, tol):
+    """chexpert_b200.fused_bn.bn_relu (training mode) on a strided channel slice of a feature buffer against
+    nn.BatchNorm2d + ReLU on the contiguous copy: output, running statistics, dx, dweight, dbias."""
+    from chexpert_b200.fused_bn import bn_relu
+    torch.manual_seed(0)
+    B, Ctot, C, H, W = 5, 48, 24, 9, 7
+    buf = (torch.randn(B, Ctot, H, W, device='cuda') * 2 + 0.5).to(dt)
+    ref = torch.nn.BatchNorm2d(C).cuda()
+    ours = torch.nn.BatchNorm2d(C).cuda()
+    with torch.no_grad():
+        ref.weight.uniform_(0.5, 1.5), ref.bias.uniform_(-0.5, 0.5)
+    ours.load_state_dict(ref.state_dict())
+    xa = buf[:, :C].clone().float().requires_grad_(True)                 # contiguous fp32 reference input
+    xb = buf[:, :C].detach().requires_grad_(True)                         # the strided slice itself
+    assert not xb.is_contiguous()
+    ya = torch.relu(ref(xa))
+    yb = bn_relu(ours, xb)
+    assert yb.dtype == dt and yb.is_contiguous()
+    scale = float(ya.abs().max())
+    assert float((ya - yb.float()).abs().max()) < tol * scale
+    assert torch.allclose(ours.running_mean, ref.running_mean, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(ours.running_var, ref.running_var, rtol=1e-4, atol=1e-5)
+    assert int(ours.num_batches_tracked) == int(ref.num_batches_tracked) == 1
+    g = torch.randn_like(ya)
+    ya.backward(g)
+    yb.backward(g.to(dt))
+    assert float((xa.grad - xb.grad.float()).abs().max()) < tol * float(xa.grad.abs().max()) * 2
+    assert rel_err(ours.weight.grad, ref.weight.grad) < tol and rel_err(ours.bias.grad, ref.bias.grad) < tol
+    ours.eval(), ref.eval()                                               # eval mode goes through the module itself
+    assert torch.allclose(bn_relu(ours, xb.detach()).float(), torch.relu(ref(xa.detach())), rtol=tol, atol=tol)
