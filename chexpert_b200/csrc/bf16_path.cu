@@ -85,10 +85,12 @@ int bf16_forward(const Dims& d, const void* xin, const aaconv_params* p, void* y
   float* o = at<float>(saved, f32_saved_offset(d, "o"));
   float* lse = at<float>(saved, f32_saved_offset(d, "lse"));
   SavedAug sa(d, saved);
-  if (d.fuse_in) AACONV_TRY(in_stats(d, xin, sa.stats, st));     // InstanceNorm statistics (attn_aug_conv.py:438)
+  NvtxRange r_fwd("aaconv.forward");
+  if (d.fuse_in) { NvtxRange r("aaconv.prologue"); AACONV_TRY(in_stats(d, xin, sa.stats, st)); }   // InstanceNorm statistics (attn_aug_conv.py:438)
   const float* x = static_cast<const float*>(xin);                // fp32 view of the (normalised) input for the FFMA fallbacks
   if (w.xn && !w.gemm_ok) { AACONV_TRY(in_relu_apply(d, xin, sa.stats, w.xn, st)); x = w.xn; }
   if (w.gemm_ok) {
+    NvtxRange r("aaconv.fprop");
     w.gemm.xh = sa.xh;
     // layout + precision pack of the GEMM operand, with relu((x-mean)*rstd) applied on the way (attn_aug_conv.py:438-439)
     AACONV_TRY(pack_x(xin, d.x_bf16, d.fuse_in ? sa.stats : nullptr, sa.xh, d.B, d.Cin, w.gemm.CinK, d.Hin * d.Win, st));
@@ -97,9 +99,13 @@ int bf16_forward(const Dims& d, const void* xin, const aaconv_params* p, void* y
     AACONV_TRY(f32_conv_fwd(d, x, p->conv_w, y, st));
     AACONV_TRY(f32_qkv_fwd(d, x, p->qkv_w, q, k, v, st));
   }
-  AACONV_TRY(aug_build_fwd(d, q, k, v, p->key_rel_w, p->key_rel_h, sa.qa, sa.ka, st));
-  if (cc_attn_supported(d) == 0) AACONV_TRY(cc_attn_fwd(d, sa.qa, sa.ka, v, o, lse, st));
-  else AACONV_TRY(tc_attn_fwd(d, sa.qa, sa.ka, o, lse, st));
+  { NvtxRange r("aaconv.aug_build"); AACONV_TRY(aug_build_fwd(d, q, k, v, p->key_rel_w, p->key_rel_h, sa.qa, sa.ka, st)); }
+  {
+    NvtxRange r("aaconv.attention");
+    if (cc_attn_supported(d) == 0) AACONV_TRY(cc_attn_fwd(d, sa.qa, sa.ka, v, o, lse, st));
+    else AACONV_TRY(tc_attn_fwd(d, sa.qa, sa.ka, o, lse, st));
+  }
+  NvtxRange r_epi("aaconv.epilogue");
   // visualise path only: the bf16 kernels' own probabilities -- their bf16 operands, their lse (attn_aug_conv.py:87)
   if (weights) AACONV_TRY(aug_weights(d, sa.qa, sa.ka, lse, weights, st));
   AACONV_TRY(out_proj_fwd(d, o, p->out_w, y, st));
@@ -124,6 +130,7 @@ int bf16_backward(const Dims& d, const void* xin, const aaconv_params* p, const 
   const float* o = at<float>(saved, f32_saved_offset(d, "o"));
   const float* lse = at<float>(saved, f32_saved_offset(d, "lse"));
   SavedAug sa(d, saved);
+  NvtxRange r_bwd("aaconv.backward");
   if (w.xn) { AACONV_TRY(in_relu_apply(d, xin, sa.stats, w.xn, st)); x = w.xn; }
   // the backward-only columns of Qa (-lse, dO, -delta) are filled in place; idempotent, so a retained graph may
   // run backward again
@@ -137,10 +144,14 @@ int bf16_backward(const Dims& d, const void* xin, const aaconv_params* p, const 
   // operand of the projection dgrad/wgrad GEMMs; its padding columns must be finite (they meet zero weights)
   const bool direct = w.gemm_ok && rel_bwd_supported(d) == 0 && tc_wgrad_supported(d) == 0;
   if (direct) AACONV_CUDA_OK(cudaMemsetAsync(w.gemm.dqkvh, 0, sizeof(uint16_t) * (size_t)d.B * d.L * w.gemm.KPq, st));
-  if (cc_attn_supported(d) == 0)
-    AACONV_TRY(cc_attn_bwd(d, sa.qa, sa.ka, v, w.d_o, w.delta, w.dqa, w.dk, w.dv, direct ? w.gemm.dqkvh : nullptr, w.gemm.KPq, st));
-  else
-    AACONV_TRY(tc_attn_bwd(d, sa.qa, sa.ka, w.dqa, w.dk, w.dv, direct ? w.gemm.dqkvh : nullptr, w.gemm.KPq, st));
+  {
+    NvtxRange r("aaconv.attention_bwd");
+    if (cc_attn_supported(d) == 0)
+      AACONV_TRY(cc_attn_bwd(d, sa.qa, sa.ka, v, w.d_o, w.delta, w.dqa, w.dk, w.dv, direct ? w.gemm.dqkvh : nullptr, w.gemm.KPq, st));
+    else
+      AACONV_TRY(tc_attn_bwd(d, sa.qa, sa.ka, w.dqa, w.dk, w.dv, direct ? w.gemm.dqkvh : nullptr, w.gemm.KPq, st));
+  }
+  NvtxRange r_rest("aaconv.rel_bwd+dgrad+wgrad");
   if (direct) {
     AACONV_TRY(rel_bwd(d, w.dqa, q, p->key_rel_w, p->key_rel_h, nullptr, w.gemm.dqkvh, w.gemm.KPq, g->key_rel_w, g->key_rel_h,
                        w.relpart, st));

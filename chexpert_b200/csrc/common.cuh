@@ -41,6 +41,14 @@ cudaStream_t pre_launch(cudaStream_t st);
   } while (0)
 #define AACONV_LAUNCH_OK(name) AACONV_LAUNCH_OK_ON(name, st)
 
+// NVTX range around one stage of a forward / backward call (header-only NVTX v3: no extra library; a no-op unless a tool such
+// as nsys / ncu --nvtx is attached).  Stage names: aaconv.prologue, .fprop, .aug_build, .attention, .epilogue, .out_bwd,
+// .attention_bwd, .rel_bwd, .dgrad, .wgrad, .prologue_bwd
+struct NvtxRange {
+  explicit NvtxRange(const char* name);
+  ~NvtxRange();
+};
+
 #define AACONV_TRY(expr)                                                                           \
   do {                                                                                             \
     int r__ = (expr);                                                                              \

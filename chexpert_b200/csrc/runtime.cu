@@ -3,6 +3,7 @@
 #include <mutex>
 #include <vector>
 #include <cstring>
+#include <nvtx3/nvToolsExt.h>
 #include "common.cuh"
 
 namespace aaconv {
@@ -21,6 +22,9 @@ int fail(int code, const char* fmt, ...) {
   last_error_ref() = buf;
   return code;
 }
+
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 namespace {
 std::atomic<long long> g_launches{0};
