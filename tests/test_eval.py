@@ -142,6 +142,20 @@ def test_ensemble_eval_bf16_auroc(gold, eval_set):
     ref_loss = torch.nn.BCEWithLogitsLoss(reduction='none')
     el = torch.stack([ref_loss(z, eval_set[1]) for z in want], 2).mean(2).mean(0)
     np.testing.assert_allclose(res['loss'].cpu().numpy(), el.numpy(), rtol=2e-2, atol=1e-2)
+    # the measured figures travel back from the GPU box (gpurun_out/) and are committed as profiles/parity_bf16.json, which
+    # bench.py prints in its line: the per-class AUROC figure is a documented exception to north_star's 1e-3
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    if os.path.isdir(out_dir):
+        import json
+        json.dump({'what': 'bf16 mode vs the unmodified reference (fp32) on the fixed synthetic 234-image set, 10 seed-initialised '
+                           'checkpoints (tests/test_eval.py::test_ensemble_eval_bf16_auroc)',
+                   'ensemble_auroc_abs_diff_per_class': [float(v) for v in d], 'ensemble_auroc_abs_diff_mean': float(d.mean()),
+                   'per_checkpoint_auroc_abs_diff_max': float(dm.max()), 'per_checkpoint_auroc_abs_diff_mean': float(dm.mean()),
+                   'logit_abs_diff_max': float((got - want).abs().max()), 'logit_std_over_images': float(want.std(1).mean()),
+                   'north_star': 'per-class AUROC within 1e-3', 'gate_in_test': 'per class < 2e-3, mean over classes < 1e-3',
+                   'note': 'untrained checkpoints separate images by ~0.03 in logit; a bf16 logit error of ~1e-3 swaps ~10 of '
+                           '11.5 k positive/negative pairs = 1e-3 AUROC; fp32 mode meets 1e-3 per class'},
+                  open(os.path.join(out_dir, 'parity_bf16.json'), 'w'), indent=1)
 
 
 @pytest.mark.gpu

@@ -14,7 +14,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # kernel function name -> the launch label bench.py / the library profile uses
 LABEL = {'attn_fwd_cc_kernel': 'attn_fwd_cc', 'attn_bwd_dq_cc_kernel': 'attn_bwd_dq_cc', 'attn_bwd_dkv_cc_kernel': 'attn_bwd_dkv_cc',
          'aug_build_fwd_kernel': 'aug_build_fwd', 'rel_bwd_kernel': 'rel_bwd', 'wgrad_tc_kernel': 'conv_qkv_wgrad_tc',
-         'pack_x_v4_kernel': 'pack_nhwc_bf16', 'out_bwd_patch_kernel': 'out_bwd_patch', 'attn_fwd_tc_kernel': 'attn_fwd_tc',
+         'pack_x_v4_kernel': 'pack_nhwc_bf16', 'out_bwd_patch_kernel': 'out_bwd_patch', 'out_proj_fwd_kernel': 'out_proj_fwd',
+         'rel_bwd_reduce_kernel': 'rel_bwd_reduce', 'out_w_reduce_kernel': 'out_w_reduce', 'wgrad_reduce_kernel': 'wgrad_reduce',
+         'pack_wf_kernel': 'pack_wf', 'pack_wd_kernel': 'pack_wd', 'attn_fwd_tc_kernel': 'attn_fwd_tc',
          'attn_bwd_dq_tc_kernel': 'attn_bwd_dq_tc', 'attn_bwd_dkv_tc_kernel': 'attn_bwd_dkv_tc'}
 
 
@@ -30,7 +32,7 @@ def main():
     for r in rows[2:]:
         if len(r) < len(H):
             continue
-        name = r[kn].replace('void ', '').split('(')[0].split('<')[0].replace('aaconv::', '').replace('(anonymous namespace)::', '')
+        name = r[kn].replace('void ', '').split('(')[0].split('<')[0].replace('aaconv::', '').replace('(anonymous namespace)::', '').replace('<unnamed>::', '').replace('unnamed>::', '')
         label = LABEL.get(name, name)
         if name == 'pixel_gemm_tc_kernel':     # launched three ways per step, in this order: fprop, dgrad (wgrad has its own kernel)
             label = ('conv_qkv_fprop_tc', 'conv_qkv_dgrad_tc')[order[name] % 2]
