@@ -59,7 +59,7 @@ SYMBOLS = {
     'aaconv_auroc': (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, _P, _P, _P]),
     'aaconv_bn_relu_workspace_bytes': (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     'aaconv_bn_relu_forward': (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, _P, _P, _P, _P,
-                                              ctypes.c_float, ctypes.c_float, _P, _P, _P, _P]),
+                                              ctypes.c_float, ctypes.c_float, _P, _P, _P, ctypes.c_int, _P]),
     'aaconv_bn_relu_backward': (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, _P, _P, _P, _P,
                                                _P, _P, _P, _P, _P]),
     'aaconv_launch_count': (ctypes.c_longlong, []),

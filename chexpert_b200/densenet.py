@@ -135,9 +135,15 @@ class BufferedDenseBlock(nn.ModuleDict):
                 or not buf.is_contiguous() or buf.data_ptr() != init_features.data_ptr()):
             buf = torch.empty(B, self.out_channels, H, W, dtype=init_features.dtype, device=init_features.device)
         feats = _Adopt.apply(init_features, buf)
+        # per-(channel, sample) plane statistics of the buffer, shared by the norm1 of every layer: layer i only reduces the channels
+        # layer i-1 has not seen (its own 32 new ones); the first layer reduces the block's input channels
+        stats = torch.empty(2 * B * self.out_channels, device=buf.device, dtype=torch.float32) if buf.is_cuda else None
+        valid = 0
         for layer in self.values():
             # norm -> relu pairs: fused strided kernels in training on CUDA (chexpert_b200.fused_bn), the torch modules otherwise
-            new = layer.conv2(bn_relu(layer.norm2, layer.conv1(bn_relu(layer.norm1, feats))))
+            c = feats.shape[1]
+            new = layer.conv2(bn_relu(layer.norm2, layer.conv1(bn_relu(layer.norm1, feats, None if stats is None else (stats, valid)))))
+            valid = c
             if layer.drop_rate > 0:
                 new = F.dropout(new, p=layer.drop_rate, training=self.training)
             feats = _Append.apply(feats, new.to(buf.dtype), buf)

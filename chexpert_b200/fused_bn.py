@@ -22,7 +22,7 @@ def _strided_ok(x):
 
 class _BNReLU(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps):
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, stats=None):
         lib = _lib.load()
         B, C, H, W = x.shape
         xs = x.detach()
@@ -30,10 +30,15 @@ class _BNReLU(torch.autograd.Function):
         with torch.cuda.device(x.device):
             y = torch.empty(B, C, H, W, device=x.device, dtype=x.dtype)
             saved = torch.empty(C, 2, device=x.device, dtype=torch.float32)
-            ws = torch.empty(lib.aaconv_bn_relu_workspace_bytes(B, C), device=x.device, dtype=torch.uint8)
+            # stats = (buffer, n_valid): plane statistics shared along a dense block -- channels [0, n_valid) of THIS input were
+            # already reduced into `buffer` by the previous layer (channel-major (C_total, B) float2: a prefix is a valid (C, B) table)
+            if stats is not None and stats[0].numel() * 4 >= 8 * B * C:
+                ws, valid = stats[0], min(int(stats[1]), C)
+            else:
+                ws, valid = torch.empty(lib.aaconv_bn_relu_workspace_bytes(B, C) // 4, device=x.device, dtype=torch.float32), 0
             _lib.check(lib.aaconv_bn_relu_forward(_ptr(xs), _DT[x.dtype], B, C, H * W, xs.stride(0), _ptr(w), _ptr(b),
                                                   _ptr(running_mean), _ptr(running_var), float(momentum), float(eps), _ptr(y),
-                                                  _ptr(saved), _ptr(ws), _stream()), 'aaconv_bn_relu_forward')
+                                                  _ptr(saved), _ptr(ws), valid, _stream()), 'aaconv_bn_relu_forward')
         ctx.save_for_backward(xs, saved, w, b)
         return y
 
@@ -51,15 +56,17 @@ class _BNReLU(torch.autograd.Function):
             ws = torch.empty(lib.aaconv_bn_relu_workspace_bytes(B, C), device=xs.device, dtype=torch.uint8)
             _lib.check(lib.aaconv_bn_relu_backward(_ptr(xs), _DT[xs.dtype], B, C, H * W, xs.stride(0), _ptr(g), _ptr(saved), _ptr(w),
                                                    _ptr(b), _ptr(dx), _ptr(dw), _ptr(db), _ptr(ws), _stream()), 'aaconv_bn_relu_backward')
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
-def bn_relu(bn, x):
-    """relu(bn(x)) for an nn.BatchNorm2d `bn`; the fused strided kernels when it is training on CUDA, the modules otherwise."""
+def bn_relu(bn, x, stats=None):
+    """relu(bn(x)) for an nn.BatchNorm2d `bn`; the fused strided kernels when it is training on CUDA, the modules otherwise.
+    ``stats = (float32 buffer of >= 2*B*C elements, n_valid_channels)`` shares the per-plane statistics between the layers of a
+    dense block (see aaconv_bn_relu_forward)."""
     fused = (bn.training and x.is_cuda and x.dim() == 4 and x.dtype in _DT and bn.affine and bn.track_running_stats
              and bn.momentum is not None and _strided_ok(x) and x.shape[0] <= 65535)
     if not fused:
         return F.relu(bn(x), inplace=True)
     if bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
-    return _BNReLU.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps)
+    return _BNReLU.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, stats)

@@ -149,11 +149,15 @@ int aaconv_auroc(const float* logits, const float* targets, int N, int C, float*
  * with x_batch_stride >= C*HW elements between samples; y, dy, dx dense (B, C, HW) of the same dtype; weight, bias,
  * running_mean, running_var (C) fp32 (running_* may both be NULL; updated with `momentum`, unbiased variance);
  * saved: (C) x (mean, rstd) fp32 written by forward for backward; workspace: aaconv_bn_relu_workspace_bytes(B, C) bytes.
+ * forward keeps the per-(channel, sample) plane statistics in the first 8*B*C bytes of `workspace`, channel-major; with
+ * stats_valid_channels = n > 0 the caller asserts that the entries of channels [0, n) already hold the statistics of THIS input
+ * (a dense block passes the same buffer from layer to layer: channels [0, c_{i-1}) were reduced by the previous layer), and only
+ * channels [n, C) are reduced.
  * backward: dx may be NULL; dweight / dbias (C) are WRITTEN (may be NULL).  All reductions run in a fixed order. */
 size_t aaconv_bn_relu_workspace_bytes(int B, int C);
 int aaconv_bn_relu_forward(const void* x, int dtype, int B, int C, int HW, int64_t x_batch_stride, const float* weight, const float* bias,
                            float* running_mean, float* running_var, float momentum, float eps, void* y, float* saved, void* workspace,
-                           void* stream);
+                           int stats_valid_channels, void* stream);
 int aaconv_bn_relu_backward(const void* x, int dtype, int B, int C, int HW, int64_t x_batch_stride, const void* dy, const float* saved,
                             const float* weight, const float* bias, void* dx, float* dweight, float* dbias, void* workspace, void* stream);
 
