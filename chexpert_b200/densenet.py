@@ -195,19 +195,29 @@ class DenseNet(nn.Module):
                 nn.init.constant_(m.bias, 0)
 
     def _features(self, x):
+        """-> relu(features(x)) (models/attn_aug_conv.py:513-514)."""
         if not self.feature_buffer:
-            return self.features(x)
-        mods = list(self.features.children())
-        for i, m in enumerate(mods):
-            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            return F.relu(self.features(x), inplace=True)
+        mods = list(self.features.named_children())
+        skip = False
+        for i, (name, m) in enumerate(mods):
+            if skip:
+                skip = False
+                continue
+            nxt = mods[i + 1][1] if i + 1 < len(mods) else None
             if isinstance(m, AATransition) and isinstance(nxt, BufferedDenseBlock):
                 x = m(x, out_total=nxt.out_channels)      # the AAConv2d epilogues write into the next block's buffer
+            elif isinstance(m, nn.BatchNorm2d) and isinstance(nxt, nn.ReLU):
+                x = bn_relu(m, x)                         # stem: norm0 -> relu0 as one fused op (grid (C, B) instead of one CTA per channel)
+                skip = True
+            elif isinstance(m, nn.BatchNorm2d) and nxt is None:
+                return bn_relu(m, x)                      # norm5 followed by forward()'s F.relu
             else:
                 x = m(x)
-        return x
+        return F.relu(x, inplace=True)
 
     def forward(self, x):
-        f = F.relu(self._features(x), inplace=True)
+        f = self._features(x)
         return self.classifier(F.adaptive_avg_pool2d(f, (1, 1)).flatten(1))
 
     def attn_layers(self):
