@@ -19,8 +19,15 @@ import torch.distributed as dist
 
 
 class GradientBuckets:
-    def __init__(self, module, bucket_mb=25.0, process_group=None, broadcast_from=0):
+    """``overlap=True``: gradients accumulate straight into the buckets and every bucket is all-reduced from the backward hooks as
+    soon as it is complete (communication under the rest of backward).  ``overlap=False``: autograd writes fresh gradients,
+    ``finish()`` packs them into the buckets with one multi-tensor copy per bucket, all-reduces (average) and points ``p.grad`` at
+    the bucket views -- no per-parameter accumulate kernel (360 small launches per step for aadensenet121, ~1 ms under a CUDA
+    graph) at the price of a 50 MB all-reduce that is not hidden (~0.2 ms over NVLink 5 at 8 GPUs)."""
+
+    def __init__(self, module, bucket_mb=25.0, process_group=None, broadcast_from=0, overlap=True):
         self.group = process_group
+        self.overlap = bool(overlap)
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.params = [p for p in module.parameters() if p.requires_grad]
         if not self.params:
@@ -46,7 +53,7 @@ class GradientBuckets:
         self._next = 0            # buckets [0, _next) have had their all-reduce issued this step
         self._state = 'finished'  # 'armed' between reset() and finish()
         self._sync = True
-        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params] if self.overlap else []
         self.reset()
 
     def _seal(self, params):
@@ -63,6 +70,11 @@ class GradientBuckets:
 
     def reset(self):
         """Zero the buckets (replaces optimizer.zero_grad(); keeps the grad views alive) and arm the step."""
+        if not self.overlap:                      # fresh gradients from autograd: nothing to zero, nothing to accumulate into
+            for p in self.params:
+                p.grad = None
+            self._state = 'armed'
+            return
         for flat, _ in self.buckets:
             flat.zero_()
         self._pending = [len(ps) for _, ps in self.buckets]
@@ -105,6 +117,26 @@ class GradientBuckets:
         """Wait for the exchange and turn sums into means.  Call once after backward(), before optimizer.step()."""
         if self._state != 'armed':
             raise RuntimeError('GradientBuckets: finish() called twice (or before reset())')
+        if not self.overlap:
+            avg = dist.ReduceOp.AVG if (self.world > 1 and dist.get_backend(self.group) == 'nccl') else None
+            for flat, params in self.buckets:
+                views = [self._view[p] for p in params]
+                have = [(v, p.grad) for v, p in zip(views, params) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
+                for v, p in zip(views, params):
+                    if p.grad is None:
+                        v.zero_()                 # parameter without a gradient on this rank contributes zeros
+                if have:
+                    torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+                if self.world > 1:
+                    if avg is not None:
+                        dist.all_reduce(flat, op=avg, group=self.group)
+                    else:
+                        dist.all_reduce(flat, group=self.group)
+                        flat.div_(self.world)
+                for v, p in zip(views, params):
+                    p.grad = v
+            self._state = 'finished'
+            return
         self._issue_ready(upto=len(self.buckets))     # buckets with parameters that received no gradient this step, in order
         if self.world > 1:
             for w in self._works:

@@ -51,7 +51,9 @@ class TrainStep:
         self.opt = torch.optim.SGD(self.model.parameters(), lr=lr, momentum=0.9, nesterov=True)
         self.sched = torch.optim.lr_scheduler.MultiStepLR(self.opt, [40000, 60000])
         self.world = dist.get_world_size() if dist.is_initialized() else 1
-        self.buckets = GradientBuckets(self.model, bucket_mb=bucket_mb) if self.world > 1 else None
+        # on NVLink the exchange is ~0.2 ms: pack + all-reduce after backward instead of 360 per-parameter accumulate kernels
+        self.buckets = (GradientBuckets(self.model, bucket_mb=bucket_mb, overlap=self.device.type != 'cuda')
+                        if self.world > 1 else None)
         # the dense blocks are torch/cuDNN (outside the hot path); bf16 autocast only decides THEIR arithmetic
         self.autocast = bool(autocast and precision == 'bf16' and self.device.type == 'cuda')
         # cuda_graph: after `graph_after` eager steps (they create the momentum buffers and warm cuDNN up) the whole step --

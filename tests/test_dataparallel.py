@@ -186,3 +186,32 @@ def test_trainstep_nccl_two_ranks_equal_the_full_batch_step(tmp_path):
     for a, b, w in zip(r0['params'], r1['params'], want):
         assert torch.equal(a, b)                                          # replicas stay identical
         assert torch.allclose(a, w, rtol=2e-4, atol=2e-6), float((a - w).abs().max())
+
+
+def _worker_post(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from chexpert_b200.dataparallel import GradientBuckets
+    net = _net()
+    gb = GradientBuckets(net, bucket_mb=0.0005, overlap=False)
+    x, t = _data()
+    xs, ts = x.chunk(world)[rank], t.chunk(world)[rank]
+    for _ in range(2):
+        gb.reset()
+        nn.functional.binary_cross_entropy_with_logits(net(xs), ts, reduction='none').sum(1).mean(0).backward()
+        gb.finish()
+    torch.save([p.grad.clone() for p in net.parameters()], os.path.join(out_dir, f'p{rank}.pt'))
+    dist.destroy_process_group()
+
+
+def test_pack_after_backward_mode_matches_full_batch(tmp_path):
+    """overlap=False (what TrainStep uses on CUDA): fresh gradients, one multi-tensor pack per bucket, averaged all-reduce."""
+    world = 2
+    mp.spawn(_worker_post, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    net = _net()
+    x, t = _data()
+    nn.functional.binary_cross_entropy_with_logits(net(x), t, reduction='none').sum(1).mean(0).backward()
+    g0, g1 = (torch.load(tmp_path / f'p{r}.pt') for r in range(world))
+    for a, b, p in zip(g0, g1, net.parameters()):
+        assert torch.equal(a, b)
+        assert torch.allclose(a, p.grad, rtol=1e-5, atol=1e-7)
