@@ -15,6 +15,7 @@
 //   dq_rel    [rows x dkh]     = dR[rows x 2N-1] . T^T                      dR[row, r] = dAq[row, r + x - (N-1)]
 //   dT^T      [2N-1 x dkh]    += dR^T[2N-1 x rows] . Q[rows x dkh]          (accumulated in registers, fixed order)
 #include <algorithm>
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include "tc_common.cuh"
 #include "bf16_path.cuh"
@@ -470,6 +471,9 @@ size_t aug_build_smem(const Dims& d) {
 int aug_build_fwd(const Dims& d, const float* q, const float* k, const float* v, const float* krw, const float* krh,
                   void* qa, void* ka, cudaStream_t st) {
   AACONV_TRY(aug_supported(d));
+  // AACONV_AUG_BUILD=legacy keeps the mma.sync builder (A/B runs, tools/aug_ab.py)
+  static const bool legacy = [] { const char* e = getenv("AACONV_AUG_BUILD"); return e && e[0] == 'l'; }();
+  if (!legacy && aug_build_tc_supported(d) == 0) return aug_build_tc(d, q, k, v, krw, krh, qa, ka, st);
   const AugLayout a = aug_layout(d);
   BuildP p;
   p.q = q; p.k = k; p.v = v; p.krw = krw; p.krh = krh;

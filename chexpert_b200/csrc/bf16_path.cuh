@@ -17,6 +17,10 @@ int aug_supported(const Dims& d);
 // aug_ops.cu
 int aug_build_fwd(const Dims& d, const float* q, const float* k, const float* v, const float* krw, const float* krh,
                   void* qa, void* ka, cudaStream_t st);
+// aug_tc.cu: the same operands from a tcgen05 (kind::tf32) product + per-row window; square maps of 10/20/40/64, dk/nh = 20
+int aug_build_tc_supported(const Dims& d);
+int aug_build_tc(const Dims& d, const float* q, const float* k, const float* v, const float* krw, const float* krh,
+                 void* qa, void* ka, cudaStream_t st);
 // (B,nh,L,L) softmax map from the bf16 operands and the bf16 forward kernel's lse (visualise path)
 int aug_weights(const Dims& d, const void* qa, const void* ka, const float* lse, float* weights, cudaStream_t st);
 int aug_patch_bwd(const Dims& d, const float* lse, const float* d_o, const float* o, void* qa, float* delta, cudaStream_t st);
