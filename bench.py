@@ -259,6 +259,8 @@ def ncu_traffic(kernel):
 
 
 def measure_layer(ctx, args, shape, K, W, want_e2e=True, sampler=None):
+    # args.io_dtype: element type of x / dy / y at the module boundary ('fp32' as the reference module, or 'bf16' = the
+    # activations torch.autocast hands the Transition in the bf16 training configuration, configs[2])
     """One AAConv2d forward + backward at a Transition shape through the public nn.Module (configs[1]).  -> dict."""
     import chexpert_b200 as cb
     from chexpert_b200 import _lib
@@ -275,8 +277,9 @@ def measure_layer(ctx, args, shape, K, W, want_e2e=True, sampler=None):
     m = m.to(dev)
     params = [p for p in m.parameters()]
     g = torch.Generator().manual_seed(1000 + rank)
-    x_host = torch.relu(torch.randn(B, cin, hin, hin, generator=g)).pin_memory()
-    dy_host = torch.randn(B, cout, H, H, generator=g).pin_memory()
+    io_t = torch.bfloat16 if (args.io_dtype == 'bf16' and args.precision == 'bf16') else torch.float32
+    x_host = torch.relu(torch.randn(B, cin, hin, hin, generator=g)).to(io_t).pin_memory()
+    dy_host = torch.randn(B, cout, H, H, generator=g).to(io_t).pin_memory()
     x = x_host.to(dev).requires_grad_(True)
     dy = dy_host.to(dev)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -316,18 +319,19 @@ def measure_layer(ctx, args, shape, K, W, want_e2e=True, sampler=None):
     ctx.barrier()
     t_wall = time.perf_counter() - t_wall
     launches = _lib.launch_count() - l0
-    out = {'shape': shape, 'ms': ms, 'launches': launches, 't_wall': t_wall, 'h2d': 0, 'd2h': 0, 'ms_e2e': None}
+    out = {'shape': shape, 'ms': ms, 'launches': launches, 't_wall': t_wall, 'h2d': 0, 'd2h': 0, 'ms_e2e': None,
+           'io_dtype': 'bf16' if io_t == torch.bfloat16 else 'fp32'}
 
     if want_e2e:
         # end-to-end: pinned host buffers in, y + parameter grads out, every step.  The way a training loop feeds a GPU: the
         # uploads of step k+1 on a copy stream while step k computes, results read back on a third stream from double-buffered
         # device staging.  Every step's H2D and D2H copies are inside the timed region; they overlap compute.
-        y_host = torch.empty(B, cout, H, H).pin_memory()
+        y_host = torch.empty(B, cout, H, H, dtype=io_t).pin_memory()
         g_host = [torch.empty(p.shape).pin_memory() for p in params]
         up, down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         xbuf = [torch.empty_like(x) for _ in range(2)]
         dybuf = [torch.empty_like(dy) for _ in range(2)]
-        ystage = [torch.empty(B, cout, H, H, device=dev) for _ in range(2)]
+        ystage = [torch.empty(B, cout, H, H, device=dev, dtype=io_t) for _ in range(2)]
         gstage = [[torch.empty_like(p) for p in params] for _ in range(2)]
         ready = [torch.cuda.Event() for _ in range(2)]       # upload into input buffer i finished
         freed = [torch.cuda.Event() for _ in range(2)]       # compute on input buffer i finished
@@ -386,8 +390,8 @@ def measure_layer(ctx, args, shape, K, W, want_e2e=True, sampler=None):
         ctx.barrier()
         out['ms_e2e'] = e2e_timed(max(6, K // 2))
         ctx.barrier()
-        out['h2d'] = x_host.numel() * 4 + dy_host.numel() * 4
-        out['d2h'] = y_host.numel() * 4 + sum(t.numel() * 4 for t in g_host)
+        out['h2d'] = x_host.numel() * x_host.element_size() + dy_host.numel() * dy_host.element_size()
+        out['d2h'] = y_host.numel() * y_host.element_size() + sum(t.numel() * 4 for t in g_host)
 
     out['ms'], e2e_max = ctx.max_over_ranks(out['ms'], out['ms_e2e'] or 0.0)
     if want_e2e:
@@ -460,6 +464,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default=os.environ.get('AACONV_BENCH_PRECISION', 'bf16'), choices=['bf16', 'fp32'])
+    ap.add_argument('--io-dtype', default='bf16', choices=['bf16', 'fp32'],
+                    help="element type of x / dy / y at the AAConv2d boundary in bf16 mode: 'bf16' = autocast activations (what the "
+                         "Transition receives in bf16 training, configs[2]); 'fp32' = the reference module's own tensors")
     ap.add_argument('--shape', default='T1', choices=list(SHAPES))
     ap.add_argument('--batch', type=int, default=16)
     ap.add_argument('--ref-batch', type=int, default=16, help='per-step batch of the CPU reference arm (same config as ours)')
@@ -490,6 +497,12 @@ def main():
     sampler = ClockSampler(ctx.local)
     sampler.start()
     layer = measure_layer(ctx, args, args.shape, K, W, want_e2e=True)
+    other = None                                     # the same layer through the other boundary element type (reported beside)
+    if args.precision == 'bf16' and ctx.world == 1:
+        keep = args.io_dtype
+        args.io_dtype = 'fp32' if keep == 'bf16' else 'bf16'
+        other = measure_layer(ctx, args, args.shape, max(5, K // 2), 3, want_e2e=True)
+        args.io_dtype = keep
     shapes = {}
     if ctx.world == 1 and not args.no_shapes:
         for sh in ('T2', 'T3', 'T1_512'):
@@ -524,15 +537,21 @@ def main():
                 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
                 'config': {'workload': f'AAConv2d {args.shape} fwd+bwd (configs[1])', 'shape': args.shape,
                            'batch_per_gpu': B, 'cin': cin, 'hin': hin, 'cout': cout, 'dk': dk, 'dv': dv, 'nh': 8,
-                           'precision': args.precision, 'l2': 'flushed between timed steps (256 MiB memset)' if not args.no_flush else 'not flushed',
+                           'precision': args.precision, 'boundary_dtype': layer['io_dtype'], 'l2': 'flushed between timed steps (256 MiB memset)' if not args.no_flush else 'not flushed',
                            'gflop_per_step_per_gpu': f_tot / 1e9, 'wall_s_timed_region': layer['t_wall'],
                            'tolerance': 'bf16 mode: outputs rtol 2e-2 / atol 1e-2 on >= 99.9 % of elements; gradients by relative L2 <= 3e-2, '
                                         '<= 4e-2 of max-abs and <= 2.5x torch.autocast (DESIGN.md section 7) -- a substitute for a fixed atol'},
                 'e2e': {'value': f_tot * world / (layer['ms_e2e'] * 1e-3) / 1e12, 'unit': 'TFLOP/s', 'ms_per_step': layer['ms_e2e'],
                         'h2d_bytes_per_step': layer['h2d'], 'd2h_bytes_per_step': layer['d2h'],
+                        'boundary_dtype': layer['io_dtype'],
                         'pipeline': 'pinned host buffers; upload of step k+1 and read-back of step k on side streams overlap compute'},
                 'gpu_launches': layer['launches'], 'clocks': clocks, 'roofline': roofline_of(layer, args, clocks, world),
                 'kernels': layer['kernels'], 'shapes': srows, 'model': model, 'parity': parity_note()}
+        if other is not None:
+            line['other_boundary'] = {'boundary_dtype': other['io_dtype'], 'ms_per_step': other['ms'],
+                                      'value': f_tot / (other['ms'] * 1e-3) / 1e12, 'e2e_ms_per_step': other['ms_e2e'],
+                                      'e2e_value': f_tot / (other['ms_e2e'] * 1e-3) / 1e12, 'h2d_bytes_per_step': other['h2d'],
+                                      'd2h_bytes_per_step': other['d2h']}
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             cb_B = args.ref_batch

@@ -887,6 +887,13 @@ constexpr int REL_BWD_GRID = 148 * 2;
 
 }  // namespace
 
+int rel_bwd_reduce(const Dims& d, const float* partial, int nparts, int RP, int DK8, float* dkrw, float* dkrh, cudaStream_t st) {
+  const int n = 2 * RP * DK8;
+  rel_bwd_reduce_kernel<<<cdiv(n, 32), 256, 0, AACONV_ST(st)>>>(partial, nparts, RP, DK8, d.dkh, d.RW, d.RH, dkrw, dkrh);
+  AACONV_LAUNCH_OK("rel_bwd_reduce");
+  return 0;
+}
+
 int rel_bwd_supported(const Dims& d) {
   if (!d.relative) return AACONV_E_UNSUPPORTED;
   if (std::max(d.RW, d.RH) > 128 || d.dkh > 32) return AACONV_E_UNSUPPORTED;
@@ -904,6 +911,15 @@ size_t rel_bwd_partial_floats(const Dims& d) {
 int rel_bwd(const Dims& d, const float* dqa, const float* q, const float* krw, const float* krh, float* dq, void* dqkvh,
             int KPq, float* dkrw, float* dkrh, float* partial, cudaStream_t st) {
   AACONV_TRY(rel_bwd_supported(d));
+  // AACONV_REL_BWD=legacy keeps the mma.sync kernel (A/B runs, tools/stage_ab.py)
+  static const bool legacy = [] { const char* e = getenv("AACONV_REL_BWD"); return e && e[0] == 'l'; }();
+  if (!legacy && !dq && dqkvh && rel_bwd_tc_supported(d, KPq) == 0) {
+    const int RP = cdiv(std::max(d.RW, d.RH), 16) * 16, DK8 = cdiv(d.dkh, 8) * 8;
+    int nparts = 0;
+    AACONV_TRY(rel_bwd_tc(d, dqa, q, krw, krh, dqkvh, KPq, partial, RP, DK8, &nparts, st));
+    if (dkrw || dkrh) AACONV_TRY(rel_bwd_reduce(d, partial, nparts, RP, DK8, dkrw, dkrh, st));
+    return 0;
+  }
   const AugLayout a = aug_layout(d);
   RelBwdP p;
   p.dqa = dqa; p.q = q; p.krw = krw; p.krh = krh; p.dq = dq; p.dqkvh = static_cast<bf16*>(dqkvh); p.partial = partial;

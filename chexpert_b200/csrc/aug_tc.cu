@@ -290,7 +290,12 @@ __global__ void __launch_bounds__(AbCfg<W, H, DKH>::THREADS, 1) aug_build_tc_ker
           qp[2 * c + 1] = tc::pack_bf16x2(t4.z * LOG2E, t4.w * LOG2E);
         }
       }
-      tc::mbar_arrive(&sm.bar_empty[s]);
+      {   // release the q stage only once the loads above have delivered (see mbar_arrive_after)
+        uint32_t fold = 0u;
+#pragma unroll
+        for (int c = 0; c < DKH / 2; ++c) fold ^= qp[c];
+        tc::mbar_arrive_after(&sm.bar_empty[s], fold & ((uint32_t)dbg & 0x40000000u));
+      }
       // ---- Qa row: [ c q | c Aq | c Bq | 0 (lse slots, backward) | 0 .. ] -> staging tile -> TMA store ----
       if (leader) bulk_wait_read0();                 // the previous tile's Ka store has finished READING the staging tile
       wg_sync();
@@ -410,6 +415,348 @@ int aug_build_tc(const Dims& d, const float* q, const float* k, const float* v, 
     case 20: return launch_aug_build_tc<20, 20, 20>(d, q, k, v, krw, krh, qa, ka, st);
     case 40: return launch_aug_build_tc<40, 40, 20>(d, q, k, v, krw, krh, qa, ka, st);
     default: return launch_aug_build_tc<64, 64, 20>(d, q, k, v, krw, krh, qa, ka, st);
+  }
+}
+
+namespace {
+
+// ================================================================================================
+// rel_bwd_tc: dQa -> total dq (content + relative part, bf16 into the packed dqkv operand of the projection GEMMs) and the
+// key_rel_w / key_rel_h gradient partials, on tcgen05 -- round-2 replacement of rel_bwd_kernel (mma.sync TF32).
+//
+//   dR[row, r]  = dAq[row, r - (W-1-x(row))] inside the window, 0 elsewhere  (adjoint of the rel_to_abs index law)
+//   dq_rel      = dR . T^T          MMA1: D1[128 rows x 32] = A[rows x K] . B[e x K]^T, A = dR tile (K-major), B = tables
+//   dT^T[r, e] += dR^T . q          MMA2: D2[128 r x 32]   += A^T (the same tile viewed MN-major) . q tile (MN-major)
+//
+// One thread owns one row: it reads its dQa row from the staged tile, writes the window of packed bf16 pairs at its own
+// offset into the 128B-swizzled A tile (zero elsewhere) and its q row into the q tile; the MMA warp issues both products; the
+// thread then adds D1 to the content part and stores 20 bf16.  D2 accumulates over all tiles of the CTA and is written once
+// as a partial for rel_bwd_reduce_kernel.  Reference: adjoint of attn_aug_conv.py:55-63,77-86.
+// ================================================================================================
+template <int W, int H, int DKH>
+struct RbCfg {
+  static constexpr int NW = ru16(2 * W - 1), NH = ru16(2 * H - 1), KCOLS = NW + NH;
+  static constexpr int KA = (KCOLS + 63) / 64 < 2 ? 2 : (KCOLS + 63) / 64;     // 64-column atoms of the A tile (>= 2: M = 128 blocks)
+  static constexpr int NBLK = KA >= 3 ? 2 : 1;            // D2 blocks of 128 A-columns: atoms {0,1} and {KA-2, KA-1}
+  static constexpr int KD = DKH + W + H;
+  static constexpr int NKS1 = (KCOLS + 15) / 16;
+  static constexpr int IN_BYTES = AB_BM * KD * 4;
+  static constexpr int fixed = KA * AB_BM * 128 + AB_BM * 128 + KA * 32 * 128 + 2048;
+  static constexpr int fit = (225 * 1024 - fixed) / IN_BYTES;
+  static constexpr int STAGES = fit > 3 ? 3 : fit;
+  static_assert(STAGES >= 1 && KD % 4 == 0 && DKH % 4 == 0 && DKH <= 32, "rel_bwd_tc configuration");
+};
+
+template <class C>
+struct __align__(1024) RbSmem {
+  bf16 a[C::KA][AB_BM * 64];                      // dR tile: 128 rows x (NW | NH) columns, 128B-swizzled atoms
+  bf16 qt[AB_BM * 64];                            // q tile (first 32 columns used)
+  bf16 t[C::KA][32 * 64];                         // tables as the B operand of MMA1: row e, K = A column
+  float in[C::STAGES][AB_BM * C::KD];             // dQa tiles (1-D bulk copies)
+  uint64_t bar_full[C::STAGES], bar_empty[C::STAGES], bar_a_ready, bar_done;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void bulk_g2s_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+
+// N fp32 values at byte offset OFF of a staged row -> packed bf16 pairs dst[1 .. N/2] (16-byte loads when OFF allows, else 8-byte)
+template <int N, int OFF>
+__device__ __forceinline__ void load_pairs(uint32_t row, bool live, uint32_t* dst) {
+  if (OFF % 16 == 0) {
+#pragma unroll
+    for (int c = 0; c < N / 4; ++c) {
+      const float4 t4 = live ? lds128f(row + OFF + 16 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      dst[1 + 2 * c] = tc::pack_bf16x2(t4.x, t4.y);
+      dst[2 + 2 * c] = tc::pack_bf16x2(t4.z, t4.w);
+    }
+    if (N % 4) {
+      const float a0 = live ? lds32f(row + OFF + (N - 2) * 4) : 0.f, a1 = live ? lds32f(row + OFF + (N - 1) * 4) : 0.f;
+      dst[N / 2] = tc::pack_bf16x2(a0, a1);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < N / 2; ++c) {
+      float a0 = 0.f, a1 = 0.f;
+      if (live) asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(a0), "=f"(a1) : "r"(row + OFF + 8 * c) : "memory");
+      dst[1 + c] = tc::pack_bf16x2(a0, a1);
+    }
+  }
+}
+
+template <int W, int H, int DKH>
+__global__ void __launch_bounds__(192, 1) rel_bwd_tc_kernel(const float* __restrict__ dqa, const float* __restrict__ qg,
+                                                            const float* __restrict__ krw, const float* __restrict__ krh,
+                                                            bf16* __restrict__ dqkvh, float* __restrict__ partial, int L, int nh,
+                                                            int KPq, int RP, int DK8, float qscale, int tiles_per_bn, int ntiles, int dbg) {
+  typedef RbCfg<W, H, DKH> C;
+  typedef RbSmem<C> Smem;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int ST = C::STAGES, KA = C::KA;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_rows = [&](int i, int& bn, int& l0) {
+    const int tile = blockIdx.x + i * gridDim.x;
+    bn = tile / tiles_per_bn;
+    l0 = (tile - bn * tiles_per_bn) * AB_BM;
+    return min(AB_BM, L - l0);
+  };
+
+  if (warp == 4 && lane == 0) {
+    for (int s = 0; s < ST; ++s) { tc::mbar_init(&sm.bar_full[s], 1); tc::mbar_init(&sm.bar_empty[s], 128); }
+    tc::mbar_init(&sm.bar_a_ready, 128);
+    tc::mbar_init(&sm.bar_done, 1);
+    tc::fence_barrier_init();
+    for (int i = 0; i < ST && i < my_tiles && !(dbg & 4); ++i) {
+      int bn, l0;
+      const int nrows = tile_rows(i, bn, l0);
+      tc::mbar_arrive_expect_tx(&sm.bar_full[i], nrows * C::KD * 4);
+      bulk_g2s_1d(sm.in[i], dqa + ((size_t)bn * L + l0) * C::KD, nrows * C::KD * 4, &sm.bar_full[i]);
+    }
+  }
+  if (warp == 5) tc::tmem_alloc<128>(&sm.tmem_base);
+  if (warp < 4) {
+    // tables as MMA1's B operand (row e, K = A column: W axis at [0, NW), H axis at [NW, NW + NH)), zero padded; and the
+    // constant parts of the A / q tiles (everything a row owner does not rewrite per tile)
+    uint4* z = reinterpret_cast<uint4*>(sm.a);                        // a, qt, t are adjacent
+    constexpr int NZ = (KA * AB_BM * 128 + AB_BM * 128 + KA * 32 * 128) / 16;
+    for (int i = threadIdx.x; i < NZ; i += 128) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    constexpr int RW_ = 2 * W - 1, RH_ = 2 * H - 1, NTAB = DKH * (RW_ + RH_), PER = (NTAB + 127) / 128;
+    float tv[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int i = threadIdx.x + u * 128;
+      tv[u] = i < NTAB ? __ldg((i >= DKH * RW_ ? krh - DKH * RW_ : krw) + i) : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int i = threadIdx.x + u * 128;
+      if (i < NTAB) {
+        const bool hax = i >= DKH * RW_;
+        const int j = hax ? i - DKH * RW_ : i, R = hax ? RH_ : RW_;
+        const int e = j / R, k = j - e * R + (hax ? C::NW : 0);
+        const int at = k >> 6, kc = k & 63;
+        sm.t[at][e * 64 + ((((kc >> 3) ^ (e & 7)) << 3) | (kc & 7))] = __float2bfloat16(tv[u]);
+      }
+    }
+  }
+  tc::fence_proxy_async();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+  constexpr uint32_t COL_D1 = 0, COL_D2 = 32;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int i = (dbg & 4) ? 0 : ST; i < my_tiles; ++i) {
+        int bn, l0;
+        const int nrows = tile_rows(i, bn, l0), s = i % ST;
+        if (i >= ST) tc::mbar_wait(&sm.bar_empty[s], ((i / ST) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(&sm.bar_full[s], nrows * C::KD * 4);
+        bulk_g2s_1d(sm.in[s], dqa + ((size_t)bn * L + l0) * C::KD, nrows * C::KD * 4, &sm.bar_full[s]);
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t id1 = tc::idesc_bf16_f32(AB_BM, 32);
+    constexpr uint32_t id2 = tc::idesc_bf16_f32(AB_BM, 32) | (1u << 15) | (1u << 16);     // A and B MN-major
+    const uint32_t a_k = tc::desc_lo_k(smem_u32(sm.a[0])), t_k = tc::desc_lo_k(smem_u32(sm.t[0]));
+    const uint32_t q_mn = tc::desc_lo_mn(smem_u32(sm.qt), AB_BM * 128);
+    for (int i = 0; i < my_tiles; ++i) {
+      tc::mbar_wait(&sm.bar_a_ready, i & 1);
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < C::NKS1; ++ks)
+          tc::mma_ss(tmem + COL_D1, tc::desc64(a_k + (ks >> 2) * ((AB_BM * 128) >> 4) + (ks & 3) * 2),
+                     tc::desc64(t_k + (ks >> 2) * ((32 * 128) >> 4) + (ks & 3) * 2), id1, ks > 0);
+#pragma unroll
+        for (int b = 0; b < C::NBLK; ++b) {
+          const uint32_t a_mn = tc::desc_lo_mn(smem_u32(sm.a[b == 0 ? 0 : KA - 2]), AB_BM * 128);
+#pragma unroll
+          for (int ks = 0; ks < AB_BM / 16; ++ks)
+            tc::mma_ss(tmem + COL_D2 + 32 * b, tc::desc64(a_mn + ks * 128), tc::desc64(q_mn + ks * 128), id2, (i > 0 || ks > 0) ? 1u : 0u);
+        }
+        tc::mma_commit(&sm.bar_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== row owners =====================
+    const int r = threadIdx.x;
+    const uint32_t zmask = (uint32_t)dbg & 0x40000000u;          // 0 at run time; the compiler cannot know
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t swz = (uint32_t)(r & 7);
+    const uint32_t arow = smem_u32(sm.a[0]) + r * 128, qrow = smem_u32(sm.qt) + r * 128;
+    float dqc[DKH];                                  // content part of the PREVIOUS tile's row, waiting for its D1
+    bf16* dst_prev = nullptr;
+    auto finish_prev = [&](int iprev) {              // D1 of tile iprev -> dq_total -> bf16 store
+      tc::mbar_wait(&sm.bar_done, iprev & 1);
+      if (dbg & 1) { const long long t0 = clock64(); while (clock64() - t0 < 3000) {} }
+      tc::tc_fence_after();
+      uint32_t d1[32];
+      tc::tmem_ld_x32(tlane + COL_D1, d1);
+      tc::tmem_ld_wait();
+      tc::tc_fence_before();
+      if (dst_prev) {
+#pragma unroll
+        for (int e = 0; e < DKH; e += 4) {
+          uint2 w2;
+          w2.x = tc::pack_bf16x2((dqc[e] + __uint_as_float(d1[e])) * qscale, (dqc[e + 1] + __uint_as_float(d1[e + 1])) * qscale);
+          w2.y = tc::pack_bf16x2((dqc[e + 2] + __uint_as_float(d1[e + 2])) * qscale, (dqc[e + 3] + __uint_as_float(d1[e + 3])) * qscale);
+          *reinterpret_cast<uint2*>(dst_prev + e) = w2;
+        }
+      }
+    };
+    for (int i = 0; i < my_tiles; ++i) {
+      int bn, l0;
+      const int nrows = tile_rows(i, bn, l0), s = i % ST;
+      const bool live = r < nrows;
+      const int l = min(l0 + r, L - 1);
+      const int y = l / W, x = l - y * W;
+      const size_t grow = (size_t)bn * L + l;
+      float qf[DKH];
+#pragma unroll
+      for (int e = 0; e < DKH; e += 4) {
+        const float4 t4 = live ? __ldg(reinterpret_cast<const float4*>(qg + grow * DKH + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        qf[e] = t4.x; qf[e + 1] = t4.y; qf[e + 2] = t4.z; qf[e + 3] = t4.w;
+      }
+      // ---- this row of the staged dQa tile: [ dq | dAq | dBq ] ----
+      tc::mbar_wait(&sm.bar_full[s], (i / ST) & 1);
+      const uint32_t irow = smem_u32(sm.in[s]) + r * (C::KD * 4);
+      float cur[DKH];
+      uint32_t pa[W / 2 + 2], pb[H / 2 + 2];        // packed pairs with a zero word on either side
+      pa[0] = pa[W / 2 + 1] = pb[0] = pb[H / 2 + 1] = 0u;
+#pragma unroll
+      for (int c = 0; c < DKH / 4; ++c) {
+        const float4 t4 = live ? lds128f(irow + 16 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        cur[4 * c] = t4.x; cur[4 * c + 1] = t4.y; cur[4 * c + 2] = t4.z; cur[4 * c + 3] = t4.w;
+      }
+      load_pairs<W, DKH * 4>(irow, live, pa);
+      load_pairs<H, (DKH + W) * 4>(irow, live, pb);
+      {   // release the stage only once every load above has delivered (see mbar_arrive_after)
+        uint32_t fold = 0u;
+#pragma unroll
+        for (int e = 0; e < DKH; ++e) fold ^= __float_as_uint(cur[e]);
+#pragma unroll
+        for (int j = 1; j <= W / 2; ++j) fold ^= pa[j];
+#pragma unroll
+        for (int j = 1; j <= H / 2; ++j) fold ^= pb[j];
+        tc::mbar_arrive_after(&sm.bar_empty[s], fold & zmask);
+      }
+      // ---- the previous tile's products are done: its D1 leaves, and the A / q tiles may be rewritten ----
+      if (i > 0) finish_prev(i - 1);
+#pragma unroll
+      for (int e = 0; e < DKH; ++e) dqc[e] = cur[e];
+      {
+        const int b = bn / nh, n = bn - b * nh;
+        dst_prev = live ? dqkvh + ((size_t)b * L + l) * KPq + n * DKH : nullptr;
+      }
+      // zero row, then the two windows: word j of a window = pairs shifted by the parity of its start column
+#pragma unroll
+      for (int at = 0; at < KA; ++at)
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) sts128(arow + at * (AB_BM * 128) + (ch << 4), 0u, 0u, 0u, 0u);
+      auto put_word = [&](int wi, uint32_t v) {      // packed A columns 2 wi, 2 wi + 1
+        const uint32_t at = (uint32_t)wi >> 5, w5 = (uint32_t)wi & 31;
+        sts32(arow + at * (AB_BM * 128) + ((((w5 >> 2) ^ swz) << 4) | ((w5 & 3) << 2)), v);
+      };
+      {
+        const int sh = W - 1 - x, w0 = sh >> 1;
+        const uint32_t fs = (uint32_t)(sh & 1) << 4;
+#pragma unroll
+        for (int j = 0; j <= W / 2; ++j) put_word(w0 + j, __funnelshift_l(pa[j], pa[j + 1], fs));
+      }
+      {
+        const int sh = C::NW + H - 1 - y, w0 = sh >> 1;
+        const uint32_t fs = (uint32_t)(sh & 1) << 4;
+#pragma unroll
+        for (int j = 0; j <= H / 2; ++j) put_word(w0 + j, __funnelshift_l(pb[j], pb[j + 1], fs));
+      }
+      // q row (bf16) into the q tile: columns [0, 32)
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t w4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = 8 * ch + 2 * u;
+          w4[u] = e < DKH ? tc::pack_bf16x2(qf[e < DKH ? e : 0], qf[e + 1 < DKH ? e + 1 : 0]) : 0u;
+        }
+        sts128(qrow + (((uint32_t)ch ^ swz) << 4), w4[0], w4[1], w4[2], w4[3]);
+      }
+      tc::fence_proxy_async();
+      if (dbg & 2) asm volatile("bar.sync 2, 128;" ::: "memory");
+      tc::mbar_arrive(&sm.bar_a_ready);
+    }
+    if (my_tiles > 0) {
+      finish_prev(my_tiles - 1);                     // also: every MMA of this CTA has completed
+      // ---- key_rel gradient partial: D2 block b, lane = A column (colbase + r), 32 columns = e ----
+      tc::tc_fence_after();
+      float* out = partial + (size_t)blockIdx.x * 2 * RP * DK8;
+#pragma unroll
+      for (int b = 0; b < C::NBLK; ++b) {
+        uint32_t d2[32];
+        tc::tmem_ld_x32(tlane + COL_D2 + 32 * b, d2);
+        tc::tmem_ld_wait();
+        const int k = (b == 0 ? 0 : (KA - 2) * 64) + r;
+        if (b == 1 && k < 128) continue;             // columns already covered by block 0
+        const int axis = k >= C::NW ? 1 : 0, rr = k - (axis ? C::NW : 0);
+        if (rr < (axis ? 2 * H - 1 : 2 * W - 1) && rr < RP) {
+          float* o = out + ((size_t)axis * RP + rr) * DK8;
+#pragma unroll
+          for (int e = 0; e < DKH; ++e) o[e] = __uint_as_float(d2[e]);
+        }
+      }
+      tc::tc_fence_before();
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tc::tmem_dealloc<128>(tmem);
+}
+
+template <int W, int H, int DKH>
+int launch_rel_bwd_tc(const Dims& d, const float* dqa, const float* q, const float* krw, const float* krh, void* dqkvh, int KPq,
+                      float* partial, int RP, int DK8, int* grid_out, cudaStream_t st) {
+  typedef RbCfg<W, H, DKH> C;
+  const size_t smem = sizeof(RbSmem<C>) + 1024;
+  auto kern = rel_bwd_tc_kernel<W, H, DKH>;
+  AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles_per_bn = cdiv(d.L, AB_BM), ntiles = tiles_per_bn * d.BN;
+  const int grid = std::min(ntiles, sm_count_ab());
+  static const int dbg = [] { const char* e = getenv("AACONV_RB_DBG"); return e ? atoi(e) : 0; }();   // debugging experiments
+  kern<<<grid, 192, smem, AACONV_ST(st)>>>(dqa, q, krw, krh, static_cast<bf16*>(dqkvh), partial, d.L, d.nh, KPq, RP, DK8, d.qscale,
+                                           tiles_per_bn, ntiles, dbg);
+  AACONV_LAUNCH_OK("rel_bwd_tc");
+  *grid_out = grid;
+  return 0;
+}
+
+}  // namespace
+
+// same shapes as the builder, bf16 packed output only (KPq a multiple of 4: 8-byte stores)
+int rel_bwd_tc_supported(const Dims& d, int KPq) {
+  if (aug_build_tc_supported(d)) return AACONV_E_UNSUPPORTED;
+  if (KPq & 3) return AACONV_E_UNSUPPORTED;
+  return 0;
+}
+
+// -> number of partials written (one per CTA), layout [part][axis][RP][DK8] as rel_bwd_kernel's
+int rel_bwd_tc(const Dims& d, const float* dqa, const float* q, const float* krw, const float* krh, void* dqkvh, int KPq,
+               float* partial, int RP, int DK8, int* nparts, cudaStream_t st) {
+  if (rel_bwd_tc_supported(d, KPq)) return fail(AACONV_E_UNSUPPORTED, "rel_bwd_tc: shape not covered");
+  switch (d.W) {
+    case 10: return launch_rel_bwd_tc<10, 10, 20>(d, dqa, q, krw, krh, dqkvh, KPq, partial, RP, DK8, nparts, st);
+    case 20: return launch_rel_bwd_tc<20, 20, 20>(d, dqa, q, krw, krh, dqkvh, KPq, partial, RP, DK8, nparts, st);
+    case 40: return launch_rel_bwd_tc<40, 40, 20>(d, dqa, q, krw, krh, dqkvh, KPq, partial, RP, DK8, nparts, st);
+    default: return launch_rel_bwd_tc<64, 64, 20>(d, dqa, q, krw, krh, dqkvh, KPq, partial, RP, DK8, nparts, st);
   }
 }
 

@@ -118,10 +118,11 @@ int bf16_backward(const Dims& d, const void* xin, const aaconv_params* p, const 
   Scratch w(d, scratch, 0);
   // typed boundary / fused prologue: the kernels below produce the gradient wrt the AAConv2d input in w.dxraw; the last step
   // turns it into dx (InstanceNorm + ReLU adjoint, or a plain type conversion).  Otherwise they write dx directly.
-  const bool typed = d.x_bf16 || d.fuse_in;
+  // (a bf16 x without the fused prologue whose raw gradient is already bf16 needs no second pass: dgrad writes dx itself)
+  const bool typed = d.fuse_in || (d.x_bf16 && !w.dxraw_bf16);
   void* const dxv = !dx_out ? nullptr : (typed ? w.dxraw : dx_out);
   float* const dx = static_cast<float*>(dxv);                      // fp32 view for the FFMA fallbacks
-  const int dx_bf16 = typed ? w.dxraw_bf16 : 0;
+  const int dx_bf16 = typed ? w.dxraw_bf16 : d.x_bf16;
   const float* x = static_cast<const float*>(xin);
   const AugLayout a = aug_layout(d);
   const float* q = at<float>(saved, f32_saved_offset(d, "q"));

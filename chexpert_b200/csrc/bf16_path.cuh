@@ -21,6 +21,11 @@ int aug_build_fwd(const Dims& d, const float* q, const float* k, const float* v,
 int aug_build_tc_supported(const Dims& d);
 int aug_build_tc(const Dims& d, const float* q, const float* k, const float* v, const float* krw, const float* krh,
                  void* qa, void* ka, cudaStream_t st);
+// aug_tc.cu: tcgen05 version of rel_bwd (bf16 packed output only); partials in rel_bwd's layout, summed by rel_bwd_reduce
+int rel_bwd_tc_supported(const Dims& d, int KPq);
+int rel_bwd_tc(const Dims& d, const float* dqa, const float* q, const float* krw, const float* krh, void* dqkvh, int KPq,
+               float* partial, int RP, int DK8, int* nparts, cudaStream_t st);
+int rel_bwd_reduce(const Dims& d, const float* partial, int nparts, int RP, int DK8, float* dkrw, float* dkrh, cudaStream_t st);
 // (B,nh,L,L) softmax map from the bf16 operands and the bf16 forward kernel's lse (visualise path)
 int aug_weights(const Dims& d, const void* qa, const void* ka, const float* lse, float* weights, cudaStream_t st);
 int aug_patch_bwd(const Dims& d, const float* lse, const float* d_o, const float* o, void* qa, float* delta, cudaStream_t st);

@@ -33,6 +33,15 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrive that cannot ISSUE before the registers feeding `dep_zero` have been written.  A consumer that releases a shared-memory
+// stage after ld.shared'ing it must use this when nothing else consumes the loaded registers before the arrive: the loads
+// are asynchronous (only a later USE of their destination registers waits for them), the arrive is not ordered behind them,
+// and the producer's TMA write may then overwrite the stage while the last loads are still queued -- seen as run-to-run
+// differences in the last-loaded 16-byte chunks of rel_bwd_tc's rows (single-stage configuration, 512 px).
+// dep_zero = (xor of the loaded registers) & zmask with zmask == 0 at run time but unknown to the compiler.
+__device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, uint32_t dep_zero) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(1u + dep_zero) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
