@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) attn_fwd_cc_kernel(
 // ================================================================================================
 // backward
 // ================================================================================================
-constexpr int CB_BM = 128, CB_BN = 64, CB_MAXSLOTS = 5;
+constexpr int CB_BM = 128, CB_BN = 64, CB_MAXSLOTS = 7;
 // three math warpgroups (global tile t -> warpgroup t % 3): three warps per scheduler keep the MUFU pipe busy while the others sit
 // in TMEM load / store / barrier latencies;  then one TMA warp, the score-MMA issuer (+TMEM alloc) and the gradient-MMA issuer
 // (warp CB_W_G), and TWO score-MMA issuers (CB_W_S even global tiles + TMEM alloc, CB_W_S2 odd ones): the timeline showed a
@@ -398,9 +398,9 @@ constexpr int CB_NWG = 3, CB_W_TMA = 4 * CB_NWG, CB_W_S = CB_W_TMA + 1, CB_W_G =
 // Streamed-tile stages.  A stage is held from its TMA issue until the tile's GRADIENT MMA has completed (~3.5 tiles of
 // pipeline), so the prefetch lead is ST - 4.5 tiles; with 6 stages the score issuer waited 400-900 cycles per tile for the
 // K tile to land (timeline).  The dQa kernel also holds a 24-88 KB staging tile (sized by OUTW >= KD), the dK/dV kernel does not.
-template <int KATOMS, int OUT_FLOATS> struct CbStages {   // as many as fit beside the stationary tile and the staging tile
-  static constexpr int fixed = 1024 /*alignment slack*/ + 4096 /*side rows, barriers*/ + 2048 /*static dV exchange*/;
-  static constexpr int avail = 232448 - fixed - KATOMS * CB_BM * 128 - OUT_FLOATS * 4;
+template <int KATOMS, int OUT_FLOATS, int NSTAT = 1> struct CbStages {   // as many as fit beside the stationary tile(s) and the staging tile
+  static constexpr int fixed = 1024 /*alignment slack*/ + (NSTAT > 1 ? 8192 : 4096) /*side rows, barriers*/ + (NSTAT > 1 ? 4096 : 2048) /*static dV exchange*/;
+  static constexpr int avail = 232448 - fixed - NSTAT * KATOMS * CB_BM * 128 - OUT_FLOATS * 4;
   static constexpr int fit = avail / (KATOMS * CB_BN * 128);
   static constexpr int value = fit > 10 ? 10 : fit;
   static_assert(value >= 3, "not enough shared memory for three streamed stages");
@@ -419,10 +419,12 @@ template <int KATOMS, int OUT_FLOATS> struct CbStages {   // as many as fit besi
 // (and an item of a single tile would leave one issuer without a commit on bar_s_done for that item)
 __host__ __device__ constexpr int cb_issuers(int stages, int ntiles) { return (stages >= 4 && ntiles >= 2) ? 2 : 1; }
 struct CbPlan { int QB, NS; uint32_t col_slot0, col_acc; };
-__device__ __forceinline__ CbPlan cb_plan(int katoms, int acc_cols, int stages, int ntiles) {
+// qb = 1: the stationary operand lives in TMEM (TS-mode score MMAs, at most 5 slots); qb = 0: it stays in shared memory
+// (SS-mode, double-buffered by item parity) and its columns become score slots
+__device__ __forceinline__ CbPlan cb_plan(int katoms, int acc_cols, int stages, int ntiles, int qb = 1) {
   CbPlan p;
-  p.QB = 1;
-  p.NS = min(CB_MAXSLOTS, (512 - p.QB * katoms * 32 - acc_cols) / 64);
+  p.QB = qb;
+  p.NS = min(qb ? 5 : CB_MAXSLOTS, (512 - p.QB * katoms * 32 - acc_cols) / 64);
   if (stages & 1) p.NS = min(p.NS, stages);
   // Math warpgroups: global tile t belongs to warpgroup t % 3, so before waiting for S'(t) on slot t % NS a warpgroup has
   // seen S'(t-3) complete; the slot's previous phase is S'(t-NS).  With ONE issuer the score MMAs complete in order and
@@ -434,10 +436,11 @@ __device__ __forceinline__ CbPlan cb_plan(int katoms, int acc_cols, int stages, 
   return p;
 }
 
-template <int KATOMS, int SIDE_FLOATS, int OUT_FLOATS, int ROW_FLOATS>
+template <int KATOMS, int SIDE_FLOATS, int OUT_FLOATS, int ROW_FLOATS, int NSTAT = 1>
 struct __align__(1024) CbSmem {
-  static constexpr int ST = CbStages<KATOMS, OUT_FLOATS>::value;
-  bf16 stat[KATOMS][CB_BM * 64];
+  static constexpr int ST = CbStages<KATOMS, OUT_FLOATS, NSTAT>::value;
+  static constexpr int NST = NSTAT;
+  bf16 stat[NSTAT * KATOMS][CB_BM * 64];         // NSTAT = 2 (SS mode): buffer (item parity) * KATOMS + atom
   bf16 strm[ST][KATOMS][CB_BN * 64];
   float side[ST][SIDE_FLOATS];                 // fp32 side tile: v (dq kernel) or dO | delta (dkv kernel)
   float rowside[2][CB_BM * ROW_FLOATS];        // fp32 rows of the stationary tile (dO | delta, or v), by item parity
@@ -456,7 +459,8 @@ __device__ __forceinline__ void cb_load_stat(Smem& sm, const CUtensorMap* m_stat
   const int nrows = min(CB_BM, L - row0);
   const size_t g0 = (size_t)bn * L + row0;
   tc::mbar_arrive_expect_tx(&sm.bar_stat, KATOMS * CB_BM * 64 * 2 + nrows * (RW0 + RW1) * 4);
-  for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.stat[a], m_stat, &sm.bar_stat, a * 64, row0, bn);
+  const int sb = (Smem::NST > 1 ? (parity & 1) : 0) * KATOMS;
+  for (int a = 0; a < KATOMS; ++a) tc::tma_load_3d(sm.stat[sb + a], m_stat, &sm.bar_stat, a * 64, row0, bn);
   bulk_g2s(sm.rowside[parity], r0 + g0 * RW0, nrows * RW0 * 4, &sm.bar_stat);
   if (RW1) bulk_g2s(sm.rowside[parity] + CB_BM * RW0, r1 + g0 * RW1, nrows * RW1 * 4, &sm.bar_stat);
 }
@@ -506,6 +510,7 @@ __device__ __forceinline__ void cb_producer(Smem& sm, const CUtensorMap* m_stat,
         const int nitem = item + gridDim.x, nbn = nitem / nqt, nrow0 = (nitem - nbn * nqt) * CB_BM;   // has moved this item's to TMEM
         tc::hb(1, it * 1000 + j);
         tc::mbar_wait(&sm.bar_stat_free, it & 1);
+        if (Smem::NST > 1 && it > 0) tc::mbar_wait(&sm.bar_s_done, (it - 1) & 1);   // SS mode: item it-1's score MMAs have read stat[(it+1)&1]
         tc::hb(1, 500000 + it * 1000 + j);
         cb_load_stat<KATOMS>(sm, m_stat, r0, RW0, r1, RW1, L, nbn, nrow0, (it + 1) & 1);
       }
@@ -535,13 +540,19 @@ __device__ __forceinline__ void cb_score_loop(Smem& sm, uint32_t tmem, CbPlan pl
   Ring rst, rsl;
   for (int i = 0; i < sidx; ++i) { rst.next(Smem::ST); rsl.next(NS); }
   int it = 0, j = sidx, a_it = -1;
-  uint32_t a_tmem = tmem;
+  uint32_t a_tmem = tmem, a_smem = 0;
+  constexpr uint32_t STAT_ATOM = (CB_BM * 128) >> 4;
   for (int t = sidx; t < total; t += nstep) {
     while (j >= ntiles) { j -= ntiles; ++it; }
     if (it != a_it) {                              // first tile of an item for this issuer: its stationary operand is in TMEM
-      tc::mbar_wait(&sm.bar_a_ready, it & 1);
+      if (Smem::NST > 1) {                           // (SS mode: in shared memory buffer it & 1, landed with bar_stat)
+        tc::mbar_wait(&sm.bar_stat, it & 1);
+        a_smem = tc::desc_lo_k(smem_u32(sm.stat[(it & 1) * KATOMS]));
+      } else {
+        tc::mbar_wait(&sm.bar_a_ready, it & 1);
+        a_tmem = tmem + (uint32_t)((it & (pl.QB - 1)) * KATOMS * 32);
+      }
       a_it = it;
-      a_tmem = tmem + (uint32_t)((it & (pl.QB - 1)) * KATOMS * 32);
     }
     const int st = rst.i, slot = rsl.i;
     TL_STAMP(tl, 0, t);
@@ -552,7 +563,8 @@ __device__ __forceinline__ void cb_score_loop(Smem& sm, uint32_t tmem, CbPlan pl
     tc::tc_fence_after();
     TL_STAMP(tl, 2, t);
     if (tc::elect_one()) {
-      tc::issue_ts_ksteps<NKS, 0, STRM_ATOM>(tmem + pl.col_slot0 + 64 * slot, 0u, a_tmem, strm_lo + st * STAGE, idesc_s);
+      if (Smem::NST > 1) tc::issue_ss_ksteps<NKS, STAT_ATOM, STRM_ATOM>(tmem + pl.col_slot0 + 64 * slot, a_smem, strm_lo + st * STAGE, idesc_s);
+      else tc::issue_ts_ksteps<NKS, 0, STRM_ATOM>(tmem + pl.col_slot0 + 64 * slot, 0u, a_tmem, strm_lo + st * STAGE, idesc_s);
       tc::mma_commit(&sm.bar_s_full[slot]);
       if (j + nstep >= ntiles) tc::mma_commit(&sm.bar_s_done);   // this issuer's last tile of the item
     }
@@ -850,19 +862,21 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dq_cc_kernel(
 
 // ---- key-stationary: dK, dV ------------------------------------------------------------------------
 // TMEM: Ka buffers [0, QB*32K); slot s: S'^T at col_slot0 + 64 s (dS^T, bf16, over its first 32 columns); dK (32) behind the slots.
-template <int KATOMS, int DVH>
+// SS = 1: the stationary Ka tile stays in shared memory (SS-mode score MMAs, double-buffered by item parity); its TMEM columns
+// become score slots: 7 instead of 5 (the pipeline is bound by tiles in flight / chain latency, see cb_plan).
+template <int KATOMS, int DVH, int SS>
 __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
     const __grid_constant__ CUtensorMap tm_k_stat, const __grid_constant__ CUtensorMap tm_q_strm,
     const float* __restrict__ v, const float* __restrict__ d_o, const float* __restrict__ delta, float* __restrict__ dk,
     float* __restrict__ dv, bf16* __restrict__ dqkvh, int KPq, int nh, int L, int dkh, int C1, int nqt, int nitems) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  typedef CbSmem<KATOMS, CB_BN * (DVH + 1), 0, DVH> Smem;
+  typedef CbSmem<KATOMS, CB_BN * (DVH + 1), 0, DVH, SS ? 2 : 1> Smem;
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int ST = Smem::ST;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = (L + CB_BN - 1) / CB_BN;
   const int my_items = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const CbPlan pl = cb_plan(KATOMS, 32, ST, ntiles);
+  const CbPlan pl = cb_plan(KATOMS, 32, ST, ntiles, SS ? 0 : 1);
   __shared__ float dv_xch[2][CB_NWG][CB_BM][DVH];       // dV partial of every tile class (j % 3), by item parity
 
   cb_init<KATOMS>(sm, warp, lane, &tm_k_stat, &tm_q_strm, nqt, v, DVH, nullptr, 0, L);
@@ -882,8 +896,10 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
     const int NS = pl.NS;
     auto stage_stat = [&](int it) {
       tc::mbar_wait(&sm.bar_stat, it & 1);
-      stationary_to_tmem<KATOMS>(sm.stat, tlane + (uint32_t)((it & (pl.QB - 1)) * KATOMS * 32), rowi);
-      tc::mbar_arrive(&sm.bar_a_ready);
+      if (!SS) {
+        stationary_to_tmem<KATOMS>(sm.stat, tlane + (uint32_t)((it & (pl.QB - 1)) * KATOMS * 32), rowi);
+        tc::mbar_arrive(&sm.bar_a_ready);
+      }
     };
     if (wg == 0) stage_stat(0);
     uint32_t rs[2][32], pd[32];
@@ -894,7 +910,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
       const int item = blockIdx.x + it * gridDim.x, bn = item / nqt, qt = item - bn * nqt, k0 = qt * CB_BM;
       const int kj = k0 + rowi;
       const size_t row = (size_t)bn * L + kj;
-      if (wg != 0) tc::mbar_wait(&sm.bar_stat, it & 1);   // this row's v came with the stationary tile
+      if (wg != 0 || SS) tc::mbar_wait(&sm.bar_stat, it & 1);   // this row's v came with the stationary tile
       float vk[DVH], dvacc[DVH];
 #pragma unroll
       for (int e = 0; e < DVH; ++e) { vk[e] = kj < L ? sm.rowside[it & 1][rowi * DVH + e] : 0.f; dvacc[e] = 0.f; }
@@ -937,7 +953,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) attn_bwd_dkv_cc_kernel(
       for (int e = 0; e < DVH; ++e) dv_xch[it & 1][cls][rowi][e] = dvacc[e];
       tc::mbar_arrive(&sm.bar_dv);
       if (wg > 0) continue;
-      if (it + 1 < my_items) {                         // single stationary buffer: refill once the item's score MMAs are done
+      if (!SS && it + 1 < my_items) {                  // single stationary TMEM buffer: refill once the item's score MMAs are done
         tc::mbar_wait(&sm.bar_s_done, it & 1);
         tc::tc_fence_after();
         stage_stat(it + 1);
@@ -1042,9 +1058,17 @@ int launch_bwd_cc(const Dims& d, const AugLayout& a, const void* qa, const void*
   AACONV_TRY(make_aug_map(d, qa, a.KP, CB_BN, &tq_strm));
   const int nqt = cdiv(d.L, CB_BM), nitems = nqt * d.BN;
   const int grid = std::min(nitems, sm_count());
-  {
+  static const bool dkv_ss = [] { const char* e = getenv("AACONV_DKV_SS"); return e ? atoi(e) != 0 : false; }();   // A/B (profiles/r02_attn_ab.md): SS mode measured slower (167 vs 162 us), default off
+  if (dkv_ss && KATOMS <= 2) {
+    const size_t smem = sizeof(CbSmem<KATOMS, CB_BN * (DVH + 1), 0, DVH, 2>) + 1024;
+    auto kern = attn_bwd_dkv_cc_kernel<KATOMS, DVH, 1>;
+    AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, CB_THREADS, smem, AACONV_ST(st)>>>(tk_stat, tq_strm, v, d_o, delta, dk, dv, static_cast<bf16*>(dqkvh), KPq, d.nh, d.L, d.dkh, a.C1,
+                                         nqt, nitems);
+    AACONV_LAUNCH_OK("attn_bwd_dkv_cc");
+  } else {
     const size_t smem = sizeof(CbSmem<KATOMS, CB_BN * (DVH + 1), 0, DVH>) + 1024;
-    auto kern = attn_bwd_dkv_cc_kernel<KATOMS, DVH>;
+    auto kern = attn_bwd_dkv_cc_kernel<KATOMS, DVH, 0>;
     AACONV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, CB_THREADS, smem, AACONV_ST(st)>>>(tk_stat, tq_strm, v, d_o, delta, dk, dv, static_cast<bf16*>(dqkvh), KPq, d.nh, d.L, d.dkh, a.C1,
                                          nqt, nitems);

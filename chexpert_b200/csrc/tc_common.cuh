@@ -247,6 +247,13 @@ __device__ __forceinline__ void issue_ts_ksteps(uint32_t d_main, uint32_t d_extr
     mma_ts(d_main, a_tmem + ks * 8, desc64(b_lo + (ks >> 2) * B_ATOM + (ks & 3) * 2), idesc, ks > 0 ? 1u : 0u);
   if (EXTRA) mma_ts(d_extra, a_tmem + NKS * 8, desc64(b_lo + (NKS >> 2) * B_ATOM + (NKS & 3) * 2), idesc, 0u);
 }
+// the same with A in shared memory (K-major, 64-column atoms A_ATOM descriptor units apart)
+template <int NKS, uint32_t A_ATOM, uint32_t B_ATOM>
+__device__ __forceinline__ void issue_ss_ksteps(uint32_t d_main, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+#pragma unroll
+  for (int ks = 0; ks < NKS; ++ks)
+    mma_ss(d_main, desc64(a_lo + (ks >> 2) * A_ATOM + (ks & 3) * 2), desc64(b_lo + (ks >> 2) * B_ATOM + (ks & 3) * 2), idesc, ks > 0 ? 1u : 0u);
+}
 template <int EXTRA, uint32_t B_ATOM>
 __device__ __forceinline__ void issue_ts_ksteps_n(int nks, uint32_t d_main, uint32_t d_extra, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc) {
   switch (nks) {   // warp-uniform
