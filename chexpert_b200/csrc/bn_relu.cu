@@ -7,7 +7,7 @@
 // Welford reduce_kernel + three elementwise kernels: the buffered block was 7 % slower than torch.cat), and even on the fast
 // path BN + ReLU forward / backward are 4 + 8 passes over the activations with ONE CTA per channel for the reductions (64
 // CTAs on 148 SMs at the first layers).  Here:
-//   forward   bn_stats   grid (C, B): per-(b, c)-plane (count, mean, M2) partials, Chan-merged later -> no cancellation.
+//   forward   bn_stats   grid (C, G) (G groups of batch planes, see Geo): per-group (mean, M2) partials, Chan-merged later -> no cancellation.
 //                        In a dense block layer i normalises channels [0, c_i) of which [0, c_{i-1}) were already reduced by
 //                        layer i-1 (same data, same statistics): the caller keeps ONE partial buffer per block and passes
 //                        `stats_valid_channels`, so only the layer's 32 new channels are reduced (the pass shrinks ~5x)
@@ -17,6 +17,7 @@
 //             bn_bwd_dx  grid (C, B): merges the partials (fixed order), dx = w rstd (g - mean(g) - x^ mean(g x^));
 //                        the b = 0 block writes dweight = sum g x^ and dbias = sum g
 // 3 / 5 passes, all reductions in a fixed order (bit-reproducible), x read through its strides, y / dx dense.
+#include <algorithm>
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -65,45 +66,66 @@ __device__ __forceinline__ float2 block_sum2(float a, float b, float2* sh) {
   return t;
 }
 
-// partial[(c * B + b)] = (mean, M2) of plane (b, c): two passes over a plane that stays in L1 / L2 between them
-template <class T>
-__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, long long xbs, int HW, float2* __restrict__ partial, int c_from) {
-  __shared__ float2 sh[8];
-  const int c = c_from + blockIdx.x, b = blockIdx.y, B = gridDim.y;
-  const T* px = x + (size_t)b * xbs + (size_t)c * HW;
-  const bool vec = (HW & 3) == 0 && (reinterpret_cast<uintptr_t>(px) & 15) == 0;
-  float s = 0.f;
-  if (vec) for (int i = threadIdx.x * 4; i < HW; i += 1024) { const float4 v = ld4(px + i); s += (v.x + v.y) + (v.z + v.w); }
-  else for (int i = threadIdx.x; i < HW; i += 256) s += ld1(px + i);
-  const float mean = block_sum2(s, 0.f, sh).x / (float)HW;
-  float q = 0.f;
-  if (vec) {
-    for (int i = threadIdx.x * 4; i < HW; i += 1024) {
-      const float4 v = ld4(px + i);
-      const float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
-      q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
-    }
-  } else {
-    for (int i = threadIdx.x; i < HW; i += 256) { const float a0 = ld1(px + i) - mean; q += a0 * a0; }
-  }
-  const float m2 = block_sum2(q, 0.f, sh).x;
-  if (threadIdx.x == 0) partial[(size_t)c * B + b] = make_float2(mean, m2);
+// Work decomposition.  One CTA handles channel c of a GROUP of `bpb` consecutive batch planes (grid (C, G), G = ceil(B / bpb)):
+// bpb is chosen on the host so that a CTA touches ~8 k elements whatever the plane size.  With one CTA per (b, c) plane the
+// 20x20 and 10x10 blocks of DenseNet121 launched 10-12 k CTAs of 100-400 elements each (25 active threads at 10x10): the four
+// kernels averaged 4-16 us per call against 1-3 us of HBM time and were 31 % of the training step (round-2 profile).
+// Inside a CTA the 256 threads form a (256 / tx) x tx grid, tx = the power of two covering a plane's vectors: ty planes are
+// processed side by side; no integer division anywhere.
+struct Geo {
+  int B, HW, bpb, G;
+  int unit;          // elements per access: 4 (vector path) or 1
+  int n_unit;        // HW / unit
+  int txl;           // log2(tx)
+  long long xbs;
+};
+__device__ __forceinline__ int planes_of(const Geo& g, int grp) { return min(g.bpb, g.B - grp * g.bpb); }
+
+// f(plane-in-group, element offset) over this thread's share of the group
+template <class F>
+__device__ __forceinline__ void for_each(const Geo& g, int nplanes, F f) {
+  const int tx = 1 << g.txl, ox = threadIdx.x & (tx - 1), py = threadIdx.x >> g.txl, ty = 256 >> g.txl;
+  for (int p = py; p < nplanes; p += ty)
+    for (int o = ox; o < g.n_unit; o += tx) f(p, o * g.unit);
 }
 
-// Chan merge of the B plane partials of channel c, in batch order: -> (mean, biased var).  The partials are fetched by the
-// block's threads in parallel (ONE memory latency, not B dependent ones: with the merge as a serial load loop every block
-// spent ~5 us before touching its plane and bn_apply averaged 29 us), then combined by thread 0 in a fixed order.
-__device__ __forceinline__ float2 merge_stats(const float2* __restrict__ partial, int c, int B, int HW, float2* sh /*[257]*/) {
+// partial[c * G + grp] = (mean, M2) of channel c over the planes of group grp: two passes (the data stays in L1 / L2 between them)
+template <class T>
+__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, const Geo g, float2* __restrict__ partial, int c_from) {
+  __shared__ float2 sh[8];
+  const int c = c_from + blockIdx.x, grp = blockIdx.y, np = planes_of(g, grp);
+  const T* px = x + (size_t)(grp * g.bpb) * g.xbs + (size_t)c * g.HW;
+  float s = 0.f;
+  if (g.unit == 4) for_each(g, np, [&](int p, int o) { const float4 v = ld4(px + (size_t)p * g.xbs + o); s += (v.x + v.y) + (v.z + v.w); });
+  else for_each(g, np, [&](int p, int o) { s += ld1(px + (size_t)p * g.xbs + o); });
+  const float mean = block_sum2(s, 0.f, sh).x / ((float)np * g.HW);
+  float q = 0.f;
+  if (g.unit == 4) {
+    for_each(g, np, [&](int p, int o) {
+      const float4 v = ld4(px + (size_t)p * g.xbs + o);
+      const float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+      q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    });
+  } else {
+    for_each(g, np, [&](int p, int o) { const float a0 = ld1(px + (size_t)p * g.xbs + o) - mean; q += a0 * a0; });
+  }
+  const float m2 = block_sum2(q, 0.f, sh).x;
+  if (threadIdx.x == 0) partial[(size_t)c * g.G + grp] = make_float2(mean, m2);
+}
+
+// Chan merge of the G group partials of channel c, in group order: -> (mean, biased var).  The partials are fetched by the
+// block's threads in parallel (ONE memory latency, not G dependent ones), then combined by thread 0 in a fixed order.
+__device__ __forceinline__ float2 merge_stats(const float2* __restrict__ partial, int c, const Geo& g, float2* sh /*[257]*/) {
   float n = 0.f, mean = 0.f, m2 = 0.f;
-  for (int b0 = 0; b0 < B; b0 += 256) {
-    const int nb_ = min(256, B - b0);
+  for (int g0 = 0; g0 < g.G; g0 += 256) {
+    const int ng = min(256, g.G - g0);
     __syncthreads();
-    if ((int)threadIdx.x < nb_) sh[threadIdx.x] = partial[(size_t)c * B + b0 + threadIdx.x];
+    if ((int)threadIdx.x < ng) sh[threadIdx.x] = partial[(size_t)c * g.G + g0 + threadIdx.x];
     __syncthreads();
     if (threadIdx.x == 0) {
-      for (int i = 0; i < nb_; ++i) {
+      for (int i = 0; i < ng; ++i) {
         const float2 p = sh[i];
-        const float nb = (float)HW, tot = n + nb, d = p.x - mean;
+        const float nb = (float)planes_of(g, g0 + i) * g.HW, tot = n + nb, d = p.x - mean;
         mean += d * (nb / tot);
         m2 += p.y + d * d * (n * nb / tot);
         n = tot;
@@ -114,16 +136,16 @@ __device__ __forceinline__ float2 merge_stats(const float2* __restrict__ partial
   __syncthreads();
   return sh[256];
 }
-// plain sums of the B plane partials of channel c, in batch order
-__device__ __forceinline__ float2 merge_sums(const float2* __restrict__ partial, int c, int B, float2* sh /*[257]*/) {
+// plain sums of the G group partials of channel c, in group order
+__device__ __forceinline__ float2 merge_sums(const float2* __restrict__ partial, int c, int G, float2* sh /*[257]*/) {
   float s1 = 0.f, s2 = 0.f;
-  for (int b0 = 0; b0 < B; b0 += 256) {
-    const int nb_ = min(256, B - b0);
+  for (int g0 = 0; g0 < G; g0 += 256) {
+    const int ng = min(256, G - g0);
     __syncthreads();
-    if ((int)threadIdx.x < nb_) sh[threadIdx.x] = partial[(size_t)c * B + b0 + threadIdx.x];
+    if ((int)threadIdx.x < ng) sh[threadIdx.x] = partial[(size_t)c * G + g0 + threadIdx.x];
     __syncthreads();
     if (threadIdx.x == 0)
-      for (int i = 0; i < nb_; ++i) { s1 += sh[i].x; s2 += sh[i].y; }
+      for (int i = 0; i < ng; ++i) { s1 += sh[i].x; s2 += sh[i].y; }
   }
   if (threadIdx.x == 0) sh[256] = make_float2(s1, s2);
   __syncthreads();
@@ -131,138 +153,158 @@ __device__ __forceinline__ float2 merge_sums(const float2* __restrict__ partial,
 }
 
 template <class T>
-__global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, long long xbs, int HW, const float2* __restrict__ partial,
+__global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, const Geo g, const float2* __restrict__ partial,
                                                        const float* __restrict__ weight, const float* __restrict__ bias,
                                                        float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                                        float eps, T* __restrict__ y, float2* __restrict__ saved) {
   __shared__ float2 shm[257];
-  const int c = blockIdx.x, b = blockIdx.y, B = gridDim.y, C = gridDim.x;
-  const float2 st = merge_stats(partial, c, B, HW, shm);
+  const int c = blockIdx.x, grp = blockIdx.y, C = gridDim.x, np = planes_of(g, grp), b0 = grp * g.bpb;
+  const float2 st = merge_stats(partial, c, g, shm);
   const float rstd = rsqrtf(st.y + eps);
-  if (b == 0 && threadIdx.x == 0) {
+  if (grp == 0 && threadIdx.x == 0) {
     saved[c] = make_float2(st.x, rstd);
     if (running_mean) {                                    // nn.BatchNorm2d: unbiased variance in the running estimate
-      const float n = (float)B * HW;
+      const float n = (float)g.B * g.HW;
       running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * st.x;
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * st.y * (n / fmaxf(n - 1.f, 1.f));
     }
   }
   const float sc = weight[c] * rstd, sh = bias[c] - st.x * sc;
-  const T* px = x + (size_t)b * xbs + (size_t)c * HW;
-  T* py = y + ((size_t)b * C + c) * HW;
-  const bool vec = (HW & 3) == 0 && ((reinterpret_cast<uintptr_t>(px) | reinterpret_cast<uintptr_t>(py)) & 15) == 0;
-  if (vec) {
-    for (int i = threadIdx.x * 4; i < HW; i += 1024) {
-      const float4 v = ld4(px + i);
-      st4(py + i, make_float4(fmaxf(fmaf(v.x, sc, sh), 0.f), fmaxf(fmaf(v.y, sc, sh), 0.f), fmaxf(fmaf(v.z, sc, sh), 0.f),
-                              fmaxf(fmaf(v.w, sc, sh), 0.f)));
-    }
+  const T* px = x + (size_t)b0 * g.xbs + (size_t)c * g.HW;
+  T* py = y + ((size_t)b0 * C + c) * g.HW;
+  const size_t ybs = (size_t)C * g.HW;
+  if (g.unit == 4) {
+    for_each(g, np, [&](int p, int o) {
+      const float4 v = ld4(px + (size_t)p * g.xbs + o);
+      st4(py + p * ybs + o, make_float4(fmaxf(fmaf(v.x, sc, sh), 0.f), fmaxf(fmaf(v.y, sc, sh), 0.f), fmaxf(fmaf(v.z, sc, sh), 0.f),
+                                        fmaxf(fmaf(v.w, sc, sh), 0.f)));
+    });
   } else {
-    for (int i = threadIdx.x; i < HW; i += 256) st1(py + i, fmaxf(fmaf(ld1(px + i), sc, sh), 0.f));
+    for_each(g, np, [&](int p, int o) { st1(py + p * ybs + o, fmaxf(fmaf(ld1(px + (size_t)p * g.xbs + o), sc, sh), 0.f)); });
   }
 }
 
 // g = dy where the ReLU output is positive (recomputed from x and the saved statistics: y itself is not kept)
 template <class T>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict__ x, long long xbs, int HW, const T* __restrict__ dy,
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict__ x, const Geo g, const T* __restrict__ dy,
                                                             const float2* __restrict__ saved, const float* __restrict__ weight,
                                                             const float* __restrict__ bias, float2* __restrict__ partial) {
   __shared__ float2 sh[8];
-  const int c = blockIdx.x, b = blockIdx.y, B = gridDim.y, C = gridDim.x;
+  const int c = blockIdx.x, grp = blockIdx.y, C = gridDim.x, np = planes_of(g, grp), b0 = grp * g.bpb;
   const float2 st = saved[c];
   const float w = weight[c], bb = bias[c];
-  const T* px = x + (size_t)b * xbs + (size_t)c * HW;
-  const T* pg = dy + ((size_t)b * C + c) * HW;
-  const bool vec = (HW & 3) == 0 && ((reinterpret_cast<uintptr_t>(px) | reinterpret_cast<uintptr_t>(pg)) & 15) == 0;
+  const T* px = x + (size_t)b0 * g.xbs + (size_t)c * g.HW;
+  const T* pg = dy + ((size_t)b0 * C + c) * g.HW;
+  const size_t ybs = (size_t)C * g.HW;
   float s1 = 0.f, s2 = 0.f;
-  if (vec) {
-    for (int i = threadIdx.x * 4; i < HW; i += 1024) {
-      const float4 xv = ld4(px + i), gv = ld4(pg + i);
+  if (g.unit == 4) {
+    for_each(g, np, [&](int p, int o) {
+      const float4 xv = ld4(px + (size_t)p * g.xbs + o), gv = ld4(pg + p * ybs + o);
       const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const float xh = (xs[u] - st.x) * st.y;
-        const float g = fmaf(w, xh, bb) > 0.f ? gs[u] : 0.f;
-        s1 += g;
-        s2 = fmaf(g, xh, s2);
+        const float gg = fmaf(w, xh, bb) > 0.f ? gs[u] : 0.f;
+        s1 += gg;
+        s2 = fmaf(gg, xh, s2);
       }
-    }
+    });
   } else {
-    for (int i = threadIdx.x; i < HW; i += 256) {
-      const float xh = (ld1(px + i) - st.x) * st.y;
-      const float g = fmaf(w, xh, bb) > 0.f ? ld1(pg + i) : 0.f;
-      s1 += g;
-      s2 = fmaf(g, xh, s2);
-    }
+    for_each(g, np, [&](int p, int o) {
+      const float xh = (ld1(px + (size_t)p * g.xbs + o) - st.x) * st.y;
+      const float gg = fmaf(w, xh, bb) > 0.f ? ld1(pg + p * ybs + o) : 0.f;
+      s1 += gg;
+      s2 = fmaf(gg, xh, s2);
+    });
   }
   const float2 t = block_sum2(s1, s2, sh);
-  if (threadIdx.x == 0) partial[(size_t)c * B + b] = t;
+  if (threadIdx.x == 0) partial[(size_t)c * g.G + grp] = t;
 }
 
 template <class T>
-__global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const T* __restrict__ x, long long xbs, int HW, const T* __restrict__ dy,
+__global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const T* __restrict__ x, const Geo g, const T* __restrict__ dy,
                                                         const float2* __restrict__ saved, const float* __restrict__ weight,
                                                         const float* __restrict__ bias, const float2* __restrict__ partial,
                                                         T* __restrict__ dx, float* __restrict__ dweight, float* __restrict__ dbias) {
   __shared__ float2 shm[257];
-  const int c = blockIdx.x, b = blockIdx.y, B = gridDim.y, C = gridDim.x;
-  const float2 tot = merge_sums(partial, c, B, shm);                     // batch order
+  const int c = blockIdx.x, grp = blockIdx.y, C = gridDim.x, np = planes_of(g, grp), b0 = grp * g.bpb;
+  const float2 tot = merge_sums(partial, c, g.G, shm);                   // group order
   const float s1 = tot.x, s2 = tot.y;
-  if (b == 0 && threadIdx.x == 0) {
+  if (grp == 0 && threadIdx.x == 0) {
     if (dweight) dweight[c] = s2;
     if (dbias) dbias[c] = s1;
   }
   if (!dx) return;
   const float2 st = saved[c];
-  const float w = weight[c], bb = bias[c], inv_n = 1.f / ((float)B * HW);
+  const float w = weight[c], bb = bias[c], inv_n = 1.f / ((float)g.B * g.HW);
   const float m1 = s1 * inv_n, m2 = s2 * inv_n, k = w * st.y;
-  const T* px = x + (size_t)b * xbs + (size_t)c * HW;
-  const T* pg = dy + ((size_t)b * C + c) * HW;
-  T* pd = dx + ((size_t)b * C + c) * HW;
-  const bool vec = (HW & 3) == 0 && ((reinterpret_cast<uintptr_t>(px) | reinterpret_cast<uintptr_t>(pg) | reinterpret_cast<uintptr_t>(pd)) & 15) == 0;
-  if (vec) {
-    for (int i = threadIdx.x * 4; i < HW; i += 1024) {
-      const float4 xv = ld4(px + i), gv = ld4(pg + i);
+  const T* px = x + (size_t)b0 * g.xbs + (size_t)c * g.HW;
+  const size_t ybs = (size_t)C * g.HW;
+  const T* pg = dy + ((size_t)b0 * C + c) * g.HW;
+  T* pd = dx + ((size_t)b0 * C + c) * g.HW;
+  if (g.unit == 4) {
+    for_each(g, np, [&](int p, int o) {
+      const float4 xv = ld4(px + (size_t)p * g.xbs + o), gv = ld4(pg + p * ybs + o);
       const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
-      float o[4];
+      float ov[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const float xh = (xs[u] - st.x) * st.y;
-        const float g = fmaf(w, xh, bb) > 0.f ? gs[u] : 0.f;
-        o[u] = k * (g - m1 - xh * m2);
+        const float gg = fmaf(w, xh, bb) > 0.f ? gs[u] : 0.f;
+        ov[u] = k * (gg - m1 - xh * m2);
       }
-      st4(pd + i, make_float4(o[0], o[1], o[2], o[3]));
-    }
+      st4(pd + p * ybs + o, make_float4(ov[0], ov[1], ov[2], ov[3]));
+    });
   } else {
-    for (int i = threadIdx.x; i < HW; i += 256) {
-      const float xh = (ld1(px + i) - st.x) * st.y;
-      const float g = fmaf(w, xh, bb) > 0.f ? ld1(pg + i) : 0.f;
-      st1(pd + i, k * (g - m1 - xh * m2));
-    }
+    for_each(g, np, [&](int p, int o) {
+      const float xh = (ld1(px + (size_t)p * g.xbs + o) - st.x) * st.y;
+      const float gg = fmaf(w, xh, bb) > 0.f ? ld1(pg + p * ybs + o) : 0.f;
+      st1(pd + p * ybs + o, k * (gg - m1 - xh * m2));
+    });
   }
+}
+
+// host: group size, thread layout and whether every plane of every tensor can be accessed four elements at a time
+template <class T>
+Geo make_geo(int B, int C, int HW, long long xbs, const void* p0, const void* p1, const void* p2) {
+  Geo g;
+  g.B = B; g.HW = HW; g.xbs = xbs;
+  g.bpb = std::max(1, std::min(B, 8192 / std::max(HW, 1)));
+  g.G = (B + g.bpb - 1) / g.bpb;
+  const size_t al = sizeof(T) * 4;                        // bytes of one four-element access (16 for fp32, 8 for bf16)
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1) | reinterpret_cast<uintptr_t>(p2) |
+                         (uintptr_t)((size_t)xbs * sizeof(T));
+  (void)C;
+  const bool vec = (HW & 3) == 0 && (bits & (al - 1)) == 0;
+  g.unit = vec ? 4 : 1;
+  g.n_unit = HW / g.unit;
+  g.txl = 0;
+  while ((1 << g.txl) < g.n_unit && g.txl < 8) ++g.txl;
+  return g;
 }
 
 template <class T>
 int fwd_t(const T* x, long long xbs, int B, int C, int HW, const float* w, const float* b, float* rm, float* rv, float momentum, float eps,
           T* y, float* saved, float* ws, int c_from, cudaStream_t st) {
-  dim3 grid(C, B);
-  if (c_from < C) {                                       // plane statistics of channels [c_from, C); the rest is already in `ws`
-    bn_stats_kernel<T><<<dim3(C - c_from, B), 256, 0, AACONV_ST(st)>>>(x, xbs, HW, reinterpret_cast<float2*>(ws), c_from);
+  const Geo g = make_geo<T>(B, C, HW, xbs, x, y, nullptr);
+  if (c_from < C) {                                       // group statistics of channels [c_from, C); the rest is already in `ws`
+    bn_stats_kernel<T><<<dim3(C - c_from, g.G), 256, 0, AACONV_ST(st)>>>(x, g, reinterpret_cast<float2*>(ws), c_from);
     AACONV_LAUNCH_OK("bn_stats");
   }
-  bn_apply_kernel<T><<<grid, 256, 0, AACONV_ST(st)>>>(x, xbs, HW, reinterpret_cast<const float2*>(ws), w, b, rm, rv, momentum, eps, y,
-                                                      reinterpret_cast<float2*>(saved));
+  bn_apply_kernel<T><<<dim3(C, g.G), 256, 0, AACONV_ST(st)>>>(x, g, reinterpret_cast<const float2*>(ws), w, b, rm, rv, momentum, eps, y,
+                                                             reinterpret_cast<float2*>(saved));
   AACONV_LAUNCH_OK("bn_relu_apply");
   return 0;
 }
 template <class T>
 int bwd_t(const T* x, long long xbs, int B, int C, int HW, const T* dy, const float* saved, const float* w, const float* b, T* dx, float* dw,
           float* db, float* ws, cudaStream_t st) {
-  dim3 grid(C, B);
-  bn_bwd_reduce_kernel<T><<<grid, 256, 0, AACONV_ST(st)>>>(x, xbs, HW, dy, reinterpret_cast<const float2*>(saved), w, b,
+  const Geo g = make_geo<T>(B, C, HW, xbs, x, dy, dx);
+  dim3 grid(C, g.G);
+  bn_bwd_reduce_kernel<T><<<grid, 256, 0, AACONV_ST(st)>>>(x, g, dy, reinterpret_cast<const float2*>(saved), w, b,
                                                            reinterpret_cast<float2*>(ws));
   AACONV_LAUNCH_OK("bn_relu_bwd_reduce");
-  bn_bwd_dx_kernel<T><<<grid, 256, 0, AACONV_ST(st)>>>(x, xbs, HW, dy, reinterpret_cast<const float2*>(saved), w, b,
+  bn_bwd_dx_kernel<T><<<grid, 256, 0, AACONV_ST(st)>>>(x, g, dy, reinterpret_cast<const float2*>(saved), w, b,
                                                        reinterpret_cast<const float2*>(ws), dx, dw, db);
   AACONV_LAUNCH_OK("bn_relu_bwd_dx");
   return 0;
