@@ -62,6 +62,8 @@ SYMBOLS = {
                                               ctypes.c_float, ctypes.c_float, _P, _P, _P, ctypes.c_int, _P]),
     'aaconv_bn_relu_backward': (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, _P, _P, _P, _P,
                                                _P, _P, _P, _P, _P]),
+    'aaconv_bn_relu_backward_acc': (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, _P, _P, _P, _P,
+                                                   _P, ctypes.c_int64, _P, _P, _P, _P]),
     'aaconv_launch_count': (ctypes.c_longlong, []),
     'aaconv_debug_set_timeline': (None, [_P]),
     'aaconv_debug_set_mode': (None, [ctypes.c_int]),

@@ -40,6 +40,16 @@ __device__ __forceinline__ float4 ld4(const bf16* p) {
   const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
   return make_float4(a.x, a.y, b.x, b.y);
 }
+// plain (coherent) loads of data this kernel also writes
+__device__ __forceinline__ float ld1_rw(const float* p) { return *p; }
+__device__ __forceinline__ float ld1_rw(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float4 ld4_rw(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4_rw(const bf16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void st4(bf16* p, float4 v) {
   const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
@@ -221,11 +231,15 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
   if (threadIdx.x == 0) partial[(size_t)c * g.G + grp] = t;
 }
 
-template <class T>
+// ACC: dx is ADDED onto a gradient that is already there, read and written through its own batch stride `dbs` -- the gradient of
+// the dense block's feature buffer, of which this layer's input is a channel prefix (replaces a dense dx + autograd's add: two
+// passes over the slice instead of five)
+template <class T, bool ACC>
 __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const T* __restrict__ x, const Geo g, const T* __restrict__ dy,
                                                         const float2* __restrict__ saved, const float* __restrict__ weight,
                                                         const float* __restrict__ bias, const float2* __restrict__ partial,
-                                                        T* __restrict__ dx, float* __restrict__ dweight, float* __restrict__ dbias) {
+                                                        T* __restrict__ dx, long long dbs, float* __restrict__ dweight,
+                                                        float* __restrict__ dbias) {
   __shared__ float2 shm[257];
   const int c = blockIdx.x, grp = blockIdx.y, C = gridDim.x, np = planes_of(g, grp), b0 = grp * g.bpb;
   const float2 tot = merge_sums(partial, c, g.G, shm);                   // group order
@@ -241,7 +255,7 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const T* __restrict__ x,
   const T* px = x + (size_t)b0 * g.xbs + (size_t)c * g.HW;
   const size_t ybs = (size_t)C * g.HW;
   const T* pg = dy + ((size_t)b0 * C + c) * g.HW;
-  T* pd = dx + ((size_t)b0 * C + c) * g.HW;
+  T* pd = dx + (size_t)b0 * dbs + (size_t)c * g.HW;
   if (g.unit == 4) {
     for_each(g, np, [&](int p, int o) {
       const float4 xv = ld4(px + (size_t)p * g.xbs + o), gv = ld4(pg + p * ybs + o);
@@ -253,13 +267,16 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const T* __restrict__ x,
         const float gg = fmaf(w, xh, bb) > 0.f ? gs[u] : 0.f;
         ov[u] = k * (gg - m1 - xh * m2);
       }
-      st4(pd + p * ybs + o, make_float4(ov[0], ov[1], ov[2], ov[3]));
+      T* q = pd + (size_t)p * dbs + o;
+      if (ACC) { const float4 a = ld4_rw(q); ov[0] += a.x; ov[1] += a.y; ov[2] += a.z; ov[3] += a.w; }
+      st4(q, make_float4(ov[0], ov[1], ov[2], ov[3]));
     });
   } else {
     for_each(g, np, [&](int p, int o) {
       const float xh = (ld1(px + (size_t)p * g.xbs + o) - st.x) * st.y;
       const float gg = fmaf(w, xh, bb) > 0.f ? ld1(pg + p * ybs + o) : 0.f;
-      st1(pd + p * ybs + o, k * (gg - m1 - xh * m2));
+      T* q = pd + (size_t)p * dbs + o;
+      st1(q, k * (gg - m1 - xh * m2) + (ACC ? ld1_rw(q) : 0.f));
     });
   }
 }
@@ -297,15 +314,20 @@ int fwd_t(const T* x, long long xbs, int B, int C, int HW, const float* w, const
   return 0;
 }
 template <class T>
-int bwd_t(const T* x, long long xbs, int B, int C, int HW, const T* dy, const float* saved, const float* w, const float* b, T* dx, float* dw,
-          float* db, float* ws, cudaStream_t st) {
-  const Geo g = make_geo<T>(B, C, HW, xbs, x, dy, dx);
+int bwd_t(const T* x, long long xbs, int B, int C, int HW, const T* dy, const float* saved, const float* w, const float* b, T* dx,
+          long long dbs, int acc, float* dw, float* db, float* ws, cudaStream_t st) {
+  Geo g = make_geo<T>(B, C, HW, xbs, x, dy, dx);
+  if (g.unit == 4 && ((size_t)dbs * sizeof(T)) % (sizeof(T) * 4) != 0) { g.unit = 1; g.n_unit = HW; g.txl = 8; }
   dim3 grid(C, g.G);
   bn_bwd_reduce_kernel<T><<<grid, 256, 0, AACONV_ST(st)>>>(x, g, dy, reinterpret_cast<const float2*>(saved), w, b,
                                                            reinterpret_cast<float2*>(ws));
   AACONV_LAUNCH_OK("bn_relu_bwd_reduce");
-  bn_bwd_dx_kernel<T><<<grid, 256, 0, AACONV_ST(st)>>>(x, g, dy, reinterpret_cast<const float2*>(saved), w, b,
-                                                       reinterpret_cast<const float2*>(ws), dx, dw, db);
+  if (acc)
+    bn_bwd_dx_kernel<T, true><<<grid, 256, 0, AACONV_ST(st)>>>(x, g, dy, reinterpret_cast<const float2*>(saved), w, b,
+                                                               reinterpret_cast<const float2*>(ws), dx, dbs, dw, db);
+  else
+    bn_bwd_dx_kernel<T, false><<<grid, 256, 0, AACONV_ST(st)>>>(x, g, dy, reinterpret_cast<const float2*>(saved), w, b,
+                                                                reinterpret_cast<const float2*>(ws), dx, dbs, dw, db);
   AACONV_LAUNCH_OK("bn_relu_bwd_dx");
   return 0;
 }
@@ -344,9 +366,24 @@ int aaconv_bn_relu_backward(const void* x, int dtype, int B, int C, int HW, int6
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* ws = static_cast<float*>(workspace);
   return dtype == AACONV_BF16 ? bwd_t(static_cast<const bf16*>(x), x_batch_stride, B, C, HW, static_cast<const bf16*>(dy), saved, weight, bias,
-                                      static_cast<bf16*>(dx), dweight, dbias, ws, st)
+                                      static_cast<bf16*>(dx), (long long)C * HW, 0, dweight, dbias, ws, st)
                               : bwd_t(static_cast<const float*>(x), x_batch_stride, B, C, HW, static_cast<const float*>(dy), saved, weight,
-                                      bias, static_cast<float*>(dx), dweight, dbias, ws, st);
+                                      bias, static_cast<float*>(dx), (long long)C * HW, 0, dweight, dbias, ws, st);
+}
+
+int aaconv_bn_relu_backward_acc(const void* x, int dtype, int B, int C, int HW, int64_t x_batch_stride, const void* dy, const float* saved,
+                                const float* weight, const float* bias, void* gacc, int64_t g_batch_stride, float* dweight, float* dbias,
+                                void* workspace, void* stream) {
+  if (!x || !dy || !saved || !weight || !bias || !workspace || !gacc || B <= 0 || C <= 0 || HW <= 0 || B > 65535)
+    return fail(AACONV_E_ARG, "bad bn_relu_backward_acc arguments");
+  if ((dtype != AACONV_FP32 && dtype != AACONV_BF16) || x_batch_stride < (int64_t)C * HW || g_batch_stride < (int64_t)C * HW)
+    return fail(AACONV_E_ARG, "bad bn_relu dtype / stride");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* ws = static_cast<float*>(workspace);
+  return dtype == AACONV_BF16 ? bwd_t(static_cast<const bf16*>(x), x_batch_stride, B, C, HW, static_cast<const bf16*>(dy), saved, weight, bias,
+                                      static_cast<bf16*>(gacc), g_batch_stride, 1, dweight, dbias, ws, st)
+                              : bwd_t(static_cast<const float*>(x), x_batch_stride, B, C, HW, static_cast<const float*>(dy), saved, weight,
+                                      bias, static_cast<float*>(gacc), g_batch_stride, 1, dweight, dbias, ws, st);
 }
 
 }  // extern "C"

@@ -19,7 +19,7 @@ import torch.nn.functional as F
 from torchvision.models.densenet import _DenseBlock, _DenseLayer
 
 from .aaconv import AAConv2d
-from .fused_bn import bn_relu
+from .fused_bn import bn_relu, tap_bn_relu
 
 
 def transition_attn_dims(num_output_features, attn_params):
@@ -142,7 +142,9 @@ class BufferedDenseBlock(nn.ModuleDict):
         for layer in self.values():
             # norm -> relu pairs: fused strided kernels in training on CUDA (chexpert_b200.fused_bn), the torch modules otherwise
             c = feats.shape[1]
-            new = layer.conv2(bn_relu(layer.norm2, layer.conv1(bn_relu(layer.norm1, feats, None if stats is None else (stats, valid)))))
+            # norm1 taps the concatenated features: backward adds its dx into the gradient of the concatenation in place
+            feats, y1 = tap_bn_relu(layer.norm1, feats, None if stats is None else (stats, valid))
+            new = layer.conv2(bn_relu(layer.norm2, layer.conv1(y1)))
             valid = c
             if layer.drop_rate > 0:
                 new = F.dropout(new, p=layer.drop_rate, training=self.training)

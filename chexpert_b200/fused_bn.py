@@ -59,6 +59,64 @@ class _BNReLU(torch.autograd.Function):
         return dx, dw, db, None, None, None, None, None
 
 
+def _fresh_alias(t):
+    """A tensor over the same memory with its own autograd identity and version counter (later writes into other channels of the
+    same feature buffer must not invalidate what this op saved)."""
+    return torch.empty(0, dtype=t.dtype, device=t.device).set_(t.untyped_storage(), t.storage_offset(), t.shape, t.stride())
+
+
+class _TapBNReLU(torch.autograd.Function):
+    """(feats, relu(bn(feats))) for the concatenated features of a dense block: the first output IS the input (handed on to the
+    next layer's concatenation), so that backward sees both consumers' gradients at once and ADDS this layer's dx into the
+    gradient of the concatenation in place (aaconv_bn_relu_backward_acc) -- instead of a dense dx and autograd's own add."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, stats=None):
+        y = _BNReLU.forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, stats)
+        return _fresh_alias(x.detach()), y
+
+    @staticmethod
+    def backward(ctx, g_feats, dy):
+        if dy is None:
+            return g_feats, None, None, None, None, None, None, None
+        xs, saved, w, b = ctx.saved_tensors
+        B, C, H, W = xs.shape
+        ok = (g_feats is not None and ctx.needs_input_grad[0] and g_feats.dtype == xs.dtype and tuple(g_feats.shape) == (B, C, H, W)
+              and g_feats.stride(3) == 1 and g_feats.stride(2) == W and g_feats.stride(1) == H * W and g_feats.stride(0) >= C * H * W)
+        if not ok:
+            dx, dw, db = _BNReLU.backward(ctx, dy)[:3]
+            if g_feats is not None and dx is not None:
+                dx = dx + g_feats
+            elif dx is None:
+                dx = g_feats
+            return dx, dw, db, None, None, None, None, None
+        lib = _lib.load()
+        g = dy.detach().to(xs.dtype).contiguous()
+        need = ctx.needs_input_grad
+        with torch.cuda.device(xs.device):
+            dw = torch.empty(C, device=xs.device, dtype=torch.float32) if need[1] else None
+            db = torch.empty(C, device=xs.device, dtype=torch.float32) if need[2] else None
+            ws = torch.empty(lib.aaconv_bn_relu_workspace_bytes(B, C), device=xs.device, dtype=torch.uint8)
+            _lib.check(lib.aaconv_bn_relu_backward_acc(_ptr(xs), _DT[xs.dtype], B, C, H * W, xs.stride(0), _ptr(g), _ptr(saved), _ptr(w),
+                                                       _ptr(b), _ptr(g_feats), g_feats.stride(0), _ptr(dw), _ptr(db), _ptr(ws),
+                                                       _stream()), 'aaconv_bn_relu_backward_acc')
+        return g_feats, dw, db, None, None, None, None, None
+
+
+def _fused_ok(bn, x):
+    return (bn.training and x.is_cuda and x.dim() == 4 and x.dtype in _DT and bn.affine and bn.track_running_stats
+            and bn.momentum is not None and _strided_ok(x) and x.shape[0] <= 65535)
+
+
+def tap_bn_relu(bn, x, stats=None):
+    """-> (x handed on, relu(bn(x))): bn_relu for an input that has a second consumer (the concatenation of a dense block)."""
+    if not (_fused_ok(bn, x) and torch.is_grad_enabled() and x.requires_grad):
+        return x, bn_relu(bn, x, stats)
+    if bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return _TapBNReLU.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, stats)
+
+
 def bn_relu(bn, x, stats=None):
     """relu(bn(x)) for an nn.BatchNorm2d `bn`; the fused strided kernels when it is training on CUDA, the modules otherwise.
     ``stats = (float32 buffer of >= 2*B*C elements, n_valid_channels)`` shares the per-plane statistics between the layers of a

@@ -160,6 +160,12 @@ int aaconv_bn_relu_forward(const void* x, int dtype, int B, int C, int HW, int64
                            int stats_valid_channels, void* stream);
 int aaconv_bn_relu_backward(const void* x, int dtype, int B, int C, int HW, int64_t x_batch_stride, const void* dy, const float* saved,
                             const float* weight, const float* bias, void* dx, float* dweight, float* dbias, void* workspace, void* stream);
+/* The same with dx ACCUMULATED onto a gradient that is already in memory: gacc (B, C, HW) elements of `dtype` with g_batch_stride >= C*HW
+ * elements between samples -- the gradient of the dense block's feature buffer, of which this layer's input is a channel prefix
+ * (replaces the dense dx + the add autograd would run for the two consumers of the concatenated features, tv densenet.py:48,120-124). */
+int aaconv_bn_relu_backward_acc(const void* x, int dtype, int B, int C, int HW, int64_t x_batch_stride, const void* dy, const float* saved,
+                                const float* weight, const float* bias, void* gacc, int64_t g_batch_stride, float* dweight, float* dbias,
+                                void* workspace, void* stream);
 
 /* Accounting / measurement helpers used by bench.py (no reference counterpart).
  *   aaconv_launch_count   kernels launched by this library since it was loaded (all threads).
