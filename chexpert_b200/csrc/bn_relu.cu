@@ -166,10 +166,35 @@ template <class T>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, const Geo g, const float2* __restrict__ partial,
                                                        const float* __restrict__ weight, const float* __restrict__ bias,
                                                        float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
-                                                       float eps, T* __restrict__ y, float2* __restrict__ saved) {
+                                                       float eps, T* __restrict__ y, float2* __restrict__ saved, int c_from,
+                                                       float2* __restrict__ partial_out) {
   __shared__ float2 shm[257];
   const int c = blockIdx.x, grp = blockIdx.y, C = gridDim.x, np = planes_of(g, grp), b0 = grp * g.bpb;
-  const float2 st = merge_stats(partial, c, g, shm);
+  float2 st;
+  if (g.G == 1 && c >= c_from) {
+    // one CTA owns the whole channel: its statistics are computed here (two more passes over data that stays in L1 / L2) and the
+    // bn_stats launch is skipped; the partial is still written for the next layers of the dense block
+    const T* px0 = x + (size_t)c * g.HW;
+    float s = 0.f;
+    if (g.unit == 4) for_each(g, np, [&](int p, int o) { const float4 v = ld4(px0 + (size_t)p * g.xbs + o); s += (v.x + v.y) + (v.z + v.w); });
+    else for_each(g, np, [&](int p, int o) { s += ld1(px0 + (size_t)p * g.xbs + o); });
+    const float mean = block_sum2(s, 0.f, shm).x / ((float)np * g.HW);
+    float q = 0.f;
+    if (g.unit == 4) {
+      for_each(g, np, [&](int p, int o) {
+        const float4 v = ld4(px0 + (size_t)p * g.xbs + o);
+        const float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+        q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+      });
+    } else {
+      for_each(g, np, [&](int p, int o) { const float a0 = ld1(px0 + (size_t)p * g.xbs + o) - mean; q += a0 * a0; });
+    }
+    const float m2 = block_sum2(q, 0.f, shm).x;
+    if (threadIdx.x == 0) partial_out[c] = make_float2(mean, m2);
+    st = make_float2(mean, m2 / ((float)np * g.HW));
+  } else {
+    st = merge_stats(partial, c, g, shm);
+  }
   const float rstd = rsqrtf(st.y + eps);
   if (grp == 0 && threadIdx.x == 0) {
     saved[c] = make_float2(st.x, rstd);
@@ -242,7 +267,38 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const T* __restrict__ x,
                                                         float* __restrict__ dbias) {
   __shared__ float2 shm[257];
   const int c = blockIdx.x, grp = blockIdx.y, C = gridDim.x, np = planes_of(g, grp), b0 = grp * g.bpb;
-  const float2 tot = merge_sums(partial, c, g.G, shm);                   // group order
+  float2 tot;
+  if (g.G == 1) {     // one CTA owns the whole channel: the reduction pass runs here and the bn_bwd_reduce launch is skipped
+    const float2 st0 = saved[c];
+    const float w0 = weight[c], bb0 = bias[c];
+    const T* px0 = x + (size_t)c * g.HW;
+    const T* pg0 = dy + (size_t)c * g.HW;
+    const size_t ybs0 = (size_t)C * g.HW;
+    float a1 = 0.f, a2 = 0.f;
+    if (g.unit == 4) {
+      for_each(g, np, [&](int p, int o) {
+        const float4 xv = ld4(px0 + (size_t)p * g.xbs + o), gv = ld4(pg0 + p * ybs0 + o);
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float xh = (xs[u] - st0.x) * st0.y;
+          const float gg = fmaf(w0, xh, bb0) > 0.f ? gs[u] : 0.f;
+          a1 += gg;
+          a2 = fmaf(gg, xh, a2);
+        }
+      });
+    } else {
+      for_each(g, np, [&](int p, int o) {
+        const float xh = (ld1(px0 + (size_t)p * g.xbs + o) - st0.x) * st0.y;
+        const float gg = fmaf(w0, xh, bb0) > 0.f ? ld1(pg0 + p * ybs0 + o) : 0.f;
+        a1 += gg;
+        a2 = fmaf(gg, xh, a2);
+      });
+    }
+    tot = block_sum2(a1, a2, reinterpret_cast<float2*>(shm));
+  } else {
+    tot = merge_sums(partial, c, g.G, shm);                              // group order
+  }
   const float s1 = tot.x, s2 = tot.y;
   if (grp == 0 && threadIdx.x == 0) {
     if (dweight) dweight[c] = s2;
@@ -304,12 +360,12 @@ template <class T>
 int fwd_t(const T* x, long long xbs, int B, int C, int HW, const float* w, const float* b, float* rm, float* rv, float momentum, float eps,
           T* y, float* saved, float* ws, int c_from, cudaStream_t st) {
   const Geo g = make_geo<T>(B, C, HW, xbs, x, y, nullptr);
-  if (c_from < C) {                                       // group statistics of channels [c_from, C); the rest is already in `ws`
+  if (c_from < C && g.G > 1) {                            // group statistics of channels [c_from, C); the rest is already in `ws`
     bn_stats_kernel<T><<<dim3(C - c_from, g.G), 256, 0, AACONV_ST(st)>>>(x, g, reinterpret_cast<float2*>(ws), c_from);
     AACONV_LAUNCH_OK("bn_stats");
-  }
+  }                                                       // (G == 1: the apply kernel reduces the new channels itself)
   bn_apply_kernel<T><<<dim3(C, g.G), 256, 0, AACONV_ST(st)>>>(x, g, reinterpret_cast<const float2*>(ws), w, b, rm, rv, momentum, eps, y,
-                                                             reinterpret_cast<float2*>(saved));
+                                                             reinterpret_cast<float2*>(saved), c_from, reinterpret_cast<float2*>(ws));
   AACONV_LAUNCH_OK("bn_relu_apply");
   return 0;
 }
@@ -319,9 +375,11 @@ int bwd_t(const T* x, long long xbs, int B, int C, int HW, const T* dy, const fl
   Geo g = make_geo<T>(B, C, HW, xbs, x, dy, dx);
   if (g.unit == 4 && ((size_t)dbs * sizeof(T)) % (sizeof(T) * 4) != 0) { g.unit = 1; g.n_unit = HW; g.txl = 8; }
   dim3 grid(C, g.G);
-  bn_bwd_reduce_kernel<T><<<grid, 256, 0, AACONV_ST(st)>>>(x, g, dy, reinterpret_cast<const float2*>(saved), w, b,
-                                                           reinterpret_cast<float2*>(ws));
-  AACONV_LAUNCH_OK("bn_relu_bwd_reduce");
+  if (g.G > 1) {
+    bn_bwd_reduce_kernel<T><<<grid, 256, 0, AACONV_ST(st)>>>(x, g, dy, reinterpret_cast<const float2*>(saved), w, b,
+                                                             reinterpret_cast<float2*>(ws));
+    AACONV_LAUNCH_OK("bn_relu_bwd_reduce");
+  }
   if (acc)
     bn_bwd_dx_kernel<T, true><<<grid, 256, 0, AACONV_ST(st)>>>(x, g, dy, reinterpret_cast<const float2*>(saved), w, b,
                                                                reinterpret_cast<const float2*>(ws), dx, dbs, dw, db);

@@ -112,7 +112,7 @@ def tap_bn_relu(bn, x, stats=None):
     """-> (x handed on, relu(bn(x))): bn_relu for an input that has a second consumer (the concatenation of a dense block)."""
     if not (_fused_ok(bn, x) and torch.is_grad_enabled() and x.requires_grad):
         return x, bn_relu(bn, x, stats)
-    if bn.num_batches_tracked is not None:
+    if bn.num_batches_tracked is not None and not getattr(bn, '_nbt_batched', False):
         bn.num_batches_tracked.add_(1)
     return _TapBNReLU.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, stats)
 
@@ -125,6 +125,6 @@ def bn_relu(bn, x, stats=None):
              and bn.momentum is not None and _strided_ok(x) and x.shape[0] <= 65535)
     if not fused:
         return F.relu(bn(x), inplace=True)
-    if bn.num_batches_tracked is not None:
+    if bn.num_batches_tracked is not None and not getattr(bn, '_nbt_batched', False):   # TrainStep bumps all counters in one launch
         bn.num_batches_tracked.add_(1)
     return _BNReLU.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, stats)

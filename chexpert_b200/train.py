@@ -67,6 +67,13 @@ class TrainStep:
         # gradient back to fp32 in backward -- ~360 three-microsecond kernels per step (9 % of the captured step).  Same
         # arithmetic, two launches: all conv weights are cast at once into bf16 shadows (torch._foreach_copy_), the model runs
         # on the shadows (torch.func.functional_call), and the shadows' gradients are cast back at once.
+        # the fused BN+ReLU path bumps num_batches_tracked itself (118 one-element kernels per step): one foreach launch instead
+        self._nbt = []
+        if buffered and self.device.type == 'cuda':
+            for m in self.model.modules():
+                if isinstance(m, torch.nn.BatchNorm2d) and m.num_batches_tracked is not None:
+                    m._nbt_batched = True
+                    self._nbt.append(m.num_batches_tracked)
         self._sh = None
         if batched_casts and self.autocast:
             self._setup_shadows()
@@ -95,6 +102,8 @@ class TrainStep:
             self.buckets.reset()
         else:
             self.opt.zero_grad(set_to_none=True)
+        if self._nbt:
+            torch._foreach_add_(self._nbt, 1)
         with torch.autocast('cuda', dtype=torch.bfloat16, enabled=self.autocast):
             if self._sh is not None:
                 with torch.no_grad():
