@@ -18,6 +18,7 @@
 //                        the b = 0 block writes dweight = sum g x^ and dbias = sum g
 // 3 / 5 passes, all reductions in a fixed order (bit-reproducible), x read through its strides, y / dx dense.
 #include <algorithm>
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -342,7 +343,8 @@ template <class T>
 Geo make_geo(int B, int C, int HW, long long xbs, const void* p0, const void* p1, const void* p2) {
   Geo g;
   g.B = B; g.HW = HW; g.xbs = xbs;
-  g.bpb = std::max(1, std::min(B, 8192 / std::max(HW, 1)));
+  static const int target = [] { const char* e = getenv("AACONV_BN_TARGET"); return e ? atoi(e) : 8192; }();   // elements per CTA (A/B)
+  g.bpb = std::max(1, std::min(B, target / std::max(HW, 1)));
   g.G = (B + g.bpb - 1) / g.bpb;
   const size_t al = sizeof(T) * 4;                        // bytes of one four-element access (16 for fp32, 8 for bf16)
   const uintptr_t bits = reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1) | reinterpret_cast<uintptr_t>(p2) |

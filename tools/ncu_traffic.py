@@ -17,7 +17,8 @@ LABEL = {'attn_fwd_cc_kernel': 'attn_fwd_cc', 'attn_bwd_dq_cc_kernel': 'attn_bwd
          'pack_x_v4_kernel': 'pack_nhwc_bf16', 'out_bwd_patch_kernel': 'out_bwd_patch', 'out_proj_fwd_kernel': 'out_proj_fwd',
          'rel_bwd_reduce_kernel': 'rel_bwd_reduce', 'out_w_reduce_kernel': 'out_w_reduce', 'wgrad_reduce_kernel': 'wgrad_reduce',
          'pack_wf_kernel': 'pack_wf', 'pack_wd_kernel': 'pack_wd', 'attn_fwd_tc_kernel': 'attn_fwd_tc',
-         'attn_bwd_dq_tc_kernel': 'attn_bwd_dq_tc', 'attn_bwd_dkv_tc_kernel': 'attn_bwd_dkv_tc'}
+         'attn_bwd_dq_tc_kernel': 'attn_bwd_dq_tc', 'attn_bwd_dkv_tc_kernel': 'attn_bwd_dkv_tc',
+         'aug_build_tc_kernel': 'aug_build_tc', 'rel_bwd_tc_kernel': 'rel_bwd_tc'}
 
 
 def main():
