@@ -290,10 +290,9 @@ def measure_layer(ctx, args, shape, K, W, want_e2e=True, sampler=None):
         xin.grad = None
         y = m(xin)
         y.backward(dyin)
-        if world > 1:   # data-parallel exchange step: one bucket with every parameter gradient of the module
+        if world > 1:   # data-parallel exchange step: one bucket with every parameter gradient of the module, averaged by NCCL
             flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
-            flat.div_(world)
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
         return y
 
     def timed(fn, n):
