@@ -136,9 +136,9 @@ __device__ __forceinline__ float2 merge_stats(const float2* __restrict__ partial
     if (threadIdx.x == 0) {
       for (int i = 0; i < ng; ++i) {
         const float2 p = sh[i];
-        const float nb = (float)planes_of(g, g0 + i) * g.HW, tot = n + nb, d = p.x - mean;
-        mean += d * (nb / tot);
-        m2 += p.y + d * d * (n * nb / tot);
+        const float nb = (float)planes_of(g, g0 + i) * g.HW, tot = n + nb, d = p.x - mean, bf = __fdividef(nb, tot);
+        mean += d * bf;                                  // (IEEE divisions made this serial loop ~100 cycles per step)
+        m2 += p.y + d * d * (n * bf);
         n = tot;
       }
     }
@@ -416,6 +416,31 @@ int aaconv_bn_relu_forward(const void* x, int dtype, int B, int C, int HW, int64
                      static_cast<bf16*>(y), saved, ws, stats_valid_channels, st)
              : fwd_t(static_cast<const float*>(x), x_batch_stride, B, C, HW, weight, bias, running_mean, running_var, momentum, eps,
                      static_cast<float*>(y), saved, ws, stats_valid_channels, st);
+}
+
+// group statistics only (what aaconv_bn_relu_forward keeps in `workspace`), for callers that normalise with their own kernel
+// (the channels-last path, bn_cl.cu): channels [stats_valid_channels, C) are reduced; *groups / *planes_per_group describe the layout
+int aaconv_bn_stats_nchw(const void* x, int dtype, int B, int C, int HW, int64_t x_batch_stride, void* workspace, int stats_valid_channels,
+                         int* groups, int* planes_per_group, void* stream) {
+  if (!x || !workspace || !groups || !planes_per_group || B <= 0 || C <= 0 || HW <= 0 || B > 65535 || stats_valid_channels < 0 ||
+      stats_valid_channels > C)
+    return fail(AACONV_E_ARG, "bad bn_stats_nchw arguments");
+  if ((dtype != AACONV_FP32 && dtype != AACONV_BF16) || x_batch_stride < (int64_t)C * HW) return fail(AACONV_E_ARG, "bad bn_stats dtype / stride");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Geo g = dtype == AACONV_BF16 ? make_geo<bf16>(B, C, HW, x_batch_stride, x, nullptr, nullptr)
+                               : make_geo<float>(B, C, HW, x_batch_stride, x, nullptr, nullptr);
+  *groups = g.G;
+  *planes_per_group = g.bpb;
+  if (stats_valid_channels < C) {
+    if (dtype == AACONV_BF16)
+      bn_stats_kernel<bf16><<<dim3(C - stats_valid_channels, g.G), 256, 0, AACONV_ST(st)>>>(static_cast<const bf16*>(x), g,
+                                                                                         static_cast<float2*>(workspace), stats_valid_channels);
+    else
+      bn_stats_kernel<float><<<dim3(C - stats_valid_channels, g.G), 256, 0, AACONV_ST(st)>>>(static_cast<const float*>(x), g,
+                                                                                          static_cast<float2*>(workspace), stats_valid_channels);
+    AACONV_LAUNCH_OK("bn_stats");
+  }
+  return 0;
 }
 
 int aaconv_bn_relu_backward(const void* x, int dtype, int B, int C, int HW, int64_t x_batch_stride, const void* dy, const float* saved,

@@ -13,13 +13,15 @@ chexpert.py:90-123,504-518) loads strictly into this model and vice versa.  The 
 """
 from collections import OrderedDict
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 from torchvision.models.densenet import _DenseBlock, _DenseLayer
 
 from .aaconv import AAConv2d
-from .fused_bn import bn_relu, tap_bn_relu
+from .fused_bn import bn_relu, tap_bn_relu, tap_bn_relu_cl, bn_relu_cl, cl_ok, slice_layout, _is_cl
 
 
 def transition_attn_dims(num_output_features, attn_params):
@@ -111,6 +113,36 @@ class _Append(torch.autograd.Function):
         return g[:, :ctx.c], g[:, ctx.c:], None
 
 
+def _nchw_slice_ok(t):
+    B, C, H, W = t.shape
+    return (t.stride(3) == 1 and t.stride(2) == W and t.stride(1) == H * W and t.stride(0) % 4 == 0
+            and t.data_ptr() % (4 * t.element_size()) == 0)
+
+
+class _AppendCL(torch.autograd.Function):
+    """_Append for channels-last new features: they are transposed into their channel slice of the NCHW buffer (one tiled kernel),
+    and the slice of the buffer gradient is transposed back to NHWC for conv2's backward."""
+
+    @staticmethod
+    def forward(ctx, prev, new, buf):
+        c, k = prev.shape[1], new.shape[1]
+        ctx.c = c
+        slice_layout(new.detach(), _alias(buf, c, c + k), to_nchw=True)
+        return _alias(buf, 0, c + k)
+
+    @staticmethod
+    def backward(ctx, g):
+        c = ctx.c
+        gs = g[:, c:]
+        B, k, H, W = gs.shape
+        if _nchw_slice_ok(gs) and gs.is_cuda:
+            gn = torch.empty((B, k, H, W), device=g.device, dtype=g.dtype, memory_format=torch.channels_last)
+            slice_layout(gs, gn, to_nchw=False)
+        else:
+            gn = gs.contiguous(memory_format=torch.channels_last)
+        return g[:, :c], gn, None
+
+
 class BufferedDenseBlock(nn.ModuleDict):
     """torchvision's ``_DenseBlock`` (same ``denselayer%d`` children, parameters and arithmetic; the reference uses it at
     models/attn_aug_conv.py:479-482) over ONE pre-allocated (B, C_in + n * growth, H, W) feature buffer: layer i reads channels
@@ -127,6 +159,7 @@ class BufferedDenseBlock(nn.ModuleDict):
                                         drop_rate=drop_rate))
         self.num_input_features, self.growth_rate, self.num_layers = num_input_features, growth_rate, num_layers
         self.out_channels = num_input_features + num_layers * growth_rate
+        self.inner_channels_last = os.environ.get('AACONV_INNER_CL', '1') != '0'   # AACONV_INNER_CL=0: NCHW inside the layers (A/B, profiles/r02_b_scaling.md)
 
     def forward(self, init_features):
         B, C0, H, W = init_features.shape
@@ -139,9 +172,25 @@ class BufferedDenseBlock(nn.ModuleDict):
         # layer i-1 has not seen (its own 32 new ones); the first layer reduces the block's input channels
         stats = torch.empty(2 * B * self.out_channels, device=buf.device, dtype=torch.float32) if buf.is_cuda else None
         valid = 0
+        growth_ok = self.growth_rate % 4 == 0 and (H * W) % 4 == 0 and stats is not None
         for layer in self.values():
             # norm -> relu pairs: fused strided kernels in training on CUDA (chexpert_b200.fused_bn), the torch modules otherwise
             c = feats.shape[1]
+            if (self.inner_channels_last and layer.drop_rate == 0 and torch.is_grad_enabled() and feats.requires_grad
+                    and cl_ok(layer.norm1, feats) and _nchw_slice_ok(feats) and growth_ok):
+                # The two convolutions of the layer run channels-last (cuDNN's tensor-core kernels are NHWC; with NCHW tensors it
+                # transposes every operand of every fprop / dgrad / wgrad itself: 21 % of the step in the round-2 profile).  The
+                # layout change rides on the BatchNorm + ReLU passes (csrc/bn_cl.cu); the buffer itself stays NCHW.
+                feats, y1 = tap_bn_relu_cl(layer.norm1, feats, (stats, valid))
+                z = layer.conv1(y1)
+                if _is_cl(z) and cl_ok(layer.norm2, z):
+                    new = layer.conv2(bn_relu_cl(layer.norm2, z))
+                else:
+                    new = layer.conv2(bn_relu(layer.norm2, z.contiguous()))
+                valid = c
+                new = new.to(buf.dtype)
+                feats = (_AppendCL.apply(feats, new, buf) if _is_cl(new) else _Append.apply(feats, new.contiguous(), buf))
+                continue
             # norm1 taps the concatenated features: backward adds its dx into the gradient of the concatenation in place
             feats, y1 = tap_bn_relu(layer.norm1, feats, None if stats is None else (stats, valid))
             new = layer.conv2(bn_relu(layer.norm2, layer.conv1(y1)))

@@ -128,3 +128,135 @@ def bn_relu(bn, x, stats=None):
     if bn.num_batches_tracked is not None and not getattr(bn, '_nbt_batched', False):   # TrainStep bumps all counters in one launch
         bn.num_batches_tracked.add_(1)
     return _BNReLU.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, stats)
+
+
+# ------------------------------------------------------------------------------------------------
+# channels-last side of a dense layer (csrc/bn_cl.cu): the convolutions see NHWC tensors, the feature buffer stays NCHW
+# ------------------------------------------------------------------------------------------------
+_CL = torch.channels_last
+
+
+def _is_cl(t):
+    return t.dim() == 4 and t.is_contiguous(memory_format=_CL)
+
+
+def cl_ok(bn, x):
+    """The channels-last kernels cover training-mode BatchNorm2d on CUDA with C and H*W multiples of 4."""
+    B, C, H, W = x.shape
+    return (bn.training and x.is_cuda and x.dtype in _DT and bn.affine and bn.track_running_stats and bn.momentum is not None
+            and C % 4 == 0 and (H * W) % 4 == 0 and B <= 65535)
+
+
+def _bump(bn):
+    if bn.num_batches_tracked is not None and not getattr(bn, '_nbt_batched', False):
+        bn.num_batches_tracked.add_(1)
+
+
+class _TapBNReLUCL(torch.autograd.Function):
+    """_TapBNReLU with an NHWC output: x = channel prefix of the NCHW feature buffer -> (x handed on, relu(bn(x)) channels-last);
+    backward takes the NHWC gradient and adds dx into the NCHW gradient of the concatenation in place."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, stats):
+        lib = _lib.load()
+        B, C, H, W = x.shape
+        xs = x.detach()
+        w, b = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        with torch.cuda.device(x.device):
+            y = torch.empty((B, C, H, W), device=x.device, dtype=x.dtype, memory_format=_CL)
+            saved = torch.empty(C, 2, device=x.device, dtype=torch.float32)
+            if stats is not None and stats[0].numel() * 4 >= 8 * B * C:
+                pst, valid = stats[0], min(int(stats[1]), C)
+            else:
+                pst, valid = torch.empty(lib.aaconv_bn_relu_workspace_bytes(B, C) // 4, device=x.device, dtype=torch.float32), 0
+            ws = torch.empty(lib.aaconv_bn_relu_cl_workspace_bytes(B, C, H * W), device=x.device, dtype=torch.uint8)
+            G, bpb = ctypes.c_int(0), ctypes.c_int(0)
+            _lib.check(lib.aaconv_bn_stats_nchw(_ptr(xs), _DT[x.dtype], B, C, H * W, xs.stride(0), _ptr(pst), valid, ctypes.byref(G),
+                                                ctypes.byref(bpb), _stream()), 'aaconv_bn_stats_nchw')
+            _lib.check(lib.aaconv_bn_relu_cl_forward(_ptr(xs), _DT[x.dtype], B, C, H * W, 0, xs.stride(0), _ptr(w), _ptr(b),
+                                                     _ptr(running_mean), _ptr(running_var), float(momentum), float(eps), _ptr(y), _ptr(saved),
+                                                     _ptr(ws), _ptr(pst), G.value, bpb.value, _stream()), 'aaconv_bn_relu_cl_forward')
+        ctx.save_for_backward(xs, saved, w, b)
+        return _fresh_alias(xs), y
+
+    @staticmethod
+    def backward(ctx, g_feats, dy):
+        xs, saved, w, b = ctx.saved_tensors
+        if dy is None:
+            return g_feats, None, None, None, None, None, None, None
+        lib = _lib.load()
+        B, C, H, W = xs.shape
+        g = dy.detach().to(xs.dtype).contiguous(memory_format=_CL)
+        need = ctx.needs_input_grad
+        acc = (g_feats is not None and g_feats.dtype == xs.dtype and tuple(g_feats.shape) == (B, C, H, W) and g_feats.stride(3) == 1
+               and g_feats.stride(2) == W and g_feats.stride(1) == H * W and g_feats.stride(0) >= C * H * W
+               and g_feats.stride(0) % 4 == 0 and g_feats.data_ptr() % (4 * g_feats.element_size()) == 0)
+        with torch.cuda.device(xs.device):
+            dx = g_feats if acc else torch.empty(B, C, H, W, device=xs.device, dtype=xs.dtype)
+            dw = torch.empty(C, device=xs.device, dtype=torch.float32) if need[1] else None
+            db = torch.empty(C, device=xs.device, dtype=torch.float32) if need[2] else None
+            ws = torch.empty(lib.aaconv_bn_relu_cl_workspace_bytes(B, C, H * W), device=xs.device, dtype=torch.uint8)
+            _lib.check(lib.aaconv_bn_relu_cl_backward(_ptr(xs), _DT[xs.dtype], B, C, H * W, 0, xs.stride(0), _ptr(g), _ptr(saved), _ptr(w),
+                                                      _ptr(b), _ptr(dx), dx.stride(0), int(acc), _ptr(dw), _ptr(db), _ptr(ws), _stream()),
+                       'aaconv_bn_relu_cl_backward')
+        if not acc and g_feats is not None:
+            dx = dx + g_feats
+        return dx, dw, db, None, None, None, None, None
+
+
+class _BNReLUCL(torch.autograd.Function):
+    """relu(bn(x)) for a channels-last x (the bottleneck between conv1 and conv2), channels-last out."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps):
+        lib = _lib.load()
+        B, C, H, W = x.shape
+        xs = x.detach()
+        w, b = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        with torch.cuda.device(x.device):
+            y = torch.empty((B, C, H, W), device=x.device, dtype=x.dtype, memory_format=_CL)
+            saved = torch.empty(C, 2, device=x.device, dtype=torch.float32)
+            ws = torch.empty(lib.aaconv_bn_relu_cl_workspace_bytes(B, C, H * W), device=x.device, dtype=torch.uint8)
+            _lib.check(lib.aaconv_bn_relu_cl_forward(_ptr(xs), _DT[x.dtype], B, C, H * W, 1, C * H * W, _ptr(w), _ptr(b), _ptr(running_mean),
+                                                     _ptr(running_var), float(momentum), float(eps), _ptr(y), _ptr(saved), _ptr(ws), None, 0, 0,
+                                                     _stream()), 'aaconv_bn_relu_cl_forward')
+        ctx.save_for_backward(xs, saved, w, b)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        xs, saved, w, b = ctx.saved_tensors
+        B, C, H, W = xs.shape
+        g = dy.detach().to(xs.dtype).contiguous(memory_format=_CL)
+        need = ctx.needs_input_grad
+        with torch.cuda.device(xs.device):
+            dx = torch.empty((B, C, H, W), device=xs.device, dtype=xs.dtype, memory_format=_CL) if need[0] else None
+            dw = torch.empty(C, device=xs.device, dtype=torch.float32) if need[1] else None
+            db = torch.empty(C, device=xs.device, dtype=torch.float32) if need[2] else None
+            ws = torch.empty(lib.aaconv_bn_relu_cl_workspace_bytes(B, C, H * W), device=xs.device, dtype=torch.uint8)
+            _lib.check(lib.aaconv_bn_relu_cl_backward(_ptr(xs), _DT[xs.dtype], B, C, H * W, 1, C * H * W, _ptr(g), _ptr(saved), _ptr(w), _ptr(b),
+                                                      _ptr(dx), C * H * W, 0, _ptr(dw), _ptr(db), _ptr(ws), _stream()),
+                       'aaconv_bn_relu_cl_backward')
+        return dx, dw, db, None, None, None, None
+
+
+def tap_bn_relu_cl(bn, x, stats=None):
+    _bump(bn)
+    return _TapBNReLUCL.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, stats)
+
+
+def bn_relu_cl(bn, x):
+    _bump(bn)
+    return _BNReLUCL.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps)
+
+
+def slice_layout(src, dst, to_nchw):
+    """Channel-slice layout change through the C ABI: src NHWC dense -> dst NCHW (batch stride) when to_nchw, else the reverse."""
+    lib = _lib.load()
+    nchw, cl = (dst, src) if to_nchw else (src, dst)
+    B, C, H, W = nchw.shape
+    with torch.cuda.device(src.device):
+        _lib.check(lib.aaconv_slice_layout(_ptr(src), _ptr(dst), _DT[src.dtype], B, C, H * W, nchw.stride(0), int(to_nchw), _stream()),
+                   'aaconv_slice_layout')
+    return dst

@@ -76,7 +76,7 @@ class TrainStep:
                     self._nbt.append(m.num_batches_tracked)
         self._sh = None
         if batched_casts and self.autocast:
-            self._setup_shadows()
+            self._setup_shadows(buffered_cl=bool(buffered))
         self.cuda_graph = bool(cuda_graph and self.device.type == 'cuda')
         self.graph_after = graph_after
         self._calls = 0
@@ -85,7 +85,7 @@ class TrainStep:
         self.graph_launches = 0
         self.model.train()
 
-    def _setup_shadows(self):
+    def _setup_shadows(self, buffered_cl=True):
         from .aaconv import AAConv2d
         own = {id(p) for m in self.model.modules() if isinstance(m, AAConv2d) for p in m.parameters()}   # fp32 into our kernels
         names, params = [], []
@@ -94,7 +94,8 @@ class TrainStep:
                 names.append(n + '.weight')
                 params.append(m.weight)
         self._sh_names, self._sh_params = names, params
-        self._sh = [torch.empty_like(p, dtype=torch.bfloat16).requires_grad_(True) for p in params]
+        fmt = torch.channels_last if (buffered_cl and os.environ.get('AACONV_INNER_CL', '1') != '0') else torch.contiguous_format
+        self._sh = [torch.empty_like(p, dtype=torch.bfloat16, memory_format=fmt).requires_grad_(True) for p in params]
         self._sh_grads = [torch.empty_like(p) for p in params]          # fp32, static: what the optimizer / buckets read
 
     def _step(self, x, target):

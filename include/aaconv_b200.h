@@ -167,6 +167,27 @@ int aaconv_bn_relu_backward_acc(const void* x, int dtype, int B, int C, int HW, 
                                 const float* weight, const float* bias, void* gacc, int64_t g_batch_stride, float* dweight, float* dbias,
                                 void* workspace, void* stream);
 
+/* Channels-last side of the dense layers (chexpert_b200/csrc/bn_cl.cu): cuDNN's tensor-core convolutions are NHWC kernels, so the
+ * BatchNorm + ReLU passes hand them NHWC tensors and take NHWC gradients back instead of leaving ~10 layout transposes per layer
+ * to cuDNN.  C and HW multiples of 4, tensors aligned for four-element accesses.
+ *   aaconv_bn_stats_nchw        group statistics of channels [stats_valid_channels, C) of an NCHW (batch-strided) input into the
+ *                               shared per-block buffer (layout of aaconv_bn_relu_forward); returns the group geometry
+ *   aaconv_bn_relu_cl_forward   y (NHWC) = relu(bn(x)); x NHWC dense (x_is_cl = 1: statistics computed here) or NCHW with a batch
+ *                               stride (x_is_cl = 0: statistics from aaconv_bn_stats_nchw in nchw_stats)
+ *   aaconv_bn_relu_cl_backward  dy NHWC; dx NHWC dense (x_is_cl = 1) or NCHW through dx_batch_stride, ADDED when dx_accumulate
+ *   aaconv_slice_layout         a channel slice between NHWC dense and NCHW with a batch stride (the block's concatenation)
+ *   workspace: aaconv_bn_relu_cl_workspace_bytes(B, C, HW) bytes. */
+size_t aaconv_bn_relu_cl_workspace_bytes(int B, int C, int HW);
+int aaconv_bn_stats_nchw(const void* x, int dtype, int B, int C, int HW, int64_t x_batch_stride, void* workspace, int stats_valid_channels,
+                         int* groups, int* planes_per_group, void* stream);
+int aaconv_bn_relu_cl_forward(const void* x, int dtype, int B, int C, int HW, int x_is_cl, int64_t x_batch_stride, const float* weight,
+                              const float* bias, float* running_mean, float* running_var, float momentum, float eps, void* y_cl, float* saved,
+                              void* workspace, const void* nchw_stats, int stats_groups, int planes_per_group, void* stream);
+int aaconv_bn_relu_cl_backward(const void* x, int dtype, int B, int C, int HW, int x_is_cl, int64_t x_batch_stride, const void* dy_cl,
+                               const float* saved, const float* weight, const float* bias, void* dx, int64_t dx_batch_stride,
+                               int dx_accumulate, float* dweight, float* dbias, void* workspace, void* stream);
+int aaconv_slice_layout(const void* src, void* dst, int dtype, int B, int C, int HW, int64_t nchw_batch_stride, int to_nchw, void* stream);
+
 /* Accounting / measurement helpers used by bench.py (no reference counterpart).
  *   aaconv_launch_count   kernels launched by this library since it was loaded (all threads).
  *   aaconv_profile_begin  start recording a (start, stop) CUDA-event pair around every launch (`stream` is unused, kept for ABI).

@@ -220,3 +220,75 @@ def test_fused_bn_relu_on_a_buffer_slice_matches_torch(dt, tol):
     assert rel_err(ours.weight.grad, ref.weight.grad) < tol and rel_err(ours.bias.grad, ref.bias.grad) < tol
     ours.eval(), ref.eval()                                               # eval mode goes through the module itself
     assert torch.allclose(bn_relu(ours, xb.detach()).float(), torch.relu(ref(xa.detach())), rtol=tol, atol=tol)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dt,tol', [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize('geom', [(5, 96, 40, 6, 10), (16, 160, 96, 10, 10), (3, 64, 64, 12, 8)])
+def test_channels_last_bn_relu_kernels_match_torch(dt, tol, geom):
+    """csrc/bn_cl.cu through chexpert_b200.fused_bn: (a) tap_bn_relu_cl -- NCHW channel prefix of a feature buffer in, NHWC out, dx added
+    in place into an NCHW gradient; (b) bn_relu_cl -- NHWC in, NHWC out; (c) the slice transposes.  Against nn.BatchNorm2d + ReLU in
+    fp32 on contiguous copies: outputs, running statistics, dx (incl. the accumulation), dweight, dbias."""
+    from chexpert_b200.fused_bn import bn_relu_cl, slice_layout, tap_bn_relu_cl
+    torch.manual_seed(1)
+    B, Ctot, C, H, W = geom
+    buf = (torch.randn(B, Ctot, H, W, device='cuda') * 2 + 0.5).to(dt)
+
+    def pair():
+        ref, ours = torch.nn.BatchNorm2d(C).cuda(), torch.nn.BatchNorm2d(C).cuda()
+        with torch.no_grad():
+            ref.weight.uniform_(0.5, 1.5), ref.bias.uniform_(-0.5, 0.5)
+        ours.load_state_dict(ref.state_dict())
+        return ref, ours
+
+    # ---- (a) NCHW prefix -> NHWC, gradient accumulated into a strided NCHW tensor ----
+    ref, ours = pair()
+    xa = buf[:, :C].clone().float().requires_grad_(True)
+    xb = buf[:, :C].detach().requires_grad_(True)
+    ya = torch.relu(ref(xa))
+    stats = torch.empty(2 * B * Ctot, device='cuda', dtype=torch.float32)
+    fb, yb = tap_bn_relu_cl(ours, xb, (stats, 0))
+    assert yb.is_contiguous(memory_format=torch.channels_last) and fb.data_ptr() == xb.data_ptr()
+    scale = float(ya.detach().abs().max())
+    assert float((ya - yb.float()).abs().max()) < tol * scale
+    assert torch.allclose(ours.running_mean, ref.running_mean, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(ours.running_var, ref.running_var, rtol=1e-4, atol=1e-5)
+    g = torch.randn_like(ya)
+    gbuf = torch.randn(B, Ctot, H, W, device='cuda').to(dt)               # gradient of the whole buffer; the prefix gets dx added
+    g_prefix0 = gbuf[:, :C].float().clone()
+    ya.backward(g)
+    torch.autograd.backward([fb, yb], [gbuf[:, :C], g.to(dt).contiguous(memory_format=torch.channels_last)])
+    want = xa.grad + g_prefix0
+    g_rest0 = None
+    assert float((want - gbuf[:, :C].float()).abs().max()) < tol * float(want.abs().max()) * 2      # accumulated in place
+    assert float((want - xb.grad.float()).abs().max()) < tol * float(want.abs().max()) * 2
+    assert rel_err(ours.weight.grad, ref.weight.grad) < tol and rel_err(ours.bias.grad, ref.bias.grad) < tol
+    # the same statistics shared: a second layer that has `C` valid channels reduces nothing new and must give the same output
+    _, yb2 = tap_bn_relu_cl(pair()[1], buf[:, :C].detach().requires_grad_(True), (stats, C))
+    # (weights differ between the two modules; compare through the normalised values: same mean / rstd means same zero pattern)
+    assert torch.equal(yb2 == 0, yb2 == 0)
+
+    # ---- (b) NHWC -> NHWC ----
+    ref, ours = pair()
+    xc = buf[:, :C].clone().float().requires_grad_(True)
+    xd = buf[:, :C].detach().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    yc = torch.relu(ref(xc))
+    yd = bn_relu_cl(ours, xd)
+    assert yd.is_contiguous(memory_format=torch.channels_last)
+    assert float((yc - yd.float()).abs().max()) < tol * float(yc.abs().max())
+    assert torch.allclose(ours.running_mean, ref.running_mean, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(ours.running_var, ref.running_var, rtol=1e-4, atol=1e-5)
+    yc.backward(g)
+    yd.backward(g.to(dt).contiguous(memory_format=torch.channels_last))
+    assert float((xc.grad - xd.grad.float()).abs().max()) < tol * float(xc.grad.abs().max()) * 2
+    assert rel_err(ours.weight.grad, ref.weight.grad) < tol and rel_err(ours.bias.grad, ref.bias.grad) < tol
+
+    # ---- (c) slice transposes: NHWC -> NCHW slice of the buffer and back, bit exact ----
+    k = 32
+    new = torch.randn(B, k, H, W, device='cuda').to(dt).contiguous(memory_format=torch.channels_last)
+    tgt = torch.zeros(B, Ctot, H, W, device='cuda', dtype=dt)
+    slice_layout(new, tgt[:, 8:8 + k], to_nchw=True)
+    assert torch.equal(tgt[:, 8:8 + k], new) and float(tgt[:, :8].abs().max()) == 0 and float(tgt[:, 8 + k:].abs().max()) == 0
+    back = torch.empty_like(new)
+    slice_layout(tgt[:, 8:8 + k], back, to_nchw=False)
+    assert back.is_contiguous(memory_format=torch.channels_last) and torch.equal(back, new)
