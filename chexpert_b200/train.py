@@ -95,7 +95,10 @@ class TrainStep:
                 params.append(m.weight)
         self._sh_names, self._sh_params = names, params
         fmt = torch.channels_last if (buffered_cl and os.environ.get('AACONV_INNER_CL', '1') != '0') else torch.contiguous_format
-        self._sh = [torch.empty_like(p, dtype=torch.bfloat16, memory_format=fmt).requires_grad_(True) for p in params]
+        # channels-last shadows only for the convolutions inside the dense blocks (their activations are NHWC, csrc/bn_cl.cu); the stem
+        # keeps NCHW weights, or its output would come back channels-last and miss the fused strided BN + ReLU
+        self._sh = [torch.empty_like(p, dtype=torch.bfloat16, memory_format=fmt if 'denseblock' in n else torch.contiguous_format)
+                    .requires_grad_(True) for n, p in zip(names, params)]
         self._sh_grads = [torch.empty_like(p) for p in params]          # fp32, static: what the optimizer / buckets read
 
     def _step(self, x, target):
