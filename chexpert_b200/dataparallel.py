@@ -25,9 +25,16 @@ class GradientBuckets:
     the bucket views -- no per-parameter accumulate kernel (360 small launches per step for aadensenet121, ~1 ms under a CUDA
     graph) at the price of a 50 MB all-reduce that is not hidden (~0.2 ms over NVLink 5 at 8 GPUs)."""
 
-    def __init__(self, module, bucket_mb=25.0, process_group=None, broadcast_from=0, overlap=True):
+    def __init__(self, module, bucket_mb=25.0, process_group=None, broadcast_from=0, overlap=True, grad_sources=None):
+        """``overlap='bucket'``: fresh gradients as with ``overlap=False``, but every bucket is packed (one multi-tensor copy) and
+        all-reduced from ONE hook that fires when the last gradient of the bucket has been computed
+        (``torch.autograd.graph.register_multi_grad_hook``): communication under the rest of backward without the per-parameter
+        accumulate kernels.  ``grad_sources`` maps a parameter to the tensor whose gradient stands in for it (TrainStep's bf16
+        weight shadows): the pack converts to the fp32 bucket on the way."""
         self.group = process_group
-        self.overlap = bool(overlap)
+        self.bucket_hooks = overlap == 'bucket'
+        self.overlap = bool(overlap) and not self.bucket_hooks
+        self._src = dict(grad_sources or {})
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.params = [p for p in module.parameters() if p.requires_grad]
         if not self.params:
@@ -54,6 +61,12 @@ class GradientBuckets:
         self._state = 'finished'  # 'armed' between reset() and finish()
         self._sync = True
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params] if self.overlap else []
+        self._ready = [False] * len(self.buckets)
+        if self.bucket_hooks:
+            import functools
+            for bi, (_, params) in enumerate(self.buckets):
+                srcs = tuple(self._src.get(p, p) for p in params)
+                self._hooks.append(torch.autograd.graph.register_multi_grad_hook(srcs, functools.partial(self._on_bucket, bi), mode='all'))
         self.reset()
 
     def _seal(self, params):
@@ -73,6 +86,9 @@ class GradientBuckets:
         if not self.overlap:                      # fresh gradients from autograd: nothing to zero, nothing to accumulate into
             for p in self.params:
                 p.grad = None
+            self._ready = [False] * len(self.buckets)
+            self._works = []
+            self._next = 0
             self._state = 'armed'
             return
         for flat, _ in self.buckets:
@@ -96,6 +112,38 @@ class GradientBuckets:
                 self._works.append(dist.all_reduce(self.buckets[self._next][0], group=self.group, async_op=True))
             self._next += 1
 
+    def _avg_op(self):
+        return dist.ReduceOp.AVG if (self.world > 1 and dist.get_backend(self.group) == 'nccl') else None
+
+    def _pack(self, bi, grads):
+        """gradients of bucket bi (None = parameter without a gradient on this rank: zeros) -> its flat fp32 buffer"""
+        flat, params = self.buckets[bi]
+        views = [self._view[p] for p in params]
+        have = [(v, g) for v, g in zip(views, grads) if g is not None and g.data_ptr() != v.data_ptr()]
+        for v, g in zip(views, grads):
+            if g is None:
+                v.zero_()
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+
+    def _issue_packed(self):
+        """all-reduce the packed buckets in bucket order 0, 1, 2, ... (identical on every rank)"""
+        avg = self._avg_op()
+        while self._next < len(self.buckets) and self._ready[self._next]:
+            flat = self.buckets[self._next][0]
+            if self.world > 1:
+                self._works.append(dist.all_reduce(flat, op=avg, group=self.group, async_op=True) if avg is not None
+                                   else dist.all_reduce(flat, group=self.group, async_op=True))
+            self._next += 1
+
+    def _on_bucket(self, bi, grads):
+        if not self._sync or self._state != 'armed' or self._ready[bi]:
+            return                                # accumulation window / stray backward: finish() packs from .grad
+        with torch.no_grad():
+            self._pack(bi, grads)
+        self._ready[bi] = True
+        self._issue_packed()
+
     def _on_grad(self, p):
         b = self._bucket_of[p]
         view = self._view[p]
@@ -117,6 +165,24 @@ class GradientBuckets:
         """Wait for the exchange and turn sums into means.  Call once after backward(), before optimizer.step()."""
         if self._state != 'armed':
             raise RuntimeError('GradientBuckets: finish() called twice (or before reset())')
+        if self.bucket_hooks:
+            with torch.no_grad():
+                for bi, (flat, params) in enumerate(self.buckets):      # buckets whose hook did not fire (no gradient at all, no_sync)
+                    if not self._ready[bi]:
+                        self._pack(bi, [self._src.get(p, p).grad for p in params])
+                        self._ready[bi] = True
+                self._issue_packed()
+                for w in self._works:
+                    w.wait()
+                if self.world > 1 and self._avg_op() is None:
+                    for flat, _ in self.buckets:
+                        flat.div_(self.world)
+                for flat, params in self.buckets:
+                    for p in params:
+                        p.grad = self._view[p]
+            self._works = []
+            self._state = 'finished'
+            return
         if not self.overlap:
             avg = dist.ReduceOp.AVG if (self.world > 1 and dist.get_backend(self.group) == 'nccl') else None
             for flat, params in self.buckets:

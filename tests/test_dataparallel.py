@@ -188,12 +188,12 @@ def test_trainstep_nccl_two_ranks_equal_the_full_batch_step(tmp_path):
         assert torch.allclose(a, w, rtol=2e-4, atol=2e-6), float((a - w).abs().max())
 
 
-def _worker_post(rank, world, port, out_dir):
+def _worker_post(rank, world, port, out_dir, mode=False):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     from chexpert_b200.dataparallel import GradientBuckets
     net = _net()
-    gb = GradientBuckets(net, bucket_mb=0.0005, overlap=False)
+    gb = GradientBuckets(net, bucket_mb=0.0005, overlap=mode)
     x, t = _data()
     xs, ts = x.chunk(world)[rank], t.chunk(world)[rank]
     for _ in range(2):
@@ -204,10 +204,12 @@ def _worker_post(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_pack_after_backward_mode_matches_full_batch(tmp_path):
-    """overlap=False (what TrainStep uses on CUDA): fresh gradients, one multi-tensor pack per bucket, averaged all-reduce."""
+@pytest.mark.parametrize('mode', [False, 'bucket'])
+def test_pack_after_backward_mode_matches_full_batch(tmp_path, mode):
+    """overlap=False: fresh gradients, one multi-tensor pack per bucket after backward, averaged all-reduce; overlap='bucket' (what
+    TrainStep uses on CUDA): the same pack + all-reduce issued from one hook per bucket while backward is still running."""
     world = 2
-    mp.spawn(_worker_post, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker_post, args=(world, _free_port(), str(tmp_path), mode), nprocs=world, join=True)
     net = _net()
     x, t = _data()
     nn.functional.binary_cross_entropy_with_logits(net(x), t, reduction='none').sum(1).mean(0).backward()
