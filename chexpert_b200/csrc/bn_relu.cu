@@ -11,11 +11,12 @@
 //                        In a dense block layer i normalises channels [0, c_i) of which [0, c_{i-1}) were already reduced by
 //                        layer i-1 (same data, same statistics): the caller keeps ONE partial buffer per block and passes
 //                        `stats_valid_channels`, so only the layer's 32 new channels are reduced (the pass shrinks ~5x)
-//             bn_apply   grid (C, B): merges the B partials of its channel (fixed order), y = relu(w (x - mean) rstd + b);
-//                        the b = 0 block also writes mean / rstd for backward and updates running_mean / running_var
-//   backward  bn_bwd_red grid (C, B): g = dy * [y > 0], partial (sum g, sum g x^) per plane
-//             bn_bwd_dx  grid (C, B): merges the partials (fixed order), dx = w rstd (g - mean(g) - x^ mean(g x^));
-//                        the b = 0 block writes dweight = sum g x^ and dbias = sum g
+//             bn_apply   grid (C, G): merges the G partials of its channel (fixed order; computes them itself when G == 1),
+//                        y = relu(w (x - mean) rstd + b); the group-0 block also writes mean / rstd for backward and updates
+//                        running_mean / running_var
+//   backward  bn_bwd_red grid (C, G): g = dy * [y > 0], partial (sum g, sum g x^) per group (skipped when G == 1)
+//             bn_bwd_dx  grid (C, G): merges the partials (fixed order), dx = w rstd (g - mean(g) - x^ mean(g x^)), optionally ADDED
+//                        into the gradient of the feature buffer; the group-0 block writes dweight = sum g x^ and dbias = sum g
 // 3 / 5 passes, all reductions in a fixed order (bit-reproducible), x read through its strides, y / dx dense.
 #include <algorithm>
 #include <cstdlib>
