@@ -76,7 +76,10 @@ class GradientBuckets:
         for p in params:
             if p.dtype != torch.float32 or p.device != dev:
                 raise ValueError('GradientBuckets expects fp32 master parameters on one device')
-            self._view[p] = p.grad = flat[off:off + p.numel()].view_as(p)
+            # the view has the parameter's own (dense) strides -- channels-last conv weights included -- so that packing its
+            # gradient is part of one multi-tensor copy instead of a strided copy of its own
+            seg = flat[off:off + p.numel()]
+            self._view[p] = p.grad = seg.view_as(p) if p.is_contiguous() else seg.as_strided(p.shape, p.stride())
             off += p.numel()
             self._bucket_of[p] = len(self.buckets)
         self.buckets.append((flat, params))
